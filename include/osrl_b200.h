@@ -1,0 +1,185 @@
+/*
+ * osrl_b200 -- C ABI of the B200-native OSRL training-step engine (libosrl_b200.so).
+ *
+ * The reference (liuzuxin/OSRL) is pure Python; its "FFI" for the per-step hot path is
+ * the Python surface osrl.algorithms.*Trainer.train_one_step / osrl.common.*Dataset.
+ * Every entry point below names the reference interface it replaces (paths relative to
+ * the reference root).  Plain pointers and sizes only; no torch types.  All functions
+ * return 0 on success or a negative code; osrl_last_error() holds the message
+ * (thread-local).  One engine per (process, GPU); entry points are not re-entrant per
+ * engine.  The library never falls back to the CPU: without a CUDA device
+ * osrl_engine_create fails with OSRL_ERR_CUDA.
+ */
+#ifndef OSRL_B200_H_
+#define OSRL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSRL_ABI_VERSION 1
+
+enum { OSRL_OK = 0, OSRL_ERR_ARG = -1, OSRL_ERR_CUDA = -2, OSRL_ERR_STATE = -3, OSRL_ERR_NCCL = -4,
+       OSRL_ERR_UNSUPPORTED = -5 };
+
+/* algorithm ids: osrl/algorithms/{bc,bcql,cpq,bearl,cdt}.py */
+enum { OSRL_ALGO_BC = 0, OSRL_ALGO_BCQL = 1, OSRL_ALGO_CPQ = 2, OSRL_ALGO_BEARL = 3, OSRL_ALGO_CDT = 4 };
+
+#define OSRL_MAX_HIDDEN 4
+
+/* Constructor + trainer hyper-parameters of one algorithm:
+ *   BC.__init__ bc.py:26-32, BCTrainer.__init__ bc.py:81-98
+ *   BCQL.__init__ bcql.py:44-62, BCQLTrainer.__init__ bcql.py:262-281
+ *   CPQ.__init__ cpq.py:38-54,  CPQTrainer.__init__ cpq.py:272-292
+ *   BEARL.__init__ bearl.py:46-68, BEARLTrainer.__init__ bearl.py:369-387
+ *   CDT.__init__ cdt.py:45-70, CDTTrainer.__init__ cdt.py:291-341
+ * Fields an algorithm does not have are ignored. */
+typedef struct osrl_config {
+  int32_t algo;
+  int32_t obs_dim, act_dim;
+  float max_action;
+  int32_t n_a_hidden, a_hidden[OSRL_MAX_HIDDEN];
+  int32_t n_c_hidden, c_hidden[OSRL_MAX_HIDDEN];
+  int32_t vae_hidden;
+  int32_t sample_action_num;
+  float gamma, tau, phi, lmbda, beta;
+  float pid_kp, pid_ki, pid_kd;
+  int32_t num_q, num_qc;
+  float cost_limit;
+  int32_t episode_len;
+  float qc_scalar;                                            /* CPQ */
+  float mmd_sigma, target_mmd_thresh;                         /* BEAR-Lag */
+  int32_t num_samples_mmd_match, mmd_kernel /*0 gaussian, 1 laplacian*/, start_update_policy_step;
+  float actor_lr, critic_lr, vae_lr, alpha_lr;
+  /* CDT */
+  int32_t seq_len, embedding_dim, num_layers, num_heads;
+  float attention_dropout, residual_dropout, embedding_dropout;
+  int32_t use_rew, use_cost, cost_transform, stochastic;
+  float init_temperature, target_entropy;
+  float learning_rate, weight_decay, adam_beta1, adam_beta2, clip_grad;
+  int32_t lr_warmup_steps;
+  float loss_cost_weight, loss_state_weight;
+  /* engine */
+  int32_t batch_size;  /* rows per rank per step */
+  uint64_t seed;       /* Philox key of the on-device sampler / noise */
+  int32_t world_size, rank;
+} osrl_config;
+
+/* One parameter tensor of model.state_dict() (names/shapes identical to the reference's,
+ * e.g. "critic.q1_nets.0.2.weight"); `ptr` is a device pointer into the engine's arena,
+ * valid until osrl_engine_destroy (NULL from osrl_plan). */
+typedef struct osrl_param_desc {
+  char name[96];
+  int64_t rows, cols;      /* cols == 0: 1-D tensor of `rows` elements */
+  int64_t offset;          /* float offset inside its arena section */
+  int32_t section;         /* 0 trained parameter, 1 target ("*_old") copy, 2 buffer */
+  int32_t group;           /* optimiser group index, -1 if none */
+  float* ptr;
+} osrl_param_desc;
+
+/* Host-side view of a DSRL transition dataset: what TransitionDataset.__init__ receives
+ * (dataset.py:803-820).  `done` may be NULL, then terminals|timeouts is used. */
+typedef struct osrl_dataset_view {
+  int64_t n;
+  const float* observations;      /* [n, obs_dim] */
+  const float* next_observations; /* [n, obs_dim] */
+  const float* actions;           /* [n, act_dim] */
+  const float* rewards;           /* [n] */
+  const float* costs;             /* [n] */
+  const float* done;              /* [n] float or NULL */
+  const uint8_t* terminals;       /* [n] or NULL */
+  const uint8_t* timeouts;        /* [n] or NULL */
+  float reward_scale, cost_scale;
+} osrl_dataset_view;
+
+/* One collated transition minibatch = the positional arguments of
+ * BCQLTrainer.train_one_step (bcql.py:283-284); BC uses observations+actions only
+ * (bc.py:103).  Row-major float32; `on_host` != 0 means host pointers (copied H2D on the
+ * given stream inside the call), else device pointers. */
+typedef struct osrl_batch {
+  int32_t rows;
+  int32_t on_host;
+  const float* observations;
+  const float* next_observations;
+  const float* actions;
+  const float* rewards;
+  const float* costs;
+  const float* done;
+} osrl_batch;
+
+/* Noise replay: raw standard-normal draws in the order the reference consumes them
+ * (SURVEY.md Appendix B).  Slot names/sizes come from osrl_noise_layout.  NULL slots (or a
+ * NULL osrl_noise) are generated on the device with Philox4x32-10. */
+#define OSRL_MAX_NOISE 8
+typedef struct osrl_noise {
+  int32_t on_host;
+  const float* slot[OSRL_MAX_NOISE];
+} osrl_noise;
+
+typedef struct osrl_engine osrl_engine;
+
+int osrl_abi_version(void);
+const char* osrl_last_error(void);
+
+/* Parameter plan without touching CUDA (names, shapes, offsets). */
+int osrl_plan(const osrl_config* cfg, osrl_param_desc* out, int cap, int* n);
+
+/* Replaces <Algo>.__init__ + <Algo>Trainer.__init__ + setup_optimizers.  Parameters start
+ * at zero; fill them through the osrl_param_table pointers (the Python shim copies the
+ * reference-order torch initialisation in), then call osrl_sync_targets (deepcopy of
+ * actor/critic/cost_critic, bcql.py:100-105). */
+int osrl_engine_create(const osrl_config* cfg, int device, osrl_engine** out);
+void osrl_engine_destroy(osrl_engine* e);
+int osrl_param_table(osrl_engine* e, osrl_param_desc* out, int cap, int* n);
+int osrl_param_set(osrl_engine* e, int index, const float* host, int64_t count);
+int osrl_param_get(osrl_engine* e, int index, float* host, int64_t count);
+int osrl_sync_targets(osrl_engine* e);
+
+/* Replaces TransitionDataset.__init__ (dataset.py:803-820): packs the dataset once into
+ * HBM as rows [obs | next_obs | act | r*reward_scale | c*cost_scale | done]. */
+int osrl_buffer_upload(osrl_engine* e, const osrl_dataset_view* view);
+/* Replaces TransitionDataset.__prepare_sample + collate (dataset.py:832-842): gathers
+ * `n` rows by index into six device/host outputs (bit-exact row copies). */
+int osrl_gather(osrl_engine* e, const int64_t* idx, int n, int idx_on_host, osrl_batch* out /* writable ptrs */,
+                void* stream);
+
+/* Replaces <Algo>Trainer.train_one_step (bc.py:103-109, bcql.py:283-306, cpq.py:294-313,
+ * bearl.py:389-412): all sub-updates + Polyak for one minibatch, no host sync. */
+int osrl_step(osrl_engine* e, const osrl_batch* batch, const osrl_noise* noise, void* stream);
+/* k steps with minibatches drawn on the device from the resident dataset (replaces the loop
+ * body train_bcql.py:142-148 including DataLoader draw and .to(device)). */
+int osrl_steps(osrl_engine* e, int k, void* stream);
+
+/* Stats of the most recent step, in the order of osrl_stat_names (logger.store keys,
+ * bcql.py:131,154,178,205-207).  Synchronises the stream. */
+int osrl_stat_names(osrl_engine* e, const char** names, int cap, int* n);
+int osrl_stats(osrl_engine* e, float* host_out, int cap, int* n, void* stream);
+
+/* Scalar training state the reference keeps outside state_dict (PID error_old /
+ * error_integral net.py:373-374, log_alpha cpq.py:93, step counters). */
+int osrl_scalar_names(osrl_engine* e, const char** names, int cap, int* n);
+int osrl_scalars_get(osrl_engine* e, double* host_out, int cap, int* n);
+int osrl_scalars_set(osrl_engine* e, const double* host_in, int n);
+
+/* Noise slots (name, float count) of this engine's algorithm at its batch size. */
+int osrl_noise_layout(osrl_engine* e, const char** names, int64_t* counts, int cap, int* n);
+/* Debug/parity: the sampled indices and the noise the last osrl_steps() step consumed. */
+int osrl_last_indices(osrl_engine* e, int64_t* host_out, int cap);
+int osrl_last_noise(osrl_engine* e, int slot, float* host_out, int64_t cap);
+
+/* Number of kernels launched by this engine so far / per step. */
+int64_t osrl_launch_count(osrl_engine* e);
+int osrl_launches_per_step(osrl_engine* e);
+
+/* Data-parallel: one engine per rank; gradients are all-reduced (NCCL, fp32 sum, /world)
+ * before each optimiser update.  id is an ncclUniqueId made by rank 0. */
+int osrl_comm_unique_id(char out[128]);
+int osrl_comm_init(osrl_engine* e, const char id[128], int world_size, int rank);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSRL_B200_H_ */

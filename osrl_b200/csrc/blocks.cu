@@ -1,0 +1,122 @@
+// Reusable program blocks shared by BCQ-Lag / CPQ / BEAR-Lag: VAE update, VAE decode,
+// plain-MLP forward/backward.
+#include "engine.h"
+
+namespace osrl {
+
+static void flush(Engine& e, Program& p, std::vector<GemmTask> tasks) { emit_gemm(e, p, tasks); }
+
+// VAE.decode trunk (net.py:337-339): dec_in [rows, o+L] -> relu d1 -> relu d2 -> d3.
+// mode 0: out = act_lim * tanh(d3)    mode 1: out = raw d3 (BEAR decode_multiple, net.py:353)
+void emit_vae_decode(Engine& e, Program& p, const float* W, const float* dec_in, int rows, float* h1, float* h2,
+                     float* out, int ldout, int mode) {
+  const VaeLay& v = e.plan.vae;
+  const int V = v.d1.out, ldin = v.d1.in;
+  flush(e, p, {task_fwd(dec_in, ldin, rows, W, v.d1, h1, V, ACT_RELU)});
+  flush(e, p, {task_fwd(h1, V, rows, W, v.d2, h2, V, ACT_RELU)});
+  if (mode == 0) flush(e, p, {task_fwd(h2, V, rows, W, v.d3, out, ldout, ACT_TANH, e.plan.cfg.max_action)});
+  else flush(e, p, {task_fwd(h2, V, rows, W, v.d3, out, ldout, ACT_NONE)});
+}
+
+// vae_loss + backward + Adam (bcql.py:122-132 == cpq.py:125-135 == bearl.py:144-154).
+// sa = [obs|act] [B, o+a]; dec_in [B, o+L] has its obs columns already filled.
+void emit_vae_update(Engine& e, Program& p, const float* sa, float* dec_in, const float* eps, const float* act,
+                     int stat_index) {
+  const osrl_config& c = e.plan.cfg;
+  const VaeLay& v = e.plan.vae;
+  const int B = e.B, o = c.obs_dim, a = c.act_dim, L = 2 * a, V = c.vae_hidden;
+  const float iw = e.inv_world();
+  float* h1 = e.ws((size_t)B * V); float* h2 = e.ws((size_t)B * V);
+  float* ml = e.ws((size_t)B * 2 * L); float* sd = e.ws((size_t)B * L);
+  float* g1 = e.ws((size_t)B * V); float* g2 = e.ws((size_t)B * V);
+  float* u = e.ws((size_t)B * a); float* dpre3 = e.ws((size_t)B * a);
+  float* dg2 = e.ws((size_t)B * V); float* dg1 = e.ws((size_t)B * V);
+  float* dz = e.ws((size_t)B * L); float* dml = e.ws((size_t)B * 2 * L);
+  float* dh2 = e.ws((size_t)B * V); float* dh1 = e.ws((size_t)B * V);
+  float* stat = e.stats + stat_index;
+  Engine* ep = &e;
+  // encoder
+  flush(e, p, {task_fwd(sa, o + a, B, e.P, v.e1, h1, V, ACT_RELU)});
+  flush(e, p, {task_fwd(h1, V, B, e.P, v.e2, h2, V, ACT_RELU)});
+  flush(e, p, {task_fwd(h2, V, B, e.P, v.heads, ml, 2 * L, ACT_NONE)});
+  p.ops.push_back([=](cudaStream_t s) {
+    k_vae_reparam<<<(B * L + 255) / 256, 256, 0, s>>>(ml, eps, B, L, sd, dec_in, o + L, o);
+    ep->launches++;
+  });
+  p.kernels++;
+  // decoder
+  flush(e, p, {task_fwd(dec_in, o + L, B, e.P, v.d1, g1, V, ACT_RELU)});
+  flush(e, p, {task_fwd(g1, V, B, e.P, v.d2, g2, V, ACT_RELU)});
+  flush(e, p, {task_fwd(g2, V, B, e.P, v.d3, u, a, ACT_TANH, c.max_action)});
+  const float lim = c.max_action, beta = c.beta;
+  p.ops.push_back([=](cudaStream_t s) {
+    k_vae_loss<<<1, 1024, 0, s>>>(u, act, B, a, lim, ml, sd, L, beta, dpre3, stat, iw);
+    ep->launches++;
+  });
+  p.kernels++;
+  // backward
+  flush(e, p, {task_wgrad(dpre3, a, g2, V, B, e.G, v.d3), task_dgrad(dpre3, a, B, e.P, v.d3, dg2, V, g2, V, ACT_RELU)});
+  flush(e, p, {task_wgrad(dg2, V, g1, V, B, e.G, v.d2), task_dgrad(dg2, V, B, e.P, v.d2, dg1, V, g1, V, ACT_RELU)});
+  flush(e, p, {task_wgrad(dg1, V, dec_in, o + L, B, e.G, v.d1),
+               task_dgrad(dg1, V, B, e.P, v.d1, dz, L, nullptr, 0, 0, o, L)});
+  p.ops.push_back([=](cudaStream_t s) {
+    k_vae_reparam_bwd<<<(B * L + 255) / 256, 256, 0, s>>>(dz, L, 0, ml, sd, eps, B, L, beta, dml, iw);
+    ep->launches++;
+  });
+  p.kernels++;
+  flush(e, p, {task_wgrad(dml, 2 * L, h2, V, B, e.G, v.heads),
+               task_dgrad(dml, 2 * L, B, e.P, v.heads, dh2, V, h2, V, ACT_RELU)});
+  flush(e, p, {task_wgrad(dh2, V, h1, V, B, e.G, v.e2), task_dgrad(dh2, V, B, e.P, v.e2, dh1, V, h1, V, ACT_RELU)});
+  flush(e, p, {task_wgrad(dh1, V, sa, o + a, B, e.G, v.e1)});
+  const Group& g = e.plan.groups[e.plan.g_vae];
+  emit_allreduce(e, p, e.G + g.begin, g.end - g.begin);
+  emit_adam(e, p, e.plan.g_vae, g.begin, g.end, false);
+}
+
+// Plain MLP forward: hidden activation `hact` on all but the last layer; the last layer's task is
+// returned un-emitted so the caller can attach its epilogue (tanh/scale/resid/clamp/aux) and merge it
+// into a launch.  h[j] = output of layer j (j < n-1).
+GemmTask mlp_fwd_hidden(Engine& e, Program& p, const float* W, const MlpLay& m, const float* X, int ldx, int rows,
+                        int hact, std::vector<float*>& h, float* out, int ldout) {
+  const int n = (int)m.L.size();
+  const float* cur = X;
+  int ld = ldx;
+  h.clear();
+  for (int j = 0; j + 1 < n; ++j) {
+    float* y = e.ws((size_t)rows * m.L[j].out);
+    emit_gemm(e, p, {task_fwd(cur, ld, rows, W, m.L[j], y, m.L[j].out, hact)});
+    h.push_back(y);
+    cur = y;
+    ld = m.L[j].out;
+  }
+  return task_fwd(cur, ld, rows, W, m.L[n - 1], out, ldout, ACT_NONE);
+}
+
+// Plain MLP backward from dpre (gradient wrt the last layer's pre-activation) [rows, out].
+void mlp_bwd(Engine& e, Program& p, const float* W, float* Gsec, const MlpLay& m, const float* X, int ldx, int rows,
+             int hact, const std::vector<float*>& h, const float* dpre) {
+  const int n = (int)m.L.size();
+  const float* dy = dpre;
+  int lddy = m.L[n - 1].out;
+  for (int j = n - 1; j >= 0; --j) {
+    const float* xin = j == 0 ? X : h[j - 1];
+    const int ldin = j == 0 ? ldx : m.L[j - 1].out;
+    std::vector<GemmTask> ts{task_wgrad(dy, lddy, xin, ldin, rows, Gsec, m.L[j])};
+    float* dx = nullptr;
+    if (j > 0) {
+      dx = e.ws((size_t)rows * m.L[j].in);
+      ts.push_back(task_dgrad(dy, lddy, rows, W, m.L[j], dx, m.L[j].in, h[j - 1], m.L[j - 1].out, hact));
+    }
+    emit_gemm(e, p, ts);
+    dy = dx;
+    lddy = m.L[j].in;
+  }
+}
+
+}  // namespace osrl
+
+namespace osrl {
+void emit_stages(Engine& e, Program& p, std::vector<Stage>& st) {
+  for (auto& s : st) emit_gemm(e, p, s.tasks);
+}
+}  // namespace osrl

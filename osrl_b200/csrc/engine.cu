@@ -1,0 +1,737 @@
+// Engine runtime + C ABI (see include/osrl_b200.h).
+#include "engine.h"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstring>
+
+namespace osrl {
+
+thread_local std::string g_err;
+
+// ------------------------------------------------------------------ memory helpers
+float* Engine::ws(size_t n) {
+  if (n == 0) n = 1;
+  void* p = nullptr;
+  OSRL_CUDA(cudaMalloc(&p, (n + 4) * sizeof(float)));
+  OSRL_CUDA(cudaMemset(p, 0, (n + 4) * sizeof(float)));
+  allocs.push_back(p);
+  return (float*)p;
+}
+template <class Tt>
+Tt* Engine::upload(const std::vector<Tt>& v) {
+  void* p = nullptr;
+  OSRL_CUDA(cudaMalloc(&p, std::max<size_t>(1, v.size()) * sizeof(Tt)));
+  if (!v.empty()) OSRL_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(Tt), cudaMemcpyHostToDevice));
+  allocs.push_back(p);
+  return (Tt*)p;
+}
+template GemmTask* Engine::upload<GemmTask>(const std::vector<GemmTask>&);
+template CopyTask* Engine::upload<CopyTask>(const std::vector<CopyTask>&);
+template NoiseSlot* Engine::upload<NoiseSlot>(const std::vector<NoiseSlot>&);
+template AdamGroupCfg* Engine::upload<AdamGroupCfg>(const std::vector<AdamGroupCfg>&);
+
+// ------------------------------------------------------------------ GEMM task constructors
+static GemmTask blank_task() {
+  GemmTask t;
+  memset(&t, 0, sizeof(t));
+  t.scale = 1.f;
+  return t;
+}
+GemmTask task_fwd(const float* X, int ldx, int rows, const float* W, const Lin& l, float* Y, int ldy, int act,
+                  float scale) {
+  GemmTask t = blank_task();
+  t.A = X; t.lda = ldx; t.a_kc = 1;
+  t.B = W + l.w; t.ldb = l.in; t.b_kc = 1;
+  t.C = Y; t.ldc = ldy;
+  t.M = rows; t.N = l.out; t.K = l.in;
+  t.bias = W + l.b;
+  t.act = act; t.scale = scale;
+  return t;
+}
+GemmTask task_dgrad(const float* dY, int lddy, int rows, const float* W, const Lin& l, float* dX, int lddx,
+                    const float* Hprev, int ldh, int dact, int col0, int ncols) {
+  GemmTask t = blank_task();
+  if (ncols < 0) ncols = l.in - col0;
+  t.A = dY; t.lda = lddy; t.a_kc = 1;
+  t.B = W + l.w + col0; t.ldb = l.in; t.b_kc = 0;
+  t.C = dX; t.ldc = lddx;
+  t.M = rows; t.N = ncols; t.K = l.out;
+  t.dact = dact; t.dact_src = Hprev; t.ld_dact = ldh;
+  return t;
+}
+GemmTask task_wgrad(const float* dY, int lddy, const float* X, int ldx, int rows, float* Gsec, const Lin& l) {
+  GemmTask t = blank_task();
+  t.A = dY; t.lda = lddy; t.a_kc = 0;
+  t.B = X; t.ldb = ldx; t.b_kc = 0;
+  t.C = Gsec + l.w; t.ldc = l.in;
+  t.M = l.out; t.N = l.in; t.K = rows;
+  t.colsum = Gsec + l.b;
+  return t;
+}
+
+// ------------------------------------------------------------------ launch emitters
+template <int BM, int BN, int TM, int TN>
+static void launch_gemm(const GemmTask* d, int ntasks, int tiles, cudaStream_t s) {
+  k_gemm_tasks<BM, BN, TM, TN><<<tiles, (BM / TM) * (BN / TN), 0, s>>>(d, ntasks);
+}
+static int count_tiles(std::vector<GemmTask>& ts, int BM, int BN, bool assign) {
+  int tot = 0;
+  for (auto& t : ts) {
+    const int tm = (t.M + BM - 1) / BM, tn = (t.N + BN - 1) / BN;
+    if (assign) { t.tile0 = tot; t.tiles_n = tn; }
+    tot += tm * tn;
+  }
+  return tot;
+}
+void emit_gemm(Engine& e, Program& p, const std::vector<GemmTask>& tasks_in) {
+  if (tasks_in.empty()) return;
+  std::vector<GemmTask> tasks = tasks_in;
+  for (auto& t : tasks) OSRL_REQUIRE(t.M > 0 && t.N > 0 && t.K > 0, "empty gemm task");
+  // largest tile shape that still yields >= ~1 wave-fraction of CTAs (148 SMs)
+  int cfg = 2;
+  if (count_tiles(tasks, 128, 64, false) >= 120) cfg = 0;
+  else if (count_tiles(tasks, 64, 64, false) >= 96) cfg = 1;
+  static const int bm[3] = {128, 64, 32}, bn[3] = {64, 64, 32};
+  const int tiles = count_tiles(tasks, bm[cfg], bn[cfg], true);
+  GemmTask* d = e.upload(tasks);
+  const int nt = (int)tasks.size();
+  Engine* ep = &e;
+  p.ops.push_back([=](cudaStream_t s) {
+    if (cfg == 0) launch_gemm<128, 64, 8, 4>(d, nt, tiles, s);
+    else if (cfg == 1) launch_gemm<64, 64, 4, 4>(d, nt, tiles, s);
+    else launch_gemm<32, 32, 2, 2>(d, nt, tiles, s);
+    ep->launches++;
+  });
+  p.kernels++;
+}
+CopyTask copy_cols(float* dst, int ldd, int dcol0, const float* src, int lds, int scol0, int rows, int cols, int row_div,
+                   int row_mod) {
+  CopyTask t;
+  memset(&t, 0, sizeof(t));
+  t.dst = dst + dcol0; t.ldd = ldd;
+  t.src = src + scol0; t.lds = lds;
+  t.rows = rows; t.cols = cols;
+  t.row_div = row_div; t.row_mod = row_mod;
+  t.mul = 1.f;
+  return t;
+}
+void emit_copy(Engine& e, Program& p, const std::vector<CopyTask>& tasks) {
+  if (tasks.empty()) return;
+  CopyTask* d = e.upload(tasks);
+  long long mx = 1;
+  for (auto& t : tasks) mx = std::max(mx, (long long)t.rows * t.cols);
+  const int bx = (int)std::min<long long>((mx + 255) / 256, 148 * 4);
+  const int ny = (int)tasks.size();
+  Engine* ep = &e;
+  p.ops.push_back([=](cudaStream_t s) {
+    k_copy_tasks<<<dim3(bx, ny), 256, 0, s>>>(d);
+    ep->launches++;
+  });
+  p.kernels++;
+}
+void emit_adam(Engine& e, Program& p, int group, int64_t begin, int64_t end, bool polyak) {
+  const Group& g = e.plan.groups[group];
+  const int64_t n4 = (end - begin) / 4;
+  const int blocks = (int)std::min<int64_t>((n4 + 255) / 256, 148 * 8);
+  Engine* ep = &e;
+  const float tau = e.plan.cfg.tau;
+  p.ops.push_back([=](cudaStream_t s) {
+    k_adam<<<blocks, 256, 0, s>>>(ep->P + begin, ep->G + begin, ep->M + begin, ep->V + begin, ep->T + begin, n4, ep->ds,
+                                  group, g.beta1, g.beta2, g.eps, g.wd, tau, polyak ? 1 : 0, 1.f, nullptr);
+    ep->launches++;
+  });
+  p.kernels++;
+}
+
+// ------------------------------------------------------------------ NCCL (dlopen'ed; only needed when world > 1)
+namespace nccl {
+struct Uid { char internal[128]; };  // ncclUniqueId
+typedef int (*AllReduce_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*CommDestroy_t)(void*);
+typedef const char* (*GetErrorString_t)(int);
+static void* lib = nullptr;
+static int (*GetUniqueId)(Uid*) = nullptr;
+static int (*CommInitRank)(void**, int, Uid, int) = nullptr;
+static AllReduce_t AllReduce = nullptr;
+static CommDestroy_t CommDestroy = nullptr;
+static GetErrorString_t GetErrorString = nullptr;
+static void load() {
+  if (lib) return;
+  const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+  for (int i = 0; names[i] && !lib; ++i) lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) throw Err(OSRL_ERR_NCCL, std::string("cannot dlopen libnccl.so.2: ") + dlerror());
+  GetUniqueId = (int (*)(Uid*))dlsym(lib, "ncclGetUniqueId");
+  CommInitRank = (int (*)(void**, int, Uid, int))dlsym(lib, "ncclCommInitRank");
+  AllReduce = (AllReduce_t)dlsym(lib, "ncclAllReduce");
+  CommDestroy = (CommDestroy_t)dlsym(lib, "ncclCommDestroy");
+  GetErrorString = (GetErrorString_t)dlsym(lib, "ncclGetErrorString");
+  if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) throw Err(OSRL_ERR_NCCL, "libnccl lacks required symbols");
+}
+static void check(int r, const char* what) {
+  if (r != 0) throw Err(OSRL_ERR_NCCL, std::string(what) + ": " + (GetErrorString ? GetErrorString(r) : "nccl error"));
+}
+}  // namespace nccl
+
+void emit_allreduce(Engine& e, Program& p, float* buf, int64_t count) {
+  if (e.world <= 1) return;
+  Engine* ep = &e;
+  p.ops.push_back([=](cudaStream_t s) {
+    if (!ep->comm) throw Err(OSRL_ERR_STATE, "world_size > 1 but osrl_comm_init was not called");
+    nccl::check(nccl::AllReduce(buf, buf, (size_t)count, /*ncclFloat32*/ 7, /*ncclSum*/ 0, ep->comm, s), "ncclAllReduce");
+  });
+}
+
+// ------------------------------------------------------------------ ensemble helpers
+EnsBuf ens_alloc(Engine& e, const EnsLay& l, int rows) {
+  EnsBuf b;
+  b.rows = rows;
+  for (int hw : l.h) b.h.push_back(e.ws((size_t)rows * l.n * hw));
+  b.q = e.ws((size_t)rows * l.n);
+  return b;
+}
+void ens_fwd(std::vector<Stage>& st, const EnsLay& l, const float* W, const float* X, int ldx, int rows, EnsBuf& buf) {
+  const int nh = (int)l.h.size();
+  OSRL_REQUIRE((int)st.size() >= nh + 1, "ens_fwd: not enough stages");
+  st[0].tasks.push_back(task_fwd(X, ldx, rows, W, l.first, buf.h[0], l.n * l.h[0], ACT_RELU));
+  for (int k = 1; k < nh; ++k)
+    for (int i = 0; i < l.n; ++i)
+      st[k].tasks.push_back(task_fwd(buf.h[k - 1] + (size_t)i * l.h[k - 1], l.n * l.h[k - 1], rows, W, l.mid[k - 1][i],
+                                     buf.h[k] + (size_t)i * l.h[k], l.n * l.h[k], ACT_RELU));
+  for (int i = 0; i < l.n; ++i) {
+    Lin last;
+    last.in = l.h.back(); last.out = 1;
+    last.w = l.w_last + (int64_t)i * l.h.back();
+    last.b = l.b_last + i;
+    st[nh].tasks.push_back(task_fwd(buf.h[nh - 1] + (size_t)i * l.h.back(), l.n * l.h.back(), rows, W, last,
+                                    buf.q + i, l.n, ACT_NONE));
+  }
+}
+void ens_bwd(std::vector<Stage>& st, const EnsLay& l, const float* W, float* Gsec, const float* X, int ldx, int rows,
+             const EnsBuf& act, EnsBuf& grad, const float* dq, float* dX, int lddx, int xcol0, int xcols) {
+  const int nh = (int)l.h.size();
+  OSRL_REQUIRE((int)st.size() >= nh + 1, "ens_bwd: not enough stages");
+  // last layer (1 unit): dH = dq (x) w_last, masked by relu'(H)
+  for (int i = 0; i < l.n; ++i) {
+    Lin last;
+    last.in = l.h.back(); last.out = 1;
+    last.w = l.w_last + (int64_t)i * l.h.back();
+    last.b = l.b_last + i;
+    const int ldh = l.n * l.h.back();
+    if (Gsec) st[0].tasks.push_back(task_wgrad(dq + i, l.n, act.h[nh - 1] + (size_t)i * l.h.back(), ldh, rows, Gsec, last));
+    st[0].tasks.push_back(task_dgrad(dq + i, l.n, rows, W, last, grad.h[nh - 1] + (size_t)i * l.h.back(), ldh,
+                                     act.h[nh - 1] + (size_t)i * l.h.back(), ldh, ACT_RELU));
+  }
+  for (int k = nh - 1; k >= 1; --k) {
+    const int s = nh - k;
+    for (int i = 0; i < l.n; ++i) {
+      const Lin& m = l.mid[k - 1][i];
+      const int ldo = l.n * l.h[k], ldi = l.n * l.h[k - 1];
+      if (Gsec)
+        st[s].tasks.push_back(task_wgrad(grad.h[k] + (size_t)i * l.h[k], ldo, act.h[k - 1] + (size_t)i * l.h[k - 1], ldi,
+                                         rows, Gsec, m));
+      st[s].tasks.push_back(task_dgrad(grad.h[k] + (size_t)i * l.h[k], ldo, rows, W, m,
+                                       grad.h[k - 1] + (size_t)i * l.h[k - 1], ldi,
+                                       act.h[k - 1] + (size_t)i * l.h[k - 1], ldi, ACT_RELU));
+    }
+  }
+  if (Gsec) st[nh].tasks.push_back(task_wgrad(grad.h[0], l.n * l.h[0], X, ldx, rows, Gsec, l.first));
+  if (dX) st[nh].tasks.push_back(task_dgrad(grad.h[0], l.n * l.h[0], rows, W, l.first, dX, lddx, nullptr, 0, 0, xcol0, xcols));
+}
+
+// ------------------------------------------------------------------ engine life cycle
+static void free_all(Engine* e) {
+  if (e->g_body) cudaGraphExecDestroy(e->g_body);
+  if (e->g_sampled) cudaGraphExecDestroy(e->g_sampled);
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  for (void* p : e->allocs) cudaFree(p);
+  if (e->comm && nccl::CommDestroy) nccl::CommDestroy(e->comm);
+}
+
+static void build_program(Engine& e) {
+  switch (e.plan.cfg.algo) {
+    case OSRL_ALGO_BC: build_bc(e); break;
+    case OSRL_ALGO_BCQL: build_bcql(e); break;
+    case OSRL_ALGO_CPQ: build_cpq(e); break;
+    case OSRL_ALGO_BEARL: build_bearl(e); break;
+    default: throw Err(OSRL_ERR_UNSUPPORTED, "algorithm not supported");
+  }
+}
+
+static Engine* create(const osrl_config& cfg, int device) {
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    throw Err(OSRL_ERR_CUDA, std::string("no CUDA device available (osrl_b200 has no CPU fallback): ") +
+                                 cudaGetErrorString(ce));
+  OSRL_REQUIRE(device >= 0 && device < ndev, "bad device ordinal");
+  OSRL_REQUIRE(cfg.batch_size > 0, "batch_size must be positive");
+  OSRL_CUDA(cudaSetDevice(device));
+  Engine* e = new Engine();
+  try {
+    e->plan = make_plan(cfg);
+    e->device = device;
+    e->world = cfg.world_size;
+    e->rank = cfg.rank;
+    e->B = cfg.batch_size;
+    const size_t n = (size_t)e->plan.nP;
+    e->P = e->ws(n); e->T = e->ws(n); e->G = e->ws(n); e->M = e->ws(n); e->V = e->ws(n);
+    void* dsp = nullptr;
+    OSRL_CUDA(cudaMalloc(&dsp, sizeof(DevState)));
+    OSRL_CUDA(cudaMemset(dsp, 0, sizeof(DevState)));
+    e->allocs.push_back(dsp);
+    e->ds = (DevState*)dsp;
+    if (cfg.algo == OSRL_ALGO_CDT) {
+      DevState h;
+      memset(&h, 0, sizeof(h));
+      h.log_temperature = logf(cfg.init_temperature);
+      OSRL_CUDA(cudaMemcpy(e->ds, &h, sizeof(h), cudaMemcpyHostToDevice));
+    }
+    std::vector<AdamGroupCfg> gc;
+    for (auto& g : e->plan.groups) gc.push_back({g.lr, g.beta1, g.beta2, g.warmup});
+    e->d_groups = e->upload(gc);
+    const int o = cfg.obs_dim, a = cfg.act_dim, B = e->B;
+    e->b_obs = e->ws((size_t)B * o); e->b_nobs = e->ws((size_t)B * o); e->b_act = e->ws((size_t)B * a);
+    e->b_rew = e->ws(B); e->b_cost = e->ws(B); e->b_done = e->ws(B);
+    e->b_idx = (int64_t*)e->ws((size_t)B * 2);
+    std::vector<NoiseSlot> slots;
+    int si = 0;
+    for (auto& ns : e->plan.noise) {
+      float* buf = e->ws((size_t)ns.second);
+      e->noise_buf.push_back(buf);
+      slots.push_back({buf, (long long)ns.second, si++, 1});
+    }
+    e->d_slots_all = e->upload(slots);
+    e->d_slots_dyn = e->upload(slots);
+    e->stats = e->ws(std::max<size_t>(16, e->plan.stat_names.size()));
+    OSRL_CUDA(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+    build_program(*e);
+    OSRL_CUDA(cudaDeviceSynchronize());
+  } catch (...) {
+    free_all(e);
+    delete e;
+    throw;
+  }
+  return e;
+}
+
+static void run_ops(Engine& e, const Program& p, cudaStream_t s) {
+  for (auto& op : p.ops) op(s);
+}
+static void prologue(Engine& e, cudaStream_t s) {
+  k_prologue<<<1, 32, 0, s>>>(e.ds, e.d_groups, (int)e.plan.groups.size());
+  e.launches++;
+}
+static void epilogue(Engine& e, cudaStream_t s) {
+  k_epilogue<<<1, 32, 0, s>>>(e.ds);
+  e.launches++;
+}
+static void sample_front(Engine& e, cudaStream_t s) {
+  const osrl_config& c = e.plan.cfg;
+  const int warps_per_block = 8;
+  k_sample_gather<<<(e.B + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, s>>>(
+      e.ds_rows, e.ds_n, e.ds_stride, c.obs_dim, c.act_dim, nullptr, c.seed, e.ds, (uint32_t)e.rank, e.B, e.b_obs,
+      e.b_nobs, e.b_act, e.b_rew, e.b_cost, e.b_done, e.b_idx);
+  e.launches++;
+  if (!e.noise_buf.empty()) {
+    k_noise_fill<<<dim3(64, (unsigned)e.noise_buf.size()), 256, 0, s>>>(e.d_slots_all, (int)e.noise_buf.size(), c.seed,
+                                                                         e.ds, (uint32_t)e.rank);
+    e.launches++;
+  }
+}
+
+static cudaGraphExec_t capture(Engine& e, bool sampled) {
+  cudaStream_t s = e.cap_stream;
+  const int64_t before = e.launches;
+  OSRL_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  cudaGraph_t g = nullptr;
+  try {
+    if (sampled) sample_front(e, s);
+    prologue(e, s);
+    run_ops(e, e.body, s);
+    epilogue(e, s);
+  } catch (...) {
+    cudaStreamEndCapture(s, &g);
+    if (g) cudaGraphDestroy(g);
+    e.launches = before;
+    throw;
+  }
+  OSRL_CUDA(cudaStreamEndCapture(s, &g));
+  e.launches = before;  // capture does not execute
+  cudaGraphExec_t x = nullptr;
+  cudaError_t ce = cudaGraphInstantiate(&x, g, 0);
+  cudaGraphDestroy(g);
+  if (ce != cudaSuccess) throw Err(OSRL_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+  return x;
+}
+static int kernels_per_step(const Engine& e, bool sampled) {
+  return e.body.kernels + 2 + (sampled ? (1 + (e.noise_buf.empty() ? 0 : 1)) : 0);
+}
+
+}  // namespace osrl
+
+// ====================================================================== C ABI
+using namespace osrl;
+
+#define OSRL_TRY try {
+#define OSRL_CATCH                                   \
+  }                                                  \
+  catch (const Err& x) {                             \
+    g_err = x.what();                                \
+    return x.code;                                   \
+  }                                                  \
+  catch (const std::exception& x) {                  \
+    g_err = x.what();                                \
+    return OSRL_ERR_STATE;                           \
+  }                                                  \
+  return OSRL_OK;
+
+struct osrl_engine {
+  Engine* e;
+};
+
+static void fill_desc(const ParamEntry& pe, osrl_param_desc* d, const Engine* e) {
+  memset(d, 0, sizeof(*d));
+  strncpy(d->name, pe.name.c_str(), sizeof(d->name) - 1);
+  d->rows = pe.rows; d->cols = pe.cols; d->offset = pe.offset; d->section = pe.section; d->group = pe.group;
+  d->ptr = e ? ((pe.section == 1 ? e->T : e->P) + pe.offset) : nullptr;
+}
+
+extern "C" {
+
+int osrl_abi_version(void) { return OSRL_ABI_VERSION; }
+const char* osrl_last_error(void) { return g_err.c_str(); }
+
+int osrl_plan(const osrl_config* cfg, osrl_param_desc* out, int cap, int* n) {
+  OSRL_TRY
+  OSRL_REQUIRE(cfg && n, "null argument");
+  osrl_config c = *cfg;
+  if (c.batch_size <= 0) c.batch_size = 1;
+  if (c.world_size <= 0) c.world_size = 1;
+  Plan p = make_plan(c);
+  *n = (int)p.table.size();
+  if (out)
+    for (int i = 0; i < *n && i < cap; ++i) fill_desc(p.table[i], &out[i], nullptr);
+  OSRL_CATCH
+}
+
+int osrl_engine_create(const osrl_config* cfg, int device, osrl_engine** out) {
+  OSRL_TRY
+  OSRL_REQUIRE(cfg && out, "null argument");
+  osrl_config c = *cfg;
+  if (c.world_size <= 0) { c.world_size = 1; c.rank = 0; }
+  Engine* e = create(c, device);
+  *out = new osrl_engine{e};
+  OSRL_CATCH
+}
+
+void osrl_engine_destroy(osrl_engine* h) {
+  if (!h) return;
+  cudaSetDevice(h->e->device);
+  cudaDeviceSynchronize();
+  free_all(h->e);
+  delete h->e;
+  delete h;
+}
+
+int osrl_param_table(osrl_engine* h, osrl_param_desc* out, int cap, int* n) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && n, "null argument");
+  *n = (int)h->e->plan.table.size();
+  if (out)
+    for (int i = 0; i < *n && i < cap; ++i) fill_desc(h->e->plan.table[i], &out[i], h->e);
+  OSRL_CATCH
+}
+
+static int64_t entry_count(const ParamEntry& pe) { return pe.rows * (pe.cols ? pe.cols : 1); }
+
+int osrl_param_set(osrl_engine* h, int index, const float* host, int64_t count) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && host, "null argument");
+  Engine& e = *h->e;
+  OSRL_REQUIRE(index >= 0 && index < (int)e.plan.table.size(), "bad parameter index");
+  const ParamEntry& pe = e.plan.table[index];
+  OSRL_REQUIRE(count == entry_count(pe), "parameter element count mismatch");
+  OSRL_CUDA(cudaSetDevice(e.device));
+  OSRL_CUDA(cudaMemcpy((pe.section == 1 ? e.T : e.P) + pe.offset, host, count * sizeof(float), cudaMemcpyHostToDevice));
+  OSRL_CATCH
+}
+int osrl_param_get(osrl_engine* h, int index, float* host, int64_t count) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && host, "null argument");
+  Engine& e = *h->e;
+  OSRL_REQUIRE(index >= 0 && index < (int)e.plan.table.size(), "bad parameter index");
+  const ParamEntry& pe = e.plan.table[index];
+  OSRL_REQUIRE(count == entry_count(pe), "parameter element count mismatch");
+  OSRL_CUDA(cudaSetDevice(e.device));
+  OSRL_CUDA(cudaDeviceSynchronize());
+  OSRL_CUDA(cudaMemcpy(host, (pe.section == 1 ? e.T : e.P) + pe.offset, count * sizeof(float), cudaMemcpyDeviceToHost));
+  OSRL_CATCH
+}
+int osrl_sync_targets(osrl_engine* h) {
+  OSRL_TRY
+  OSRL_REQUIRE(h, "null argument");
+  Engine& e = *h->e;
+  OSRL_CUDA(cudaSetDevice(e.device));
+  for (auto& g : e.plan.groups)
+    if (g.has_target)
+      OSRL_CUDA(cudaMemcpy(e.T + g.begin, e.P + g.begin, (g.end - g.begin) * sizeof(float), cudaMemcpyDeviceToDevice));
+  OSRL_CATCH
+}
+
+int osrl_buffer_upload(osrl_engine* h, const osrl_dataset_view* v) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && v, "null argument");
+  Engine& e = *h->e;
+  OSRL_REQUIRE(v->n > 0 && v->observations && v->next_observations && v->actions && v->rewards && v->costs,
+               "dataset view incomplete");
+  OSRL_REQUIRE(v->done || (v->terminals && v->timeouts), "need done or terminals+timeouts");
+  OSRL_CUDA(cudaSetDevice(e.device));
+  const int o = e.plan.cfg.obs_dim, a = e.plan.cfg.act_dim;
+  const int stride = (2 * o + a + 3 + 3) / 4 * 4;
+  std::vector<float> packed((size_t)v->n * stride, 0.f);
+  const float rs = v->reward_scale, cs = v->cost_scale;
+  for (int64_t i = 0; i < v->n; ++i) {
+    float* r = packed.data() + (size_t)i * stride;
+    memcpy(r, v->observations + (size_t)i * o, o * sizeof(float));
+    memcpy(r + o, v->next_observations + (size_t)i * o, o * sizeof(float));
+    memcpy(r + 2 * o, v->actions + (size_t)i * a, a * sizeof(float));
+    r[2 * o + a] = v->rewards[i] * rs;   // dataset.py:836 (float32 * weak python float -> float32)
+    r[2 * o + a + 1] = v->costs[i] * cs; // dataset.py:837
+    r[2 * o + a + 2] = v->done ? v->done[i] : ((v->terminals[i] || v->timeouts[i]) ? 1.f : 0.f);  // :815-816
+  }
+  void* d = nullptr;
+  OSRL_CUDA(cudaMalloc(&d, packed.size() * sizeof(float)));
+  e.allocs.push_back(d);
+  OSRL_CUDA(cudaMemcpy(d, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+  e.ds_rows = (float*)d;
+  e.ds_n = v->n;
+  e.ds_stride = stride;
+  if (e.g_sampled) { cudaGraphExecDestroy(e.g_sampled); e.g_sampled = nullptr; }
+  OSRL_CATCH
+}
+
+int osrl_gather(osrl_engine* h, const int64_t* idx, int n, int idx_on_host, osrl_batch* out, void* stream) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && idx && out, "null argument");
+  Engine& e = *h->e;
+  OSRL_REQUIRE(e.ds_rows, "no dataset uploaded");
+  OSRL_REQUIRE(n >= 0, "negative count");
+  if (n == 0) return OSRL_OK;
+  OSRL_CUDA(cudaSetDevice(e.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int o = e.plan.cfg.obs_dim, a = e.plan.cfg.act_dim;
+  const int64_t* didx = idx;
+  void* tmp_idx = nullptr;
+  if (idx_on_host) {
+    for (int i = 0; i < n; ++i) OSRL_REQUIRE(idx[i] >= 0 && idx[i] < e.ds_n, "index out of range");
+    OSRL_CUDA(cudaMalloc(&tmp_idx, (size_t)n * sizeof(int64_t)));
+    OSRL_CUDA(cudaMemcpyAsync(tmp_idx, idx, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    didx = (const int64_t*)tmp_idx;
+  }
+  float* dst[6] = {(float*)out->observations, (float*)out->next_observations, (float*)out->actions,
+                   (float*)out->rewards,      (float*)out->costs,             (float*)out->done};
+  const size_t cnt[6] = {(size_t)n * o, (size_t)n * o, (size_t)n * a, (size_t)n, (size_t)n, (size_t)n};
+  float* dev[6];
+  void* tmp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  for (int k = 0; k < 6; ++k) {
+    if (!dst[k]) { dev[k] = nullptr; continue; }
+    if (out->on_host) { OSRL_CUDA(cudaMalloc(&tmp[k], cnt[k] * sizeof(float))); dev[k] = (float*)tmp[k]; }
+    else dev[k] = dst[k];
+  }
+  k_sample_gather<<<(n + 7) / 8, 256, 0, s>>>(e.ds_rows, e.ds_n, e.ds_stride, o, a, didx, 0, e.ds, 0, n, dev[0], dev[1],
+                                              dev[2], dev[3], dev[4], dev[5], nullptr);
+  e.launches++;
+  OSRL_CUDA(cudaGetLastError());
+  if (out->on_host)
+    for (int k = 0; k < 6; ++k)
+      if (dst[k]) OSRL_CUDA(cudaMemcpyAsync(dst[k], dev[k], cnt[k] * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (out->on_host || tmp_idx) OSRL_CUDA(cudaStreamSynchronize(s));
+  for (int k = 0; k < 6; ++k)
+    if (tmp[k]) cudaFree(tmp[k]);
+  if (tmp_idx) cudaFree(tmp_idx);
+  OSRL_CATCH
+}
+
+int osrl_step(osrl_engine* h, const osrl_batch* b, const osrl_noise* nz, void* stream) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && b, "null argument");
+  Engine& e = *h->e;
+  OSRL_REQUIRE(b->rows == e.B, "batch rows != engine batch_size");
+  OSRL_REQUIRE(b->observations && b->actions, "observations/actions required");
+  const bool bc = e.plan.cfg.algo == OSRL_ALGO_BC;
+  if (!bc) OSRL_REQUIRE(b->next_observations && b->rewards && b->costs && b->done, "incomplete transition batch");
+  OSRL_CUDA(cudaSetDevice(e.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int o = e.plan.cfg.obs_dim, a = e.plan.cfg.act_dim, B = e.B;
+  const cudaMemcpyKind kind = b->on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  OSRL_CUDA(cudaMemcpyAsync(e.b_obs, b->observations, (size_t)B * o * sizeof(float), kind, s));
+  OSRL_CUDA(cudaMemcpyAsync(e.b_act, b->actions, (size_t)B * a * sizeof(float), kind, s));
+  if (!bc) {
+    OSRL_CUDA(cudaMemcpyAsync(e.b_nobs, b->next_observations, (size_t)B * o * sizeof(float), kind, s));
+    OSRL_CUDA(cudaMemcpyAsync(e.b_rew, b->rewards, (size_t)B * sizeof(float), kind, s));
+    OSRL_CUDA(cudaMemcpyAsync(e.b_cost, b->costs, (size_t)B * sizeof(float), kind, s));
+    OSRL_CUDA(cudaMemcpyAsync(e.b_done, b->done, (size_t)B * sizeof(float), kind, s));
+  }
+  const int ns = (int)e.noise_buf.size();
+  if (ns) {
+    int provided = 0;
+    for (int i = 0; i < ns; ++i) {
+      const float* src = nz ? nz->slot[i] : nullptr;
+      if (!src) continue;
+      ++provided;
+      OSRL_CUDA(cudaMemcpyAsync(e.noise_buf[i], src, (size_t)e.plan.noise[i].second * sizeof(float),
+                                nz->on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+    }
+    if (provided < ns) {
+      const NoiseSlot* slots = e.d_slots_all;  // every slot generated on the device
+      if (provided > 0) {                      // mixed: only the missing slots
+        std::vector<NoiseSlot> dyn;
+        for (int i = 0; i < ns; ++i)
+          dyn.push_back({e.noise_buf[i], (long long)e.plan.noise[i].second, i, (nz && nz->slot[i]) ? 0 : 1});
+        OSRL_CUDA(cudaMemcpyAsync(e.d_slots_dyn, dyn.data(), dyn.size() * sizeof(NoiseSlot), cudaMemcpyHostToDevice, s));
+        OSRL_CUDA(cudaStreamSynchronize(s));
+        slots = e.d_slots_dyn;
+      }
+      k_noise_fill<<<dim3(64, (unsigned)ns), 256, 0, s>>>(slots, ns, e.plan.cfg.seed, e.ds, (uint32_t)e.rank);
+      e.launches++;
+    }
+  }
+  if (!e.g_body) e.g_body = capture(e, false);
+  OSRL_CUDA(cudaGraphLaunch(e.g_body, s));
+  e.launches += kernels_per_step(e, false);
+  OSRL_CATCH
+}
+
+int osrl_steps(osrl_engine* h, int k, void* stream) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && k >= 0, "bad argument");
+  Engine& e = *h->e;
+  OSRL_REQUIRE(e.ds_rows, "osrl_steps needs a resident dataset (osrl_buffer_upload)");
+  OSRL_CUDA(cudaSetDevice(e.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!e.g_sampled) e.g_sampled = capture(e, true);
+  for (int i = 0; i < k; ++i) OSRL_CUDA(cudaGraphLaunch(e.g_sampled, s));
+  e.launches += (int64_t)k * kernels_per_step(e, true);
+  OSRL_CATCH
+}
+
+int osrl_stat_names(osrl_engine* h, const char** names, int cap, int* n) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && n, "null argument");
+  *n = (int)h->e->plan.stat_names.size();
+  if (names)
+    for (int i = 0; i < *n && i < cap; ++i) names[i] = h->e->plan.stat_names[i].c_str();
+  OSRL_CATCH
+}
+int osrl_stats(osrl_engine* h, float* host_out, int cap, int* n, void* stream) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && host_out && n, "null argument");
+  Engine& e = *h->e;
+  *n = (int)e.plan.stat_names.size();
+  OSRL_REQUIRE(cap >= *n, "stats buffer too small");
+  OSRL_CUDA(cudaSetDevice(e.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  OSRL_CUDA(cudaMemcpyAsync(host_out, e.stats, *n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  OSRL_CUDA(cudaStreamSynchronize(s));
+  OSRL_CATCH
+}
+
+static const char* kScalarNames[] = {"step", "pid_error_old", "pid_error_integral", "log_alpha", "n_train_steps",
+                                     "log_temperature", "adam_t0", "adam_t1", "adam_t2", "adam_t3"};
+int osrl_scalar_names(osrl_engine* h, const char** names, int cap, int* n) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && n, "null argument");
+  *n = 10;
+  if (names)
+    for (int i = 0; i < *n && i < cap; ++i) names[i] = kScalarNames[i];
+  OSRL_CATCH
+}
+int osrl_scalars_get(osrl_engine* h, double* out, int cap, int* n) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && out && n && cap >= 10, "bad argument");
+  Engine& e = *h->e;
+  OSRL_CUDA(cudaSetDevice(e.device));
+  OSRL_CUDA(cudaDeviceSynchronize());
+  DevState d;
+  OSRL_CUDA(cudaMemcpy(&d, e.ds, sizeof(d), cudaMemcpyDeviceToHost));
+  *n = 10;
+  out[0] = (double)d.step; out[1] = d.pid_e_old; out[2] = d.pid_e_int; out[3] = d.log_alpha;
+  out[4] = d.n_train_steps; out[5] = d.log_temperature;
+  for (int i = 0; i < 4; ++i) out[6 + i] = d.adam_t[i];
+  OSRL_CATCH
+}
+int osrl_scalars_set(osrl_engine* h, const double* in, int n) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && in && n == 10, "bad argument");
+  Engine& e = *h->e;
+  OSRL_CUDA(cudaSetDevice(e.device));
+  OSRL_CUDA(cudaDeviceSynchronize());
+  DevState d;
+  OSRL_CUDA(cudaMemcpy(&d, e.ds, sizeof(d), cudaMemcpyDeviceToHost));
+  d.step = (unsigned long long)in[0]; d.pid_e_old = (float)in[1]; d.pid_e_int = (float)in[2];
+  d.log_alpha = (float)in[3]; d.n_train_steps = (int)in[4]; d.log_temperature = (float)in[5];
+  for (int i = 0; i < 4; ++i) d.adam_t[i] = (int)in[6 + i];
+  OSRL_CUDA(cudaMemcpy(e.ds, &d, sizeof(d), cudaMemcpyHostToDevice));
+  OSRL_CATCH
+}
+
+int osrl_noise_layout(osrl_engine* h, const char** names, int64_t* counts, int cap, int* n) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && n, "null argument");
+  *n = (int)h->e->plan.noise.size();
+  for (int i = 0; i < *n && i < cap; ++i) {
+    if (names) names[i] = h->e->plan.noise[i].first.c_str();
+    if (counts) counts[i] = h->e->plan.noise[i].second;
+  }
+  OSRL_CATCH
+}
+int osrl_last_indices(osrl_engine* h, int64_t* host_out, int cap) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && host_out && cap >= h->e->B, "bad argument");
+  Engine& e = *h->e;
+  OSRL_CUDA(cudaSetDevice(e.device));
+  OSRL_CUDA(cudaDeviceSynchronize());
+  OSRL_CUDA(cudaMemcpy(host_out, e.b_idx, (size_t)e.B * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  OSRL_CATCH
+}
+int osrl_last_noise(osrl_engine* h, int slot, float* host_out, int64_t cap) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && host_out, "null argument");
+  Engine& e = *h->e;
+  OSRL_REQUIRE(slot >= 0 && slot < (int)e.noise_buf.size(), "bad noise slot");
+  OSRL_REQUIRE(cap >= e.plan.noise[slot].second, "noise buffer too small");
+  OSRL_CUDA(cudaSetDevice(e.device));
+  OSRL_CUDA(cudaDeviceSynchronize());
+  OSRL_CUDA(cudaMemcpy(host_out, e.noise_buf[slot], (size_t)e.plan.noise[slot].second * sizeof(float),
+                       cudaMemcpyDeviceToHost));
+  OSRL_CATCH
+}
+
+int64_t osrl_launch_count(osrl_engine* h) { return h ? h->e->launches : 0; }
+int osrl_launches_per_step(osrl_engine* h) { return h ? kernels_per_step(*h->e, true) : 0; }
+
+int osrl_comm_unique_id(char out[128]) {
+  OSRL_TRY
+  OSRL_REQUIRE(out, "null argument");
+  nccl::load();
+  nccl::Uid id;
+  nccl::check(nccl::GetUniqueId(&id), "ncclGetUniqueId");
+  memcpy(out, id.internal, 128);
+  OSRL_CATCH
+}
+int osrl_comm_init(osrl_engine* h, const char id[128], int world_size, int rank) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && id, "null argument");
+  Engine& e = *h->e;
+  OSRL_REQUIRE(world_size == e.world && rank == e.rank, "world_size/rank differ from the engine config");
+  OSRL_CUDA(cudaSetDevice(e.device));
+  nccl::load();
+  nccl::Uid u;
+  memcpy(u.internal, id, 128);
+  nccl::check(nccl::CommInitRank(&e.comm, world_size, u, rank), "ncclCommInitRank");
+  OSRL_CATCH
+}
+
+}  // extern "C"

@@ -1,0 +1,171 @@
+// Engine internals shared by the per-algorithm program builders (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/osrl_b200.h"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace osrl {
+
+struct Err : std::runtime_error {
+  int code;
+  Err(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+#define OSRL_CUDA(x)                                                                                   \
+  do {                                                                                                 \
+    cudaError_t e_ = (x);                                                                              \
+    if (e_ != cudaSuccess)                                                                             \
+      throw ::osrl::Err(OSRL_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ + ":" + \
+                                           std::to_string(__LINE__));                                  \
+  } while (0)
+#define OSRL_REQUIRE(c, msg)                                   \
+  do {                                                         \
+    if (!(c)) throw ::osrl::Err(OSRL_ERR_ARG, std::string(msg)); \
+  } while (0)
+
+// ------------------------------------------------------------------ parameter layout (pure CPU)
+struct Lin {  // one nn.Linear: weight [out, in] row-major at w, bias [out] at b (float offsets in a section)
+  int64_t w = 0, b = 0;
+  int in = 0, out = 0;
+};
+struct MlpLay { std::vector<Lin> L; };
+// An ensemble of n identical ReLU MLPs in -> h[0] -> ... -> 1 (net.py:208-287), stored layer-major:
+// first layer of all nets stacked [n*h0, in]; middle layers block-diagonal; last layers stacked [n, h_last].
+struct EnsLay {
+  int n = 0, in = 0;
+  std::vector<int> h;
+  Lin first;                          // out = n*h[0]
+  std::vector<std::vector<Lin>> mid;  // mid[l-1][net] : h[l-1] -> h[l]
+  int64_t w_last = 0, b_last = 0;     // [n, h.back()], [n]
+};
+struct VaeLay { Lin e1, e2, heads /*[2L, V]: mean rows then log_std rows*/, d1, d2, d3; };
+struct SqActorLay { MlpLay trunk; Lin heads; /*[2a, H]: mu rows then log_std rows*/ };
+
+struct ParamEntry {
+  std::string name;
+  int64_t rows, cols, offset;
+  int section, group;
+};
+struct Group {
+  std::string name;
+  int64_t begin = 0, end = 0;
+  float lr = 0.f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f, wd = 0.f;
+  int warmup = 0;
+  bool has_target = false;
+};
+
+struct Plan {
+  osrl_config cfg{};
+  std::vector<ParamEntry> table;  // in the reference's state_dict order
+  std::vector<Group> groups;
+  int64_t nP = 0;
+  // layouts (which ones are used depends on cfg.algo)
+  MlpLay mlp_actor;       // BC actor / BCQL perturbation actor
+  SqActorLay sq_actor;    // CPQ / BEAR-Lag
+  EnsLay critic, cost_critic;
+  VaeLay vae;
+  int g_actor = -1, g_critic = -1, g_cost = -1, g_vae = -1;
+  double qc_thres = 0.0, q_thres = 0.0;
+  std::vector<std::string> stat_names;
+  std::vector<std::pair<std::string, int64_t>> noise;  // slot name, floats per step
+};
+Plan make_plan(const osrl_config& cfg);
+
+// ------------------------------------------------------------------ runtime
+using Op = std::function<void(cudaStream_t)>;
+
+struct Engine;
+struct Program {
+  std::vector<Op> ops;
+  int kernels = 0;
+};
+
+struct Engine {
+  Plan plan;
+  int device = 0;
+  float *P = nullptr, *T = nullptr, *G = nullptr, *M = nullptr, *V = nullptr;
+  DevState* ds = nullptr;
+  AdamGroupCfg* d_groups = nullptr;
+  // staging minibatch (device)
+  int B = 0;
+  float *b_obs = nullptr, *b_nobs = nullptr, *b_act = nullptr, *b_rew = nullptr, *b_cost = nullptr, *b_done = nullptr;
+  int64_t* b_idx = nullptr;
+  // noise slots
+  std::vector<float*> noise_buf;
+  NoiseSlot *d_slots_all = nullptr, *d_slots_dyn = nullptr;
+  // resident dataset
+  float* ds_rows = nullptr;
+  int64_t ds_n = 0;
+  int ds_stride = 0;
+  // program + graphs
+  Program body;
+  cudaGraphExec_t g_body = nullptr, g_sampled = nullptr;
+  cudaStream_t cap_stream = nullptr;
+  float* stats = nullptr;
+  std::vector<void*> allocs;
+  int64_t launches = 0;
+  // data parallel
+  void* comm = nullptr;
+  int world = 1, rank = 0;
+
+  float* ws(size_t n);  // zero-initialised device workspace
+  template <class Tt> Tt* upload(const std::vector<Tt>& v);
+  float inv_world() const { return 1.f / (float)world; }
+};
+
+// program-building helpers (engine.cu)
+struct Stage {
+  std::vector<GemmTask> tasks;
+};
+GemmTask task_fwd(const float* X, int ldx, int rows, const float* W, const Lin& l, float* Y, int ldy, int act,
+                  float scale = 1.f);
+GemmTask task_dgrad(const float* dY, int lddy, int rows, const float* W, const Lin& l, float* dX, int lddx,
+                    const float* Hprev, int ldh, int dact, int col0 = 0, int ncols = -1);
+GemmTask task_wgrad(const float* dY, int lddy, const float* X, int ldx, int rows, float* Gsec, const Lin& l);
+void emit_gemm(Engine& e, Program& p, const std::vector<GemmTask>& tasks);
+void emit_copy(Engine& e, Program& p, const std::vector<CopyTask>& tasks);
+void emit_adam(Engine& e, Program& p, int group, int64_t begin, int64_t end, bool polyak);
+void emit_allreduce(Engine& e, Program& p, float* buf, int64_t count);
+CopyTask copy_cols(float* dst, int ldd, int dcol0, const float* src, int lds, int scol0, int rows, int cols,
+                   int row_div = 1, int row_mod = 1 << 30);
+
+struct EnsBuf {
+  int rows = 0;
+  std::vector<float*> h;  // h[l] [rows, n*H_l]
+  float* q = nullptr;     // [rows, n]
+};
+EnsBuf ens_alloc(Engine& e, const EnsLay& l, int rows);
+// forward: appends to stages[0..nh] (nh+1 stages)
+void ens_fwd(std::vector<Stage>& st, const EnsLay& l, const float* W, const float* X, int ldx, int rows, EnsBuf& buf);
+// backward: stages[0] = last layer ... stages[nh] = first layer.  Gsec == nullptr: input-gradient only.
+// dX (optional) receives d loss / d X[:, xcol0 : xcol0+xcols].
+void ens_bwd(std::vector<Stage>& st, const EnsLay& l, const float* W, float* Gsec, const float* X, int ldx, int rows,
+             const EnsBuf& act, EnsBuf& grad, const float* dq, float* dX, int lddx, int xcol0, int xcols);
+
+struct MlpBuf {
+  int rows = 0;
+  std::vector<float*> h;  // outputs of every layer
+};
+// blocks.cu
+void emit_vae_decode(Engine& e, Program& p, const float* W, const float* dec_in, int rows, float* h1, float* h2,
+                     float* out, int ldout, int mode);
+void emit_vae_update(Engine& e, Program& p, const float* sa, float* dec_in, const float* eps, const float* act,
+                     int stat_index);
+GemmTask mlp_fwd_hidden(Engine& e, Program& p, const float* W, const MlpLay& m, const float* X, int ldx, int rows,
+                        int hact, std::vector<float*>& h, float* out, int ldout);
+void mlp_bwd(Engine& e, Program& p, const float* W, float* Gsec, const MlpLay& m, const float* X, int ldx, int rows,
+             int hact, const std::vector<float*>& h, const float* dpre);
+void emit_stages(Engine& e, Program& p, std::vector<Stage>& st);
+
+void build_bc(Engine& e);
+void build_bcql(Engine& e);
+void build_cpq(Engine& e);
+void build_bearl(Engine& e);
+
+}  // namespace osrl

@@ -1,0 +1,409 @@
+// Elementwise / reduction / sampling kernels of the OSRL step (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace osrl {
+
+// ------------------------------------------------------------------ device-resident scalar state
+#define OSRL_MAX_GROUPS 8
+struct DevState {
+  unsigned long long step;            // completed steps (Philox counter word)
+  int adam_t[OSRL_MAX_GROUPS];        // per-group Adam step count
+  float adam_lr[OSRL_MAX_GROUPS];     // lr used for the current step (after schedule)
+  float adam_step_size[OSRL_MAX_GROUPS];  // lr / (1 - beta1^t)
+  float adam_bc2_sqrt[OSRL_MAX_GROUPS];   // sqrt(1 - beta2^t)
+  float pid_e_old, pid_e_int;         // LagrangianPIDController state (net.py:373-374)
+  float log_alpha;                    // CPQ / BEAR dual variable (cpq.py:93, bearl.py:112)
+  int n_train_steps;                  // BEAR policy-update gate (bearl.py:249)
+  float log_temperature;              // CDT (cdt.py:144)
+  float temp_m, temp_v;               // Adam state of log_temperature
+  float scratch[16];
+};
+
+// ------------------------------------------------------------------ Philox4x32-10
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)M0 * c[0];
+    const uint64_t p1 = (uint64_t)M1 * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+    const uint32_t n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += W0; k1 += W1;
+  }
+}
+
+enum { STREAM_INDEX = 1, STREAM_NOISE0 = 16 };
+
+// minibatch index draw: idx_i = floor(u32 * N / 2^32), u32 = philox(ctr = (i, step, STREAM_INDEX, rank))[0]
+__host__ __device__ __forceinline__ int64_t draw_index(uint64_t seed, uint64_t step, uint32_t rank, uint32_t i,
+                                                       int64_t n) {
+  uint32_t c[4] = {i, (uint32_t)step, (uint32_t)STREAM_INDEX | ((uint32_t)(step >> 32) << 8), rank};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  return (int64_t)(((uint64_t)c[0] * (uint64_t)n) >> 32);
+}
+
+// ------------------------------------------------------------------ block reduction (deterministic)
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// all threads get the block total; blockDim.x multiple of 32, <= 1024
+__device__ __forceinline__ float block_sum(float v, float* sh /*[33]*/) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    float x = (l < (int)(blockDim.x >> 5)) ? sh[l] : 0.f;
+    x = warp_sum(x);
+    if (l == 0) sh[32] = x;
+  }
+  __syncthreads();
+  return sh[32];
+}
+
+// ------------------------------------------------------------------ step prologue: counters + Adam scalars
+struct AdamGroupCfg {
+  float lr, beta1, beta2;
+  int warmup;  // >0: lr * min((t)/warmup, 1) with t = step count after increment (LambdaLR, cdt.py:327-330)
+};
+static __global__ void k_prologue(DevState* ds, const AdamGroupCfg* g, int ngroups) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (int i = 0; i < ngroups; ++i) {
+    const int t = ds->adam_t[i] + 1;
+    ds->adam_t[i] = t;
+    double lr = (double)g[i].lr;
+    if (g[i].warmup > 0) {
+      double f = (double)t / (double)g[i].warmup;
+      lr = lr * (f < 1.0 ? f : 1.0);
+    }
+    const double bc1 = 1.0 - pow((double)g[i].beta1, (double)t);
+    const double bc2 = 1.0 - pow((double)g[i].beta2, (double)t);
+    ds->adam_lr[i] = (float)lr;
+    ds->adam_step_size[i] = (float)(lr / bc1);
+    ds->adam_bc2_sqrt[i] = (float)sqrt(bc2);
+  }
+}
+static __global__ void k_epilogue(DevState* ds) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) ds->step += 1ull;
+}
+
+// ------------------------------------------------------------------ Adam (+ Polyak target) over a flat range
+// torch.optim.Adam single-tensor semantics (bias-corrected, eps after sqrt); optional decoupled
+// weight decay (AdamW) and global-norm clip factor; optional fused Polyak update of the target copy
+// (bcql.py:114-120) -- valid because no later sub-update of the same step reads that target.
+static __global__ void k_adam(float* __restrict__ P, const float* __restrict__ G, float* __restrict__ Mm,
+                       float* __restrict__ Vv, float* __restrict__ T, int64_t n4, const DevState* ds, int group,
+                       float beta1, float beta2, float eps, float weight_decay, float tau, int polyak,
+                       float grad_mul, const float* clip_coef) {
+  const float step_size = ds->adam_step_size[group];
+  const float bc2s = ds->adam_bc2_sqrt[group];
+  const float lr = ds->adam_lr[group];
+  const float gm = clip_coef ? grad_mul * (*clip_coef) : grad_mul;
+  const float w1 = 1.f - beta1, w2 = 1.f - beta2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 p = reinterpret_cast<float4*>(P)[i];
+    float4 g = reinterpret_cast<const float4*>(G)[i];
+    float4 m = reinterpret_cast<float4*>(Mm)[i];
+    float4 v = reinterpret_cast<float4*>(Vv)[i];
+    float pp[4] = {p.x, p.y, p.z, p.w}, gg[4] = {g.x, g.y, g.z, g.w};
+    float mm[4] = {m.x, m.y, m.z, m.w}, vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gk = gg[k] * gm;
+      if (weight_decay != 0.f) pp[k] = pp[k] * (1.f - lr * weight_decay);
+      mm[k] = fmaf(w1, gk - mm[k], mm[k]);
+      vv[k] = vv[k] * beta2 + (w2 * gk) * gk;
+      const float denom = sqrtf(vv[k]) / bc2s + eps;
+      pp[k] = pp[k] + (-step_size * mm[k]) / denom;
+    }
+    reinterpret_cast<float4*>(P)[i] = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    reinterpret_cast<float4*>(Mm)[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    reinterpret_cast<float4*>(Vv)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    if (polyak) {
+      float4 t = reinterpret_cast<float4*>(T)[i];
+      t.x = tau * pp[0] + (1.f - tau) * t.x;
+      t.y = tau * pp[1] + (1.f - tau) * t.y;
+      t.z = tau * pp[2] + (1.f - tau) * t.z;
+      t.w = tau * pp[3] + (1.f - tau) * t.w;
+      reinterpret_cast<float4*>(T)[i] = t;
+    }
+  }
+}
+
+static __global__ void k_polyak(const float* __restrict__ P, float* __restrict__ T, int64_t n4, float tau) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 p = reinterpret_cast<const float4*>(P)[i];
+    float4 t = reinterpret_cast<float4*>(T)[i];
+    t.x = tau * p.x + (1.f - tau) * t.x;
+    t.y = tau * p.y + (1.f - tau) * t.y;
+    t.z = tau * p.z + (1.f - tau) * t.z;
+    t.w = tau * p.w + (1.f - tau) * t.w;
+    reinterpret_cast<float4*>(T)[i] = t;
+  }
+}
+
+// ------------------------------------------------------------------ noise: raw N(0,1) via Philox + Box-Muller
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+  const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float r = sqrtf(-2.0f * logf(u1));
+  float s, c;
+  sincosf(6.283185307179586f * u2, &s, &c);
+  z0 = r * c;
+  z1 = r * s;
+}
+struct NoiseSlot { float* dst; long long count; int stream; int enabled; };
+static __global__ void k_noise_fill(const NoiseSlot* slots, int nslots, uint64_t seed, const DevState* ds, uint32_t rank) {
+  const NoiseSlot s = slots[blockIdx.y];
+  if (!s.enabled) return;
+  const uint64_t step = ds->step;
+  const long long n4 = (s.count + 3) / 4;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {
+    uint32_t c[4] = {(uint32_t)q, (uint32_t)step,
+                     (uint32_t)(STREAM_NOISE0 + s.stream) | ((uint32_t)(step >> 32) << 8), rank};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    float z[4];
+    box_muller(c[0], c[1], z[0], z[1]);
+    box_muller(c[2], c[3], z[2], z[3]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (q * 4 + k < s.count) s.dst[q * 4 + k] = z[k];
+  }
+}
+
+// ------------------------------------------------------------------ resident dataset: sample + gather
+// Packed row: [obs(o) | next_obs(o) | act(a) | r | c | done | pad] ; stride multiple of 4 floats.
+// Replaces TransitionDataset.__iter__/__prepare_sample + collate + .to(device)
+// (dataset.py:832-847, train_bcql.py:143-146).  One warp per sampled row.
+static __global__ void k_sample_gather(const float* __restrict__ ds_rows, int64_t n, int stride, int o, int a,
+                                const int64_t* __restrict__ idx_in, uint64_t seed, const DevState* st, uint32_t rank,
+                                int rows, float* obs, float* nobs, float* act, float* rew, float* cost, float* done,
+                                int64_t* idx_out) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= rows) return;
+  int64_t idx;
+  if (idx_in) idx = idx_in[w];
+  else idx = draw_index(seed, st->step, rank, (uint32_t)w, n);
+  if (idx_out && lane == 0) idx_out[w] = idx;
+  const float* __restrict__ row = ds_rows + idx * (int64_t)stride;
+  for (int c = lane; c < o; c += 32) {
+    if (obs) obs[(size_t)w * o + c] = row[c];
+    if (nobs) nobs[(size_t)w * o + c] = row[o + c];
+  }
+  for (int c = lane; c < a; c += 32)
+    if (act) act[(size_t)w * a + c] = row[2 * o + c];
+  if (lane == 0) {
+    if (rew) rew[w] = row[2 * o + a];
+    if (cost) cost[w] = row[2 * o + a + 1];
+    if (done) done[w] = row[2 * o + a + 2];
+  }
+}
+
+// ------------------------------------------------------------------ column copies (concat / repeat / clamp)
+struct CopyTask {
+  float* dst; int ldd;
+  const float* src; int lds;
+  int rows, cols;
+  int row_div, row_mod;   // src_row = (r / row_div) % row_mod
+  int clamp; float lo, hi;
+  float add, mul;          // value = src*mul + add  (then clamp)
+};
+static __global__ void k_copy_tasks(const CopyTask* tasks) {
+  const CopyTask t = tasks[blockIdx.y];
+  const long long total = (long long)t.rows * t.cols;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(e / t.cols), c = (int)(e % t.cols);
+    const int sr = (r / t.row_div) % t.row_mod;
+    float v = t.src[(size_t)sr * t.lds + c] * t.mul + t.add;
+    if (t.clamp) v = fminf(fmaxf(v, t.lo), t.hi);
+    t.dst[(size_t)r * t.ldd + c] = v;
+  }
+}
+
+// ------------------------------------------------------------------ BC loss (bc.py:45-52)
+// u = act_lim * tanh(pre) [B,a] -> loss = mean((u-a)^2); dpre = 2(u-a)/(B a) * act_lim * (1 - (u/act_lim)^2)
+static __global__ void k_bc_loss(const float* __restrict__ u, const float* __restrict__ act, int n, float lim,
+                          float* __restrict__ dpre, float* stat, float inv_world) {
+  __shared__ float sh[33];
+  float s = 0.f;
+  const float inv = 1.f / (float)n;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const float d = u[e] - act[e];
+    s += d * d;
+    const float t = u[e] / lim;
+    dpre[e] = 2.f * d * inv * inv_world * lim * (1.f - t * t);
+  }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) stat[0] = s * inv;
+}
+
+// ------------------------------------------------------------------ VAE (net.py:319-339, bcql.py:122-132)
+// ml = [mean | raw_log_std] [B, 2L]; z = mean + exp(clamp(raw,-4,15)) * eps, written into dec_in[:, o:o+L]
+static __global__ void k_vae_reparam(const float* __restrict__ ml, const float* __restrict__ eps, int B, int L,
+                              float* __restrict__ stdv, float* __restrict__ dec_in, int ldd, int col0) {
+  const int n = B * L;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int b = e / L, j = e % L;
+    const float mean = ml[(size_t)b * 2 * L + j];
+    const float raw = ml[(size_t)b * 2 * L + L + j];
+    const float sd = expf(fminf(fmaxf(raw, -4.f), 15.f));
+    stdv[e] = sd;
+    dec_in[(size_t)b * ldd + col0 + j] = mean + sd * eps[e];
+  }
+}
+// loss_vae = mse(u, act) + beta * KL; dpre3 = d loss / d (d3 pre-activation)
+static __global__ void k_vae_loss(const float* __restrict__ u, const float* __restrict__ act, int B, int a, float lim,
+                           const float* __restrict__ ml, const float* __restrict__ stdv, int L, float beta,
+                           float* __restrict__ dpre3, float* stat, float inv_world) {
+  __shared__ float sh[33];
+  float s = 0.f;
+  const int n = B * a;
+  const float inv = 1.f / (float)n;
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
+    const float d = u[e] - act[e];
+    s += d * d;
+    const float t = u[e] / lim;
+    dpre3[e] = 2.f * d * inv * inv_world * lim * (1.f - t * t);
+  }
+  const float recon = block_sum(s, sh) * inv;
+  float k = 0.f;
+  const int nl = B * L;
+  for (int e = threadIdx.x; e < nl; e += blockDim.x) {
+    const int b = e / L, j = e % L;
+    const float mean = ml[(size_t)b * 2 * L + j];
+    const float sd = stdv[e];
+    k += 1.f + logf(sd * sd) - mean * mean - sd * sd;
+  }
+  const float kl = -0.5f * block_sum(k, sh) / (float)nl;
+  if (threadIdx.x == 0) stat[0] = recon + beta * kl;
+}
+// dz = d loss / d dec_in[:, o:o+L]  ->  dml = [dmean | draw_log_std]
+static __global__ void k_vae_reparam_bwd(const float* __restrict__ ddec_in, int ldd, int col0, const float* __restrict__ ml,
+                                  const float* __restrict__ stdv, const float* __restrict__ eps, int B, int L,
+                                  float beta, float* __restrict__ dml, float inv_world) {
+  const int n = B * L;
+  const float c = beta / (float)n * inv_world;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int b = e / L, j = e % L;
+    const float dz = ddec_in[(size_t)b * ldd + col0 + j];
+    const float mean = ml[(size_t)b * 2 * L + j];
+    const float raw = ml[(size_t)b * 2 * L + L + j];
+    const float sd = stdv[e];
+    const float dmean = dz + c * mean;
+    const float dstd = dz * eps[e] + c * (sd - 1.f / sd);
+    const float dls = dstd * sd;
+    dml[(size_t)b * 2 * L + j] = dmean;
+    dml[(size_t)b * 2 * L + L + j] = (raw >= -4.f && raw <= 15.f) ? dls : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------ Bellman backup from sampled target Qs
+// q [R, n] with R = B*S rows (b-major), n = 2*num nets (first half = q1 list, second = q2 list).
+// lambda*min(q1,q2) + (1-lambda)*max(q1,q2), max over the S samples, then
+// backup = r + gamma * (1-done)^use_done * max     (bcql.py:143-148, 166-172)
+static __global__ void k_q_backup(const float* __restrict__ q, int B, int S, int n, float lmbda, float gamma,
+                           const float* __restrict__ r, const float* __restrict__ done, int use_done,
+                           float* __restrict__ backup) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int h = n / 2;
+  float best = -INFINITY;
+  for (int s = 0; s < S; ++s) {
+    const float* row = q + ((size_t)b * S + s) * n;
+    float q1 = row[0], q2 = row[h];
+    for (int i = 1; i < h; ++i) { q1 = fminf(q1, row[i]); q2 = fminf(q2, row[h + i]); }
+    const float v = lmbda * fminf(q1, q2) + (1.f - lmbda) * fmaxf(q1, q2);
+    best = fmaxf(best, v);
+  }
+  const float nd = use_done ? (1.f - done[b]) : 1.f;
+  backup[b] = r[b] + gamma * nd * best;
+}
+
+// ensemble MSE against the backup: loss = sum_i mean_b (q[b,i]-y[b])^2 ; dq = 2 (q-y) / B  (net.py:285-287)
+static __global__ void k_critic_loss(const float* __restrict__ q, const float* __restrict__ y, int B, int n,
+                              float* __restrict__ dq, float* stat, float inv_world, float extra_const_ptr_mul,
+                              const float* extra) {
+  __shared__ float sh[33];
+  float s = 0.f;
+  const float inv = 1.f / (float)B;
+  for (int e = threadIdx.x; e < B * n; e += blockDim.x) {
+    const float d = q[e] - y[e / n];
+    s += d * d;
+    dq[e] = 2.f * d * inv * inv_world;
+  }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) stat[0] = s * inv + (extra ? extra_const_ptr_mul * extra[0] : 0.f);
+}
+
+// ------------------------------------------------------------------ BCQ-Lag actor loss + PID (bcql.py:181-208, net.py:376-387)
+// q [B,nq], qc [B,nqc] (all nets of each double critic).  q_pi = min over all nets; gradient flows to the argmin.
+static __global__ void k_bcql_actor_loss(const float* __restrict__ q, int nq, const float* __restrict__ qc, int nqc, int B,
+                                  float qc_thres, float kp, float ki, float kd, DevState* ds,
+                                  float* __restrict__ dq, float* __restrict__ dqc, float* stat /*[3]*/,
+                                  float inv_world, const float* qc_mean_global) {
+  __shared__ float sh[33];
+  float sq = 0.f, sc = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    float m = q[(size_t)b * nq];
+    for (int i = 1; i < nq; ++i) m = fminf(m, q[(size_t)b * nq + i]);
+    float c = qc[(size_t)b * nqc];
+    for (int i = 1; i < nqc; ++i) c = fminf(c, qc[(size_t)b * nqc + i]);
+    sq += m;
+    sc += c - qc_thres;
+  }
+  const float q_mean = block_sum(sq, sh) / (float)B;
+  float e_new = block_sum(sc, sh) / (float)B;
+  if (qc_mean_global) e_new = *qc_mean_global;  // data-parallel: mean over the global batch
+  __shared__ float mult_s;
+  if (threadIdx.x == 0) {
+    const float e_diff = fmaxf(e_new - ds->pid_e_old, 0.f);
+    const float e_int = fmaxf(ds->pid_e_int + e_new, 0.f);
+    ds->pid_e_int = e_int;
+    ds->pid_e_old = e_new;
+    mult_s = fmaxf(kp * fmaxf(e_new, 0.f) + ki * e_int + kd * e_diff, 0.f);
+  }
+  __syncthreads();
+  const float mult = mult_s;
+  const float invB = 1.f / (float)B * inv_world;
+  float pen = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    int am = 0; float m = q[(size_t)b * nq];
+    for (int i = 1; i < nq; ++i) { const float v = q[(size_t)b * nq + i]; if (v < m) { m = v; am = i; } }
+    for (int i = 0; i < nq; ++i) dq[(size_t)b * nq + i] = (i == am) ? -invB : 0.f;
+    int ac = 0; float c = qc[(size_t)b * nqc];
+    for (int i = 1; i < nqc; ++i) { const float v = qc[(size_t)b * nqc + i]; if (v < c) { c = v; ac = i; } }
+    for (int i = 0; i < nqc; ++i) dqc[(size_t)b * nqc + i] = (i == ac) ? mult * invB : 0.f;
+    pen += (c - qc_thres) * mult;
+  }
+  const float qc_pen = block_sum(pen, sh) / (float)B;
+  if (threadIdx.x == 0) {
+    stat[0] = -q_mean + qc_pen;  // loss/actor_loss
+    stat[1] = qc_pen;            // loss/qc_penalty
+    stat[2] = mult;              // loss/lagrangian
+  }
+}
+
+// a = clamp(phi*lim*t + a_vae, +-lim), t = tanh(l3): d l3pre = (da_q + da_qc) * [|.|<=lim] * phi*lim*(1-t^2)
+static __global__ void k_perturb_bwd(const float* __restrict__ da1, const float* __restrict__ da2, int ld_da,
+                              const float* __restrict__ t, const float* __restrict__ avae, int ld_av, int B, int a,
+                              float philim, float lim, float* __restrict__ dpre) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < B * a; e += gridDim.x * blockDim.x) {
+    const int b = e / a, j = e % a;
+    const float tv = t[e];
+    const float pre = philim * tv + avae[(size_t)b * ld_av + j];
+    const float g = da1[(size_t)b * ld_da + j] + (da2 ? da2[(size_t)b * ld_da + j] : 0.f);
+    dpre[e] = (pre >= -lim && pre <= lim) ? g * philim * (1.f - tv * tv) : 0.f;
+  }
+}
+
+}  // namespace osrl

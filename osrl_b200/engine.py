@@ -1,0 +1,294 @@
+"""Python handle on one C-ABI engine (one process, one GPU).
+
+Thin plumbing only: builds the ``osrl_config``, exposes the parameter arena as zero-copy
+torch views (``__cuda_array_interface__``), forwards minibatches / noise by raw pointer on
+torch's current CUDA stream.  All arithmetic happens in libosrl_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from typing import Dict, Iterable, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ALGO, Batch, Config, DatasetView, Noise, ParamDesc, check
+
+_BATCH_KEYS = ("observations", "next_observations", "actions", "rewards", "costs", "done")
+
+
+def make_config(algo: str, *, batch_size: int, seed: int = 0, world_size: int = 1, rank: int = 0, **kw) -> Config:
+    """Fill an ``osrl_config`` from the reference's constructor/trainer keyword names."""
+    cfg = Config()
+    cfg.algo = ALGO[algo]
+    cfg.batch_size, cfg.seed, cfg.world_size, cfg.rank = int(batch_size), int(seed), int(world_size), int(rank)
+    ren = {"state_dim": "obs_dim", "action_dim": "act_dim", "vae_hidden_sizes": "vae_hidden"}
+    # defaults of fields the reference defaults too
+    cfg.max_action, cfg.gamma, cfg.tau, cfg.phi, cfg.lmbda, cfg.beta = 1.0, 0.99, 0.005, 0.05, 0.75, 0.5
+    cfg.pid_kp, cfg.pid_ki, cfg.pid_kd = 0.1, 0.003, 0.001
+    cfg.num_q = cfg.num_qc = 1
+    cfg.cost_limit, cfg.episode_len, cfg.sample_action_num = 10, 300, 10
+    cfg.qc_scalar, cfg.mmd_sigma, cfg.target_mmd_thresh, cfg.num_samples_mmd_match = 1.5, 50.0, 0.05, 10
+    cfg.start_update_policy_step = 20000
+    cfg.actor_lr = cfg.critic_lr = cfg.vae_lr = 1e-4
+    cfg.alpha_lr = 1e-4 if algo == "cpq" else 1e-3
+    for k, v in kw.items():
+        k = ren.get(k, k)
+        if k in ("a_hidden_sizes", "c_hidden_sizes"):
+            v = list(v)
+            if not 1 <= len(v) <= _lib.OSRL_MAX_HIDDEN:
+                raise ValueError(f"{k}: 1..{_lib.OSRL_MAX_HIDDEN} hidden layers supported")
+            p = k[0]
+            setattr(cfg, f"n_{p}_hidden", len(v))
+            arr = getattr(cfg, f"{p}_hidden")
+            for i, x in enumerate(v):
+                arr[i] = int(x)
+        elif k == "PID":
+            cfg.pid_kp, cfg.pid_ki, cfg.pid_kd = [float(x) for x in v]
+        elif k == "kernel":
+            cfg.mmd_kernel = {"gaussian": 0, "laplacian": 1}[v]
+        elif k in ("device", "episode_len_unused"):
+            continue
+        elif hasattr(cfg, k):
+            setattr(cfg, k, v)
+        else:
+            raise TypeError(f"unknown config field {k!r}")
+    return cfg
+
+
+class _Cai:
+    """Non-owning CUDA array view for torch.as_tensor."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def _as_f32(x, device_index: int):
+    """-> (tensor kept alive, pointer, on_host)"""
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+    if not isinstance(x, torch.Tensor):
+        x = torch.as_tensor(x, dtype=torch.float32)
+    if x.dtype != torch.float32:
+        x = x.float()
+    x = x.contiguous()
+    if x.is_cuda and x.device.index != device_index:
+        raise ValueError("batch tensor lives on a different GPU than the engine")
+    return x, x.data_ptr(), (0 if x.is_cuda else 1)
+
+
+class Engine:
+    def __init__(self, algo: str, *, batch_size: int, device: int = 0, seed: int = 0, world_size: int = 1,
+                 rank: int = 0, **hyper):
+        self.lib = _lib.load()
+        self.algo = algo
+        self.device = int(device)
+        self.batch_size = int(batch_size)
+        self.cfg = make_config(algo, batch_size=batch_size, seed=seed, world_size=world_size, rank=rank, **hyper)
+        h = C.c_void_p()
+        check(self.lib.osrl_engine_create(C.byref(self.cfg), self.device, C.byref(h)))
+        self.h = h
+        self._keep = []
+        n = C.c_int()
+        check(self.lib.osrl_param_table(self.h, None, 0, C.byref(n)))
+        arr = (ParamDesc * n.value)()
+        check(self.lib.osrl_param_table(self.h, arr, n.value, C.byref(n)))
+        self.table = list(arr)
+        names = (C.c_char_p * 16)()
+        check(self.lib.osrl_stat_names(self.h, names, 16, C.byref(n)))
+        self.stat_names = [names[i].decode() for i in range(n.value)]
+        nn_ = (C.c_char_p * _lib.OSRL_MAX_NOISE)()
+        cnt = (C.c_int64 * _lib.OSRL_MAX_NOISE)()
+        check(self.lib.osrl_noise_layout(self.h, nn_, cnt, _lib.OSRL_MAX_NOISE, C.byref(n)))
+        self.noise_layout = OrderedDict((nn_[i].decode(), int(cnt[i])) for i in range(n.value))
+
+    # ------------------------------------------------------------------ life cycle
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.osrl_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self) -> int:
+        return int(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ parameters
+    def param_views(self) -> "OrderedDict[str, torch.Tensor]":
+        """state_dict-ordered zero-copy float32 views into the arena (trained + target sections)."""
+        out = OrderedDict()
+        for d in self.table:
+            shape = (d.rows, d.cols) if d.cols else (d.rows,)
+            t = torch.as_tensor(_Cai(d.ptr, shape), device=f"cuda:{self.device}")
+            t._osrl_engine = self  # keep the arena alive as long as a view exists
+            out[d.name.decode()] = t
+        return out
+
+    def load_params(self, params: Dict[str, torch.Tensor], sync_targets: bool = False) -> None:
+        """Copy tensors (reference state_dict names) into the arena."""
+        names = [d.name.decode() for d in self.table]
+        for i, name in enumerate(names):
+            if name not in params:
+                continue
+            t = params[name].detach().to(torch.float32).cpu().contiguous()
+            check(self.lib.osrl_param_set(self.h, i, C.c_void_p(t.data_ptr()), t.numel()))
+        if sync_targets:
+            check(self.lib.osrl_sync_targets(self.h))
+
+    def read_params(self) -> "OrderedDict[str, torch.Tensor]":
+        out = OrderedDict()
+        for i, d in enumerate(self.table):
+            shape = (d.rows, d.cols) if d.cols else (d.rows,)
+            t = torch.empty(shape, dtype=torch.float32)
+            check(self.lib.osrl_param_get(self.h, i, C.c_void_p(t.data_ptr()), t.numel()))
+            out[d.name.decode()] = t
+        return out
+
+    def sync_targets(self):
+        check(self.lib.osrl_sync_targets(self.h))
+
+    # ------------------------------------------------------------------ dataset
+    def upload_dataset(self, data: dict, reward_scale: float = 1.0, cost_scale: float = 1.0) -> None:
+        keep = {k: np.ascontiguousarray(data[k], dtype=np.float32)
+                for k in ("observations", "next_observations", "actions", "rewards", "costs")}
+        v = DatasetView()
+        v.n = keep["observations"].shape[0]
+        for k, a in keep.items():
+            setattr(v, k, a.ctypes.data)
+        if "done" in data:
+            keep["done"] = np.ascontiguousarray(data["done"], dtype=np.float32)
+            v.done = keep["done"].ctypes.data
+        else:
+            keep["terminals"] = np.ascontiguousarray(data["terminals"]).astype(np.uint8)
+            keep["timeouts"] = np.ascontiguousarray(data["timeouts"]).astype(np.uint8)
+            v.terminals, v.timeouts = keep["terminals"].ctypes.data, keep["timeouts"].ctypes.data
+        v.reward_scale, v.cost_scale = float(reward_scale), float(cost_scale)
+        check(self.lib.osrl_buffer_upload(self.h, C.byref(v)))
+        self.dataset_size = int(v.n)
+
+    def gather(self, idx) -> Dict[str, torch.Tensor]:
+        """Bit-exact row gather by explicit indices -> six CUDA tensors."""
+        idx = torch.as_tensor(idx, dtype=torch.int64).contiguous()
+        n = idx.numel()
+        o, a = self.cfg.obs_dim, self.cfg.act_dim
+        dev = f"cuda:{self.device}"
+        out = {"observations": torch.empty(n, o, device=dev), "next_observations": torch.empty(n, o, device=dev),
+               "actions": torch.empty(n, a, device=dev), "rewards": torch.empty(n, device=dev),
+               "costs": torch.empty(n, device=dev), "done": torch.empty(n, device=dev)}
+        b = Batch()
+        b.rows, b.on_host = n, 0
+        for k in _BATCH_KEYS:
+            setattr(b, k, out[k].data_ptr())
+        check(self.lib.osrl_gather(self.h, C.c_void_p(idx.data_ptr()), n, 0 if idx.is_cuda else 1, C.byref(b),
+                                   C.c_void_p(self._stream())))
+        return out
+
+    # ------------------------------------------------------------------ stepping
+    def step(self, batch: dict, noise: Optional[dict] = None) -> None:
+        """One train_one_step on an explicit minibatch (host or device tensors)."""
+        keep = []
+        b = Batch()
+        b.rows = self.batch_size
+        kinds = set()
+        for k in _BATCH_KEYS:
+            if k not in batch or batch[k] is None:
+                continue
+            t, p, on_host = _as_f32(batch[k], self.device)
+            keep.append(t)
+            kinds.add(on_host)
+            setattr(b, k, p)
+        if len(kinds) != 1:
+            raise ValueError("all batch tensors must live on the same side (host or this GPU)")
+        b.on_host = kinds.pop()
+        nz_ptr = None
+        if noise is not None:
+            nz = Noise()
+            nk = set()
+            for i, name in enumerate(self.noise_layout):
+                if name in noise and noise[name] is not None:
+                    t, p, on_host = _as_f32(noise[name], self.device)
+                    if t.numel() != self.noise_layout[name]:
+                        raise ValueError(f"noise slot {name}: expected {self.noise_layout[name]} floats, got {t.numel()}")
+                    keep.append(t)
+                    nk.add(on_host)
+                    nz.slot[i] = p
+            if len(nk) > 1:
+                raise ValueError("all noise tensors must live on the same side")
+            nz.on_host = nk.pop() if nk else 0
+            nz_ptr = C.byref(nz)
+        check(self.lib.osrl_step(self.h, C.byref(b), nz_ptr, C.c_void_p(self._stream())))
+        self._keep = keep  # pinned/device sources must outlive the async copies
+
+    def steps(self, k: int) -> None:
+        """k steps sampled on the device from the resident dataset."""
+        check(self.lib.osrl_steps(self.h, int(k), C.c_void_p(self._stream())))
+
+    def stats(self) -> Dict[str, float]:
+        buf = (C.c_float * 16)()
+        n = C.c_int()
+        check(self.lib.osrl_stats(self.h, buf, 16, C.byref(n), C.c_void_p(self._stream())))
+        return {self.stat_names[i]: float(buf[i]) for i in range(n.value)}
+
+    def scalars(self) -> Dict[str, float]:
+        names = (C.c_char_p * 16)()
+        n = C.c_int()
+        check(self.lib.osrl_scalar_names(self.h, names, 16, C.byref(n)))
+        vals = (C.c_double * 16)()
+        check(self.lib.osrl_scalars_get(self.h, vals, 16, C.byref(n)))
+        return {names[i].decode(): float(vals[i]) for i in range(n.value)}
+
+    def set_scalars(self, **kw) -> None:
+        cur = self.scalars()
+        cur.update(kw)
+        vals = (C.c_double * len(cur))(*cur.values())
+        check(self.lib.osrl_scalars_set(self.h, vals, len(cur)))
+
+    def last_indices(self) -> np.ndarray:
+        out = np.empty(self.batch_size, dtype=np.int64)
+        check(self.lib.osrl_last_indices(self.h, C.c_void_p(out.ctypes.data), self.batch_size))
+        return out
+
+    def last_noise(self) -> Dict[str, np.ndarray]:
+        out = {}
+        for i, (name, cnt) in enumerate(self.noise_layout.items()):
+            a = np.empty(cnt, dtype=np.float32)
+            check(self.lib.osrl_last_noise(self.h, i, C.c_void_p(a.ctypes.data), cnt))
+            out[name] = a
+        return out
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.osrl_launch_count(self.h))
+
+    @property
+    def launches_per_step(self) -> int:
+        return int(self.lib.osrl_launches_per_step(self.h))
+
+    # ------------------------------------------------------------------ data parallel
+    def init_comm(self, unique_id: bytes) -> None:
+        buf = (C.c_char * 128).from_buffer_copy(unique_id)
+        check(self.lib.osrl_comm_init(self.h, buf, self.cfg.world_size, self.cfg.rank))
+
+
+def comm_unique_id() -> bytes:
+    buf = (C.c_char * 128)()
+    check(_lib.load().osrl_comm_unique_id(buf))
+    return bytes(buf.raw)
+
+
+def plan(algo: str, **hyper):
+    """Parameter table (name, shape) without a GPU -- osrl_plan."""
+    lib = _lib.load()
+    cfg = make_config(algo, batch_size=hyper.pop("batch_size", 1), **hyper)
+    n = C.c_int()
+    check(lib.osrl_plan(C.byref(cfg), None, 0, C.byref(n)))
+    arr = (ParamDesc * n.value)()
+    check(lib.osrl_plan(C.byref(cfg), arr, n.value, C.byref(n)))
+    return [(d.name.decode(), (d.rows, d.cols) if d.cols else (d.rows,), d.section, d.group) for d in arr]
