@@ -170,6 +170,16 @@ int osrl_noise_layout(osrl_engine* e, const char** names, int64_t* counts, int c
 int osrl_last_indices(osrl_engine* e, int64_t* host_out, int cap);
 int osrl_last_noise(osrl_engine* e, int slot, float* host_out, int64_t cap);
 
+/* Debug/parity: read `count` floats at float offset `offset` of an arena section
+ * (0 params, 1 targets, 2 gradients of the last step, 3 Adam m, 4 Adam v). */
+int osrl_debug_read(osrl_engine* e, int section, int64_t offset, int64_t count, float* host_out);
+
+/* Per-launch timing of one step: runs the step program eagerly `reps` times on `stream` with a CUDA
+ * event pair around every launch and returns, per launch, its name, mean milliseconds and its
+ * algorithmic bytes / flops.  Call with ms == NULL to query the launch count. */
+int osrl_profile(osrl_engine* e, int reps, int* n_ops, const char** names, double* ms, double* bytes,
+                 double* flops, int cap, void* stream);
+
 /* Number of kernels launched by this engine so far / per step. */
 int64_t osrl_launch_count(osrl_engine* e);
 int osrl_launches_per_step(osrl_engine* e);

@@ -19,8 +19,25 @@ import torch.nn.functional as F
 from . import core as C
 
 
+_DTYPE = [torch.float32]
+
+
+class precision:
+    """Context manager: run the oracle arithmetic in another dtype (float64 conditioning probe in tests)."""
+
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        _DTYPE.append(self.dtype)
+
+    def __exit__(self, *a):
+        _DTYPE.pop()
+
+
 def _draw(noise: Optional[Dict[str, torch.Tensor]], used: Dict[str, torch.Tensor], name: str, shape):
-    x = torch.randn(shape) if noise is None else noise[name].reshape(shape).to(torch.float32)
+    x = torch.randn(shape) if noise is None else noise[name].reshape(shape)
+    x = x.to(_DTYPE[-1])
     used[name] = x
     return x
 
@@ -55,6 +72,7 @@ class BCOracle:
         loss = F.mse_loss(pred, actions)  # bc.py:47
         g = C.grads_of(loss, p, self.g_actor)
         C.require_grad(p, self.g_actor, False)
+        self.last_grads = dict(g)
         self.opt.step(p, g)
         return {"loss/actor_loss": loss.item()}
 
@@ -137,6 +155,8 @@ class BCQLOracle:
     def _update(self, name: str, loss: torch.Tensor) -> None:
         g = C.grads_of(loss, self.params, self.g[name])
         C.require_grad(self.params, self.g[name], False)
+        self.last_grads = getattr(self, "last_grads", {})
+        self.last_grads.update(g)
         self.opt[name].step(self.params, g)
 
     def step(self, observations, next_observations, actions, rewards, costs, done, noise=None):
@@ -268,6 +288,8 @@ class CPQOracle:
     def _update(self, name, loss):
         g = C.grads_of(loss, self.params, self.g[name])
         C.require_grad(self.params, self.g[name], False)
+        self.last_grads = getattr(self, "last_grads", {})
+        self.last_grads.update(g)
         self.opt[name].step(self.params, g)
 
     def _pi(self, obs, eps):
@@ -418,6 +440,8 @@ class BEARLOracle:
     def _update(self, name, loss):
         g = C.grads_of(loss, self.params, self.g[name])
         C.require_grad(self.params, self.g[name], False)
+        self.last_grads = getattr(self, "last_grads", {})
+        self.last_grads.update(g)
         self.opt[name].step(self.params, g)
 
     def _q_target(self, critic_old, num, next_obs, eps):

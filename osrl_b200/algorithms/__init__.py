@@ -1,0 +1,4 @@
+from .bc import BC, BCTrainer  # noqa: F401
+from .bcql import BCQL, BCQLTrainer  # noqa: F401
+from .cpq import CPQ, CPQTrainer  # noqa: F401
+from .bearl import BEARL, BEARLTrainer  # noqa: F401

@@ -3,15 +3,7 @@
 
 namespace osrl {
 
-#define KOP(p, e, ...)                         \
-  do {                                         \
-    Engine* ep_ = &(e);                        \
-    (p).ops.push_back([=](cudaStream_t s) {    \
-      __VA_ARGS__;                             \
-      ep_->launches++;                         \
-    });                                        \
-    (p).kernels++;                             \
-  } while (0)
+
 
 // ====================================================================== BC
 void build_bc(Engine& e) {
@@ -29,7 +21,7 @@ void build_bc(Engine& e) {
   float* stat = e.stats;
   const float lim = c.max_action, iw = e.inv_world();
   const float* act = e.b_act;
-  KOP(p, e, (k_bc_loss<<<1, 1024, 0, s>>>(u, act, B * a, lim, dpre, stat, iw)));
+  KOP(p, e, 0.0, (k_bc_loss<<<1, 1024, 0, s>>>(u, act, B * a, lim, dpre, stat, iw)));
   mlp_bwd(e, p, e.P, e.G, m, e.b_obs, o, B, ACT_RELU, h, dpre);
   const Group& g = e.plan.groups[e.plan.g_actor];
   emit_allreduce(e, p, e.G + g.begin, g.end - g.begin);
@@ -114,10 +106,10 @@ void build_bcql(Engine& e) {
     const float *tqv = tq.q, *tqcv = tqc.q, *oqv = oq.q, *oqcv = oqc.q;
     const int nq = cr.n, nqc = cc.n;
     float* st1 = e.stats + 1; float* st2 = e.stats + 2;
-    KOP(p, e, (k_q_backup<<<(B + 127) / 128, 128, 0, s>>>(tqv, B, S, nq, lm, gm, rew, done, 1, y_q)));
-    KOP(p, e, (k_q_backup<<<(B + 127) / 128, 128, 0, s>>>(tqcv, B, S, nqc, lm, gm, cost, done, 0, y_qc)));
-    KOP(p, e, (k_critic_loss<<<1, 1024, 0, s>>>(oqv, y_q, B, nq, dq, st1, iw, 0.f, nullptr)));
-    KOP(p, e, (k_critic_loss<<<1, 1024, 0, s>>>(oqcv, y_qc, B, nqc, dqc, st2, iw, 0.f, nullptr)));
+    KOP(p, e, 0.0, (k_q_backup<<<(B + 127) / 128, 128, 0, s>>>(tqv, B, S, nq, lm, gm, rew, done, 1, y_q)));
+    KOP(p, e, 0.0, (k_q_backup<<<(B + 127) / 128, 128, 0, s>>>(tqcv, B, S, nqc, lm, gm, cost, done, 0, y_qc)));
+    KOP(p, e, 0.0, (k_critic_loss<<<1, 1024, 0, s>>>(oqv, y_q, B, nq, dq, st1, iw, 0.f, nullptr)));
+    KOP(p, e, 0.0, (k_critic_loss<<<1, 1024, 0, s>>>(oqcv, y_qc, B, nqc, dqc, st2, iw, 0.f, nullptr)));
   }
   {
     EnsBuf gq = ens_alloc(e, cr, B), gqc = ens_alloc(e, cc, B);
@@ -162,7 +154,7 @@ void build_bcql(Engine& e) {
     const int nq = cr.n, nqc = cc.n;
     DevState* ds = e.ds;
     float* st3 = e.stats + 3;
-    KOP(p, e, (k_bcql_actor_loss<<<1, 1024, 0, s>>>(pqv, nq, pqcv, nqc, B, thres, kp, ki, kd, ds, dpq, dpqc, st3, iw,
+    KOP(p, e, 0.0, (k_bcql_actor_loss<<<1, 1024, 0, s>>>(pqv, nq, pqcv, nqc, B, thres, kp, ki, kd, ds, dpq, dpqc, st3, iw,
                                                    nullptr)));
   }
   float* da_q = e.ws((size_t)B * a); float* da_qc = e.ws((size_t)B * a);
@@ -176,7 +168,7 @@ void build_bcql(Engine& e) {
   float* dpre = e.ws((size_t)B * a);
   {
     const float* av = p_ain + o;
-    KOP(p, e, (k_perturb_bwd<<<(B * a + 255) / 256, 256, 0, s>>>(da_q, da_qc, a, pt, av, in, B, a, philim, lim, dpre)));
+    KOP(p, e, 0.0, (k_perturb_bwd<<<(B * a + 255) / 256, 256, 0, s>>>(da_q, da_qc, a, pt, av, in, B, a, philim, lim, dpre)));
   }
   mlp_bwd(e, p, e.P, e.G, act, p_ain, in, B, ACT_TANH, pah, dpre);
   {

@@ -34,36 +34,23 @@ void emit_vae_update(Engine& e, Program& p, const float* sa, float* dec_in, cons
   float* dz = e.ws((size_t)B * L); float* dml = e.ws((size_t)B * 2 * L);
   float* dh2 = e.ws((size_t)B * V); float* dh1 = e.ws((size_t)B * V);
   float* stat = e.stats + stat_index;
-  Engine* ep = &e;
   // encoder
   flush(e, p, {task_fwd(sa, o + a, B, e.P, v.e1, h1, V, ACT_RELU)});
   flush(e, p, {task_fwd(h1, V, B, e.P, v.e2, h2, V, ACT_RELU)});
   flush(e, p, {task_fwd(h2, V, B, e.P, v.heads, ml, 2 * L, ACT_NONE)});
-  p.ops.push_back([=](cudaStream_t s) {
-    k_vae_reparam<<<(B * L + 255) / 256, 256, 0, s>>>(ml, eps, B, L, sd, dec_in, o + L, o);
-    ep->launches++;
-  });
-  p.kernels++;
+  KOP(p, e, 20.0 * B * L, (k_vae_reparam<<<(B * L + 255) / 256, 256, 0, s>>>(ml, eps, B, L, sd, dec_in, o + L, o)));
   // decoder
   flush(e, p, {task_fwd(dec_in, o + L, B, e.P, v.d1, g1, V, ACT_RELU)});
   flush(e, p, {task_fwd(g1, V, B, e.P, v.d2, g2, V, ACT_RELU)});
   flush(e, p, {task_fwd(g2, V, B, e.P, v.d3, u, a, ACT_TANH, c.max_action)});
   const float lim = c.max_action, beta = c.beta;
-  p.ops.push_back([=](cudaStream_t s) {
-    k_vae_loss<<<1, 1024, 0, s>>>(u, act, B, a, lim, ml, sd, L, beta, dpre3, stat, iw);
-    ep->launches++;
-  });
-  p.kernels++;
+  KOP(p, e, 12.0 * B * a + 12.0 * B * L, (k_vae_loss<<<1, 1024, 0, s>>>(u, act, B, a, lim, ml, sd, L, beta, dpre3, stat, iw)));
   // backward
   flush(e, p, {task_wgrad(dpre3, a, g2, V, B, e.G, v.d3), task_dgrad(dpre3, a, B, e.P, v.d3, dg2, V, g2, V, ACT_RELU)});
   flush(e, p, {task_wgrad(dg2, V, g1, V, B, e.G, v.d2), task_dgrad(dg2, V, B, e.P, v.d2, dg1, V, g1, V, ACT_RELU)});
   flush(e, p, {task_wgrad(dg1, V, dec_in, o + L, B, e.G, v.d1),
                task_dgrad(dg1, V, B, e.P, v.d1, dz, L, nullptr, 0, 0, o, L)});
-  p.ops.push_back([=](cudaStream_t s) {
-    k_vae_reparam_bwd<<<(B * L + 255) / 256, 256, 0, s>>>(dz, L, 0, ml, sd, eps, B, L, beta, dml, iw);
-    ep->launches++;
-  });
-  p.kernels++;
+  KOP(p, e, 28.0 * B * L, (k_vae_reparam_bwd<<<(B * L + 255) / 256, 256, 0, s>>>(dz, L, 0, ml, sd, eps, B, L, beta, dml, iw)));
   flush(e, p, {task_wgrad(dml, 2 * L, h2, V, B, e.G, v.heads),
                task_dgrad(dml, 2 * L, B, e.P, v.heads, dh2, V, h2, V, ACT_RELU)});
   flush(e, p, {task_wgrad(dh2, V, h1, V, B, e.G, v.e2), task_dgrad(dh2, V, B, e.P, v.e2, dh1, V, h1, V, ACT_RELU)});

@@ -19,19 +19,6 @@ float* Engine::ws(size_t n) {
   allocs.push_back(p);
   return (float*)p;
 }
-template <class Tt>
-Tt* Engine::upload(const std::vector<Tt>& v) {
-  void* p = nullptr;
-  OSRL_CUDA(cudaMalloc(&p, std::max<size_t>(1, v.size()) * sizeof(Tt)));
-  if (!v.empty()) OSRL_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(Tt), cudaMemcpyHostToDevice));
-  allocs.push_back(p);
-  return (Tt*)p;
-}
-template GemmTask* Engine::upload<GemmTask>(const std::vector<GemmTask>&);
-template CopyTask* Engine::upload<CopyTask>(const std::vector<CopyTask>&);
-template NoiseSlot* Engine::upload<NoiseSlot>(const std::vector<NoiseSlot>&);
-template AdamGroupCfg* Engine::upload<AdamGroupCfg>(const std::vector<AdamGroupCfg>&);
-
 // ------------------------------------------------------------------ GEMM task constructors
 static GemmTask blank_task() {
   GemmTask t;
@@ -72,9 +59,25 @@ GemmTask task_wgrad(const float* dY, int lddy, const float* X, int ldx, int rows
 }
 
 // ------------------------------------------------------------------ launch emitters
-template <int BM, int BN, int TM, int TN>
+// tile shapes: {BM, BN, BK, TM, TN, NSTAGE}
+#define OSRL_GEMM_CFG0 128, 64, 16, 8, 4, 4
+#define OSRL_GEMM_CFG1 64, 64, 32, 4, 4, 4
+#define OSRL_GEMM_CFG2 32, 32, 32, 2, 2, 6
+template <int BM, int BN, int BK, int TM, int TN, int NS>
 static void launch_gemm(const GemmTask* d, int ntasks, int tiles, cudaStream_t s) {
-  k_gemm_tasks<BM, BN, TM, TN><<<tiles, (BM / TM) * (BN / TN), 0, s>>>(d, ntasks);
+  using Cfg = GemmCfg<BM, BN, BK, TM, TN, NS>;
+  k_gemm_tasks<BM, BN, BK, TM, TN, NS><<<tiles, Cfg::NT, Cfg::SMEM_BYTES, s>>>(d, ntasks);
+}
+template <int BM, int BN, int BK, int TM, int TN, int NS>
+static void prepare_gemm() {
+  using Cfg = GemmCfg<BM, BN, BK, TM, TN, NS>;
+  OSRL_CUDA(cudaFuncSetAttribute(k_gemm_tasks<BM, BN, BK, TM, TN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::SMEM_BYTES));
+}
+void prepare_kernels() {
+  prepare_gemm<OSRL_GEMM_CFG0>();
+  prepare_gemm<OSRL_GEMM_CFG1>();
+  prepare_gemm<OSRL_GEMM_CFG2>();
 }
 static int count_tiles(std::vector<GemmTask>& ts, int BM, int BN, bool assign) {
   int tot = 0;
@@ -88,7 +91,12 @@ static int count_tiles(std::vector<GemmTask>& ts, int BM, int BN, bool assign) {
 void emit_gemm(Engine& e, Program& p, const std::vector<GemmTask>& tasks_in) {
   if (tasks_in.empty()) return;
   std::vector<GemmTask> tasks = tasks_in;
-  for (auto& t : tasks) OSRL_REQUIRE(t.M > 0 && t.N > 0 && t.K > 0, "empty gemm task");
+  for (auto& t : tasks) {
+    OSRL_REQUIRE(t.M > 0 && t.N > 0 && t.K > 0, "empty gemm task");
+    // 16-byte cp.async needs base, leading dimension and the contiguous extent 4-float aligned
+    t.a_vec = ((uintptr_t)t.A % 16 == 0) && (t.lda % 4 == 0) && ((t.a_kc ? t.K : t.M) % 4 == 0);
+    t.b_vec = ((uintptr_t)t.B % 16 == 0) && (t.ldb % 4 == 0) && ((t.b_kc ? t.K : t.N) % 4 == 0);
+  }
   // largest tile shape that still yields >= ~1 wave-fraction of CTAs (148 SMs)
   int cfg = 2;
   if (count_tiles(tasks, 128, 64, false) >= 120) cfg = 0;
@@ -98,13 +106,19 @@ void emit_gemm(Engine& e, Program& p, const std::vector<GemmTask>& tasks_in) {
   GemmTask* d = e.upload(tasks);
   const int nt = (int)tasks.size();
   Engine* ep = &e;
-  p.ops.push_back([=](cudaStream_t s) {
-    if (cfg == 0) launch_gemm<128, 64, 8, 4>(d, nt, tiles, s);
-    else if (cfg == 1) launch_gemm<64, 64, 4, 4>(d, nt, tiles, s);
-    else launch_gemm<32, 32, 2, 2>(d, nt, tiles, s);
+  double bytes = 0.0, flops = 0.0;
+  for (auto& t : tasks) {
+    bytes += 4.0 * ((double)t.M * t.K + (double)t.K * t.N + (double)t.M * t.N);
+    flops += 2.0 * (double)t.M * t.N * t.K;
+  }
+  static const char* names[3] = {"k_gemm_tasks<128,64,16,8,4,4>", "k_gemm_tasks<64,64,32,4,4,4>",
+                                 "k_gemm_tasks<32,32,32,2,2,6>"};
+  p.add(names[cfg], bytes, flops, true, [=](cudaStream_t s) {
+    if (cfg == 0) launch_gemm<OSRL_GEMM_CFG0>(d, nt, tiles, s);
+    else if (cfg == 1) launch_gemm<OSRL_GEMM_CFG1>(d, nt, tiles, s);
+    else launch_gemm<OSRL_GEMM_CFG2>(d, nt, tiles, s);
     ep->launches++;
   });
-  p.kernels++;
 }
 CopyTask copy_cols(float* dst, int ldd, int dcol0, const float* src, int lds, int scol0, int rows, int cols, int row_div,
                    int row_mod) {
@@ -125,11 +139,12 @@ void emit_copy(Engine& e, Program& p, const std::vector<CopyTask>& tasks) {
   const int bx = (int)std::min<long long>((mx + 255) / 256, 148 * 4);
   const int ny = (int)tasks.size();
   Engine* ep = &e;
-  p.ops.push_back([=](cudaStream_t s) {
+  double bytes = 0.0;
+  for (auto& t : tasks) bytes += 8.0 * (double)t.rows * t.cols;
+  p.add("k_copy_tasks", bytes, 0.0, true, [=](cudaStream_t s) {
     k_copy_tasks<<<dim3(bx, ny), 256, 0, s>>>(d);
     ep->launches++;
   });
-  p.kernels++;
 }
 void emit_adam(Engine& e, Program& p, int group, int64_t begin, int64_t end, bool polyak) {
   const Group& g = e.plan.groups[group];
@@ -137,12 +152,14 @@ void emit_adam(Engine& e, Program& p, int group, int64_t begin, int64_t end, boo
   const int blocks = (int)std::min<int64_t>((n4 + 255) / 256, 148 * 8);
   Engine* ep = &e;
   const float tau = e.plan.cfg.tau;
-  p.ops.push_back([=](cudaStream_t s) {
+  // read p,g,m,v + write p,m,v = 28 B/param; Polyak adds read+write of the target = 8 B/param
+  const double bytes = (double)(end - begin) * (polyak ? 36.0 : 28.0);
+  p.add(polyak ? "k_adam+polyak" : "k_adam", bytes, 0.0, true, [=](cudaStream_t s) {
     k_adam<<<blocks, 256, 0, s>>>(ep->P + begin, ep->G + begin, ep->M + begin, ep->V + begin, ep->T + begin, n4, ep->ds,
-                                  group, g.beta1, g.beta2, g.eps, g.wd, tau, polyak ? 1 : 0, 1.f, nullptr);
+                                  group, (float)g.beta1, (float)g.beta2, (float)(1.0 - g.beta1), (float)(1.0 - g.beta2),
+                                  g.eps, g.wd, tau, polyak ? 1 : 0, 1.f, nullptr);
     ep->launches++;
   });
-  p.kernels++;
 }
 
 // ------------------------------------------------------------------ NCCL (dlopen'ed; only needed when world > 1)
@@ -177,7 +194,7 @@ static void check(int r, const char* what) {
 void emit_allreduce(Engine& e, Program& p, float* buf, int64_t count) {
   if (e.world <= 1) return;
   Engine* ep = &e;
-  p.ops.push_back([=](cudaStream_t s) {
+  p.add("ncclAllReduce", 4.0 * (double)count, 0.0, false, [=](cudaStream_t s) {
     if (!ep->comm) throw Err(OSRL_ERR_STATE, "world_size > 1 but osrl_comm_init was not called");
     nccl::check(nccl::AllReduce(buf, buf, (size_t)count, /*ncclFloat32*/ 7, /*ncclSum*/ 0, ep->comm, s), "ncclAllReduce");
   });
@@ -289,7 +306,7 @@ static Engine* create(const osrl_config& cfg, int device) {
       OSRL_CUDA(cudaMemcpy(e->ds, &h, sizeof(h), cudaMemcpyHostToDevice));
     }
     std::vector<AdamGroupCfg> gc;
-    for (auto& g : e->plan.groups) gc.push_back({g.lr, g.beta1, g.beta2, g.warmup});
+    for (auto& g : e->plan.groups) gc.push_back({(double)g.lr, g.beta1, g.beta2, g.warmup});
     e->d_groups = e->upload(gc);
     const int o = cfg.obs_dim, a = cfg.act_dim, B = e->B;
     e->b_obs = e->ws((size_t)B * o); e->b_nobs = e->ws((size_t)B * o); e->b_act = e->ws((size_t)B * a);
@@ -306,6 +323,7 @@ static Engine* create(const osrl_config& cfg, int device) {
     e->d_slots_dyn = e->upload(slots);
     e->stats = e->ws(std::max<size_t>(16, e->plan.stat_names.size()));
     OSRL_CUDA(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+    prepare_kernels();
     build_program(*e);
     OSRL_CUDA(cudaDeviceSynchronize());
   } catch (...) {
@@ -706,6 +724,58 @@ int osrl_last_noise(osrl_engine* h, int slot, float* host_out, int64_t cap) {
   OSRL_CUDA(cudaDeviceSynchronize());
   OSRL_CUDA(cudaMemcpy(host_out, e.noise_buf[slot], (size_t)e.plan.noise[slot].second * sizeof(float),
                        cudaMemcpyDeviceToHost));
+  OSRL_CATCH
+}
+
+int osrl_debug_read(osrl_engine* h, int section, int64_t offset, int64_t count, float* host_out) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && host_out, "null argument");
+  Engine& e = *h->e;
+  float* secs[5] = {e.P, e.T, e.G, e.M, e.V};
+  OSRL_REQUIRE(section >= 0 && section < 5, "bad section");
+  OSRL_REQUIRE(offset >= 0 && count >= 0 && offset + count <= e.plan.nP, "range outside the arena section");
+  OSRL_CUDA(cudaSetDevice(e.device));
+  OSRL_CUDA(cudaDeviceSynchronize());
+  OSRL_CUDA(cudaMemcpy(host_out, secs[section] + offset, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost));
+  OSRL_CATCH
+}
+
+int osrl_profile(osrl_engine* h, int reps, int* n_ops, const char** names, double* ms, double* bytes, double* flops,
+                 int cap, void* stream) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && n_ops && reps >= 1, "bad argument");
+  Engine& e = *h->e;
+  OSRL_CUDA(cudaSetDevice(e.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n = (int)e.body.ops.size();
+  *n_ops = n;
+  if (!ms) return OSRL_OK;
+  OSRL_REQUIRE(cap >= n, "profile buffers too small");
+  std::vector<cudaEvent_t> ev(2 * n);
+  for (auto& x : ev) OSRL_CUDA(cudaEventCreate(&x));
+  std::vector<double> acc(n, 0.0);
+  for (int r = 0; r < reps; ++r) {
+    prologue(e, s);
+    for (int i = 0; i < n; ++i) {
+      OSRL_CUDA(cudaEventRecord(ev[2 * i], s));
+      e.body.ops[i](s);
+      OSRL_CUDA(cudaEventRecord(ev[2 * i + 1], s));
+    }
+    epilogue(e, s);
+    OSRL_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < n; ++i) {
+      float t = 0.f;
+      OSRL_CUDA(cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]));
+      acc[i] += t;
+    }
+  }
+  for (auto& x : ev) cudaEventDestroy(x);
+  for (int i = 0; i < n; ++i) {
+    ms[i] = acc[i] / reps;
+    if (names) names[i] = e.body.meta[i].name.c_str();
+    if (bytes) bytes[i] = e.body.meta[i].bytes;
+    if (flops) flops[i] = e.body.meta[i].flops;
+  }
   OSRL_CATCH
 }
 

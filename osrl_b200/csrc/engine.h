@@ -55,7 +55,9 @@ struct ParamEntry {
 struct Group {
   std::string name;
   int64_t begin = 0, end = 0;
-  float lr = 0.f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f, wd = 0.f;
+  float lr = 0.f;
+  double beta1 = 0.9, beta2 = 0.999;  // kept in double: torch derives 1-beta and beta^t from python doubles
+  float eps = 1e-8f, wd = 0.f;
   int warmup = 0;
   bool has_target = false;
 };
@@ -81,10 +83,34 @@ Plan make_plan(const osrl_config& cfg);
 using Op = std::function<void(cudaStream_t)>;
 
 struct Engine;
+struct OpMeta {
+  std::string name;     // kernel (or collective) name
+  double bytes = 0.0;   // algorithmic bytes of this launch (operands read once + results written once)
+  double flops = 0.0;   // algorithmic flops of this launch
+  bool kernel = true;   // one of OUR kernels (false: NCCL collective)
+};
 struct Program {
   std::vector<Op> ops;
+  std::vector<OpMeta> meta;
   int kernels = 0;
+  void add(const std::string& name, double bytes, double flops, bool kernel, Op fn) {
+    ops.push_back(std::move(fn));
+    meta.push_back({name, bytes, flops, kernel});
+    if (kernel) ++kernels;
+  }
 };
+// elementwise / reduction kernel launch as one program op: KOP(p, e, bytes, (kernel<<<...>>>(args)))
+#define KOP(p, e, bytes_, ...)                                              \
+  do {                                                                      \
+    ::osrl::Engine* ep_ = &(e);                                             \
+    std::string nm_ = #__VA_ARGS__;                                         \
+    nm_ = nm_.substr(nm_.find_first_not_of("( "));                          \
+    nm_ = nm_.substr(0, nm_.find_first_of("<( "));                          \
+    (p).add(nm_, (double)(bytes_), 0.0, true, [=](cudaStream_t s) {         \
+      __VA_ARGS__;                                                          \
+      ep_->launches++;                                                      \
+    });                                                                     \
+  } while (0)
 
 struct Engine {
   Plan plan;
@@ -115,7 +141,14 @@ struct Engine {
   int world = 1, rank = 0;
 
   float* ws(size_t n);  // zero-initialised device workspace
-  template <class Tt> Tt* upload(const std::vector<Tt>& v);
+  template <class Tt>
+  Tt* upload(const std::vector<Tt>& v) {  // host vector -> device array owned by the engine
+    void* p = nullptr;
+    OSRL_CUDA(cudaMalloc(&p, (v.empty() ? 1 : v.size()) * sizeof(Tt)));
+    if (!v.empty()) OSRL_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(Tt), cudaMemcpyHostToDevice));
+    allocs.push_back(p);
+    return (Tt*)p;
+  }
   float inv_world() const { return 1.f / (float)world; }
 };
 
@@ -128,6 +161,7 @@ GemmTask task_fwd(const float* X, int ldx, int rows, const float* W, const Lin& 
 GemmTask task_dgrad(const float* dY, int lddy, int rows, const float* W, const Lin& l, float* dX, int lddx,
                     const float* Hprev, int ldh, int dact, int col0 = 0, int ncols = -1);
 GemmTask task_wgrad(const float* dY, int lddy, const float* X, int ldx, int rows, float* Gsec, const Lin& l);
+void prepare_kernels();
 void emit_gemm(Engine& e, Program& p, const std::vector<GemmTask>& tasks);
 void emit_copy(Engine& e, Program& p, const std::vector<CopyTask>& tasks);
 void emit_adam(Engine& e, Program& p, int group, int64_t begin, int64_t end, bool polyak);

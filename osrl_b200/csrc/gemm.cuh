@@ -7,6 +7,12 @@
 // sum) so no elementwise kernel runs between layers.  Replaces nn.Linear + activation in
 // the reference's mlp() (osrl/common/net.py:12-30) and their autograd backward.
 //
+// The layers of this workload are small (M = 256..5120, N,K <= 1024) and every operand is
+// L2-resident, so a tile's k-loop is bound by load latency, not bandwidth: operands are
+// staged global->shared with cp.async (LDGSTS) through an NSTAGE-deep ring so several
+// k-slabs are in flight per CTA, in their native layout (no transpose on the way in):
+//   k-contiguous operand  X[i*ld + k]  ->  smem [rows][BK+4]   (float4 fragments along k)
+//   mn-contiguous operand X[k*ld + i]  ->  smem [BK][rows+4]   (float4 fragments along m/n)
 // Arithmetic: fp32 FFMA with fp32 accumulation -- the parity mode (1e-5 vs the reference).
 #pragma once
 #include <cuda_runtime.h>
@@ -29,6 +35,7 @@ struct GemmTask {
   int lda, ldb, ldc, ldr, ld_dact, ldaux;
   int a_kc;               // 1: A[i*lda + k] (k contiguous); 0: A[k*lda + i]
   int b_kc;               // 1: B[j*ldb + k];                 0: B[k*ldb + j]
+  int a_vec, b_vec;       // 16-byte cp.async allowed (base, ld and contiguous extent 4-float aligned)
   int act;                // Act applied to acc + bias
   float scale;            // multiplies the activated value
   int clamp;              // clamp final value to [lo, hi]
@@ -44,16 +51,99 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-template <int BM, int BN, int TM, int TN>
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// load T consecutive floats from shared memory (T in {1,2,4,8}), address aligned to min(T,4) floats
+template <int T>
+__device__ __forceinline__ void lds_vec(const float* p, float* out) {
+  if constexpr (T == 1) {
+    out[0] = p[0];
+  } else if constexpr (T == 2) {
+    const float2 v = *reinterpret_cast<const float2*>(p);
+    out[0] = v.x; out[1] = v.y;
+  } else {
+#pragma unroll
+    for (int q = 0; q < T / 4; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(p + 4 * q);
+      out[4 * q] = v.x; out[4 * q + 1] = v.y; out[4 * q + 2] = v.z; out[4 * q + 3] = v.w;
+    }
+  }
+}
+
+template <int BM, int BN, int BK, int TM, int TN, int NSTAGE>
+struct GemmCfg {
+  static constexpr int NT = (BM / TM) * (BN / TN);
+  static constexpr int A_KC = BM * (BK + 4), A_MC = BK * (BM + 4);
+  static constexpr int B_KC = BN * (BK + 4), B_MC = BK * (BN + 4);
+  static constexpr int A_STAGE = A_KC > A_MC ? A_KC : A_MC;
+  static constexpr int B_STAGE = B_KC > B_MC ? B_KC : B_MC;
+  static constexpr int SMEM_BYTES = NSTAGE * (A_STAGE + B_STAGE) * (int)sizeof(float);
+};
+
+// stage one operand slab: ROWS x BK elements starting at (r0, k0)
+template <int ROWS, int BK, int NT>
+__device__ __forceinline__ void stage_operand(float* __restrict__ s, const float* __restrict__ G, int ld, bool kc,
+                                              bool vec, int r0, int k0, int R, int K, int tid) {
+  if (kc) {  // G[r*ld + k] -> s[r*(BK+4) + k]
+    if (vec) {
+      constexpr int CH = ROWS * (BK / 4);
+#pragma unroll
+      for (int c = tid; c < CH; c += NT) {
+        const int r = c / (BK / 4), kq = (c % (BK / 4)) * 4;
+        const bool ok = (r0 + r < R) && (k0 + kq < K);
+        cp_async16(s + r * (BK + 4) + kq, ok ? G + (size_t)(r0 + r) * ld + k0 + kq : G, ok);
+      }
+    } else {
+      constexpr int EL = ROWS * BK;
+#pragma unroll
+      for (int e = tid; e < EL; e += NT) {
+        const int r = e / BK, k = e % BK;
+        const bool ok = (r0 + r < R) && (k0 + k < K);
+        cp_async4(s + r * (BK + 4) + k, ok ? G + (size_t)(r0 + r) * ld + k0 + k : G, ok);
+      }
+    }
+  } else {  // G[k*ld + r] -> s[k*(ROWS+4) + r]
+    if (vec) {
+      constexpr int CH = BK * (ROWS / 4);
+#pragma unroll
+      for (int c = tid; c < CH; c += NT) {
+        const int k = c / (ROWS / 4), rq = (c % (ROWS / 4)) * 4;
+        const bool ok = (k0 + k < K) && (r0 + rq < R);
+        cp_async16(s + k * (ROWS + 4) + rq, ok ? G + (size_t)(k0 + k) * ld + r0 + rq : G, ok);
+      }
+    } else {
+      constexpr int EL = ROWS * BK;
+#pragma unroll
+      for (int e = tid; e < EL; e += NT) {
+        const int k = e / ROWS, r = e % ROWS;
+        const bool ok = (k0 + k < K) && (r0 + r < R);
+        cp_async4(s + k * (ROWS + 4) + r, ok ? G + (size_t)(k0 + k) * ld + r0 + r : G, ok);
+      }
+    }
+  }
+}
+
+template <int BM, int BN, int BK, int TM, int TN, int NSTAGE>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 k_gemm_tasks(const GemmTask* __restrict__ tasks, int ntasks) {
-  constexpr int BK = 16;
-  constexpr int NT = (BM / TM) * (BN / TN);
-  constexpr int EA = BM * BK / NT;
-  constexpr int EB = BN * BK / NT;
-  static_assert(BM * BK % NT == 0 && BN * BK % NT == 0, "tile/threads mismatch");
-  __shared__ __align__(16) float As[2][BK][BM + 4];
-  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+  using Cfg = GemmCfg<BM, BN, BK, TM, TN, NSTAGE>;
+  constexpr int NT = Cfg::NT;
+  constexpr int TXN = BN / TN;  // threads along N
+  extern __shared__ __align__(16) float smem[];
+  float* As = smem;
+  float* Bs = smem + NSTAGE * Cfg::A_STAGE;
   __shared__ GemmTask ts;
 
   const int tid = threadIdx.x;
@@ -73,9 +163,10 @@ k_gemm_tasks(const GemmTask* __restrict__ tasks, int ntasks) {
   const float* __restrict__ B = t.B;
   const int lda = t.lda, ldb = t.ldb;
   const bool akc = t.a_kc != 0, bkc = t.b_kc != 0;
+  const bool avec = t.a_vec != 0, bvec = t.b_vec != 0;
 
-  const int tx = tid % (BN / TN);
-  const int ty = tid / (BN / TN);
+  const int tx = tid % TXN;
+  const int ty = tid / TXN;
 
   float acc[TM][TN];
 #pragma unroll
@@ -87,74 +178,68 @@ k_gemm_tasks(const GemmTask* __restrict__ tasks, int ntasks) {
   for (int i = 0; i < TM; ++i) rs[i] = 0.f;
   const bool want_colsum = (t.colsum != nullptr) && (n0 == 0) && (tx == 0);
 
-  float ra[EA], rb[EB];
-  auto load_tiles = [&](int k0) {
-#pragma unroll
-    for (int r = 0; r < EA; ++r) {
-      const int e = tid + r * NT;
-      int i, k;
-      if (akc) { i = e / BK; k = e % BK; } else { i = e % BM; k = e / BM; }
-      const int gi = m0 + i, gk = k0 + k;
-      float v = 0.f;
-      if (gi < M && gk < K) v = akc ? A[(size_t)gi * lda + gk] : A[(size_t)gk * lda + gi];
-      ra[r] = v;
-    }
-#pragma unroll
-    for (int r = 0; r < EB; ++r) {
-      const int e = tid + r * NT;
-      int j, k;
-      if (bkc) { j = e / BK; k = e % BK; } else { j = e % BN; k = e / BN; }
-      const int gj = n0 + j, gk = k0 + k;
-      float v = 0.f;
-      if (gj < N && gk < K) v = bkc ? B[(size_t)gj * ldb + gk] : B[(size_t)gk * ldb + gj];
-      rb[r] = v;
-    }
-  };
-  auto store_tiles = [&](int buf) {
-#pragma unroll
-    for (int r = 0; r < EA; ++r) {
-      const int e = tid + r * NT;
-      int i, k;
-      if (akc) { i = e / BK; k = e % BK; } else { i = e % BM; k = e / BM; }
-      As[buf][k][i] = ra[r];
-    }
-#pragma unroll
-    for (int r = 0; r < EB; ++r) {
-      const int e = tid + r * NT;
-      int j, k;
-      if (bkc) { j = e / BK; k = e % BK; } else { j = e % BN; k = e / BN; }
-      Bs[buf][k][j] = rb[r];
-    }
-  };
-
   const int nk = (K + BK - 1) / BK;
-  load_tiles(0);
-  store_tiles(0);
-  __syncthreads();
+  // prologue: NSTAGE-1 slabs in flight
+#pragma unroll
+  for (int s = 0; s < NSTAGE - 1; ++s) {
+    if (s < nk) {
+      stage_operand<BM, BK, NT>(As + s * Cfg::A_STAGE, A, lda, akc, avec, m0, s * BK, M, K, tid);
+      stage_operand<BN, BK, NT>(Bs + s * Cfg::B_STAGE, B, ldb, bkc, bvec, n0, s * BK, N, K, tid);
+    }
+    cp_async_commit();
+  }
+
   for (int kt = 0; kt < nk; ++kt) {
-    const int cur = kt & 1;
-    if (kt + 1 < nk) load_tiles((kt + 1) * BK);
+    cp_async_wait<NSTAGE - 2>();
+    __syncthreads();  // slab kt visible to all; slab kt-1's buffer is free
+    {
+      const int nx = kt + NSTAGE - 1;
+      if (nx < nk) {
+        const int sb = nx % NSTAGE;
+        stage_operand<BM, BK, NT>(As + sb * Cfg::A_STAGE, A, lda, akc, avec, m0, nx * BK, M, K, tid);
+        stage_operand<BN, BK, NT>(Bs + sb * Cfg::B_STAGE, B, ldb, bkc, bvec, n0, nx * BK, N, K, tid);
+      }
+      cp_async_commit();
+    }
+    const float* __restrict__ as = As + (kt % NSTAGE) * Cfg::A_STAGE;
+    const float* __restrict__ bs = Bs + (kt % NSTAGE) * Cfg::B_STAGE;
 #pragma unroll
-    for (int k = 0; k < BK; ++k) {
-      float a[TM], b[TN];
+    for (int k4 = 0; k4 < BK; k4 += 4) {
+      float a[4][TM], b[4][TN];
+      if (akc) {
 #pragma unroll
-      for (int i = 0; i < TM; ++i) a[i] = As[cur][k][ty * TM + i];
+        for (int i = 0; i < TM; ++i) {
+          const float4 v = *reinterpret_cast<const float4*>(as + (ty * TM + i) * (BK + 4) + k4);
+          a[0][i] = v.x; a[1][i] = v.y; a[2][i] = v.z; a[3][i] = v.w;
+        }
+      } else {
 #pragma unroll
-      for (int j = 0; j < TN; ++j) b[j] = Bs[cur][k][tx * TN + j];
+        for (int kk = 0; kk < 4; ++kk) lds_vec<TM>(as + (k4 + kk) * (BM + 4) + ty * TM, a[kk]);
+      }
+      if (bkc) {  // strided column ownership: col = tx + j*TXN (bank-conflict-free float4 reads along k)
 #pragma unroll
-      for (int i = 0; i < TM; ++i)
+        for (int j = 0; j < TN; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(bs + (tx + j * TXN) * (BK + 4) + k4);
+          b[0][j] = v.x; b[1][j] = v.y; b[2][j] = v.z; b[3][j] = v.w;
+        }
+      } else {    // consecutive column ownership: col = tx*TN + j
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-      if (want_colsum) {
+        for (int kk = 0; kk < 4; ++kk) lds_vec<TN>(bs + (k4 + kk) * (BN + 4) + tx * TN, b[kk]);
+      }
 #pragma unroll
-        for (int i = 0; i < TM; ++i) rs[i] += a[i];
+      for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[kk][i], b[kk][j], acc[i][j]);
+        if (want_colsum) {
+#pragma unroll
+          for (int i = 0; i < TM; ++i) rs[i] += a[kk][i];
+        }
       }
     }
-    if (kt + 1 < nk) {
-      store_tiles(cur ^ 1);
-      __syncthreads();
-    }
   }
+  cp_async_wait<0>();
 
   // ---- fused epilogue
 #pragma unroll
@@ -164,7 +249,7 @@ k_gemm_tasks(const GemmTask* __restrict__ tasks, int ntasks) {
     if (want_colsum) t.colsum[gi] = rs[i];
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
-      const int gj = n0 + tx * TN + j;
+      const int gj = n0 + (bkc ? tx + j * TXN : tx * TN + j);
       if (gj >= N) continue;
       float v = acc[i][j];
       if (t.bias) v += t.bias[gj];

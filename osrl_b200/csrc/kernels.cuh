@@ -72,7 +72,7 @@ __device__ __forceinline__ float block_sum(float v, float* sh /*[33]*/) {
 
 // ------------------------------------------------------------------ step prologue: counters + Adam scalars
 struct AdamGroupCfg {
-  float lr, beta1, beta2;
+  double lr, beta1, beta2;
   int warmup;  // >0: lr * min((t)/warmup, 1) with t = step count after increment (LambdaLR, cdt.py:327-330)
 };
 static __global__ void k_prologue(DevState* ds, const AdamGroupCfg* g, int ngroups) {
@@ -85,8 +85,8 @@ static __global__ void k_prologue(DevState* ds, const AdamGroupCfg* g, int ngrou
       double f = (double)t / (double)g[i].warmup;
       lr = lr * (f < 1.0 ? f : 1.0);
     }
-    const double bc1 = 1.0 - pow((double)g[i].beta1, (double)t);
-    const double bc2 = 1.0 - pow((double)g[i].beta2, (double)t);
+    const double bc1 = 1.0 - pow(g[i].beta1, (double)t);
+    const double bc2 = 1.0 - pow(g[i].beta2, (double)t);
     ds->adam_lr[i] = (float)lr;
     ds->adam_step_size[i] = (float)(lr / bc1);
     ds->adam_bc2_sqrt[i] = (float)sqrt(bc2);
@@ -102,13 +102,14 @@ static __global__ void k_epilogue(DevState* ds) {
 // (bcql.py:114-120) -- valid because no later sub-update of the same step reads that target.
 static __global__ void k_adam(float* __restrict__ P, const float* __restrict__ G, float* __restrict__ Mm,
                        float* __restrict__ Vv, float* __restrict__ T, int64_t n4, const DevState* ds, int group,
-                       float beta1, float beta2, float eps, float weight_decay, float tau, int polyak,
-                       float grad_mul, const float* clip_coef) {
+                       float beta1, float beta2, float w1, float w2, float eps, float weight_decay, float tau,
+                       int polyak, float grad_mul, const float* clip_coef) {
   const float step_size = ds->adam_step_size[group];
   const float bc2s = ds->adam_bc2_sqrt[group];
   const float lr = ds->adam_lr[group];
   const float gm = clip_coef ? grad_mul * (*clip_coef) : grad_mul;
-  const float w1 = 1.f - beta1, w2 = 1.f - beta2;
+  // w1 = float(1 - beta1), w2 = float(1 - beta2) are rounded from the double difference on the host, as torch
+  // does (a float 1.f - 0.999f would be off by 1.3e-5 relative)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 p = reinterpret_cast<float4*>(P)[i];
     float4 g = reinterpret_cast<const float4*>(G)[i];
@@ -403,6 +404,306 @@ static __global__ void k_perturb_bwd(const float* __restrict__ da1, const float*
     const float pre = philim * tv + avae[(size_t)b * ld_av + j];
     const float g = da1[(size_t)b * ld_da + j] + (da2 ? da2[(size_t)b * ld_da + j] : 0.f);
     dpre[e] = (pre >= -lim && pre <= lim) ? g * philim * (1.f - tv * tv) : 0.f;
+  }
+}
+
+}  // namespace osrl
+
+// ====================================================================== CPQ / BEAR-Lag kernels
+namespace osrl {
+
+// ------------------------------------------------------------------ squashed-Gaussian sampling (net.py:169-205)
+// mh = [mu | raw_log_std] [*, 2a]; u = mu + exp(clamp(ls,-20,2)) * eps; out = do_tanh ? scale*tanh(u) : u
+struct SquashTask {
+  const float* mh; int row_div, row_mod;  // source row of (mu, log_std) = (r / row_div) % row_mod
+  const float* eps;                       // [rows, a]
+  float* dst; int ldd;                    // dst[r*ldd + j]
+  float* u_out;                           // optional raw u [rows, a]
+  int rows, a, do_tanh;
+  float scale;
+};
+static __global__ void k_squash_tasks(const SquashTask* tasks) {
+  const SquashTask t = tasks[blockIdx.y];
+  const int n = t.rows * t.a;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int r = e / t.a, j = e % t.a;
+    const int sr = (r / t.row_div) % t.row_mod;
+    const float mu = t.mh[(size_t)sr * 2 * t.a + j];
+    const float ls = fminf(fmaxf(t.mh[(size_t)sr * 2 * t.a + t.a + j], -20.f), 2.f);
+    const float u = mu + expf(ls) * t.eps[e];
+    if (t.u_out) t.u_out[e] = u;
+    t.dst[(size_t)r * t.ldd + j] = t.do_tanh ? t.scale * tanhf(u) : u;
+  }
+}
+
+// ------------------------------------------------------------------ CPQ Bellman backups (cpq.py:140-146, 158-161)
+__device__ __forceinline__ float row_min(const float* p, int n) {
+  float m = p[0];
+  for (int i = 1; i < n; ++i) m = fminf(m, p[i]);
+  return m;
+}
+static __global__ void k_cpq_backup(const float* __restrict__ tq, int nq, const float* __restrict__ tqc1,
+                                    const float* __restrict__ tqc2, int nqc, int B, float gamma, float q_thres,
+                                    const float* __restrict__ r, const float* __restrict__ c,
+                                    const float* __restrict__ done, float* __restrict__ yq, float* __restrict__ yc) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float q = row_min(tq + (size_t)b * nq, nq);
+  const float qc1 = row_min(tqc1 + (size_t)b * nqc, nqc);
+  const float qc2 = row_min(tqc2 + (size_t)b * nqc, nqc);
+  yq[b] = r[b] + gamma * (1.f - done[b]) * (qc1 <= q_thres ? 1.f : 0.f) * q;
+  yc[b] = c[b] + gamma * qc2;
+}
+
+// per-row KL of the OOD samples (cpq.py:178-182) and ensemble-min cost Q
+static __global__ void k_cpq_kl_rows(const float* __restrict__ ml, int L, const float* __restrict__ qc, int nqc,
+                                     int rows, float* __restrict__ kl, float* __restrict__ qcmin) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float s = 0.f;
+  for (int j = 0; j < L; ++j) {
+    const float mean = ml[(size_t)r * 2 * L + j];
+    const float sd = expf(fminf(fmaxf(ml[(size_t)r * 2 * L + L + j], -4.f), 15.f));
+    s += 1.f + logf(sd * sd) - mean * mean - sd * sd;
+  }
+  kl[r] = -0.5f * (s / (float)L);
+  qcmin[r] = row_min(qc + (size_t)r * nqc, nqc);
+}
+
+__device__ __forceinline__ uint32_t f2key(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+// k-th smallest (0-based) of v[0..n) by 4-pass radix select; single CTA; sh: 256+2 uints
+static __device__ uint32_t block_select(const float* __restrict__ v, int n, int kth, uint32_t* hist) {
+  uint32_t prefix = 0, mask = 0;
+  int k = kth;
+  for (int pass = 3; pass >= 0; --pass) {
+    const int shift = pass * 8;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint32_t key = f2key(v[i]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int acc = 0, d = 0;
+      for (; d < 256; ++d) {
+        if (acc + (int)hist[d] > k) break;
+        acc += hist[d];
+      }
+      hist[256] = (uint32_t)d;
+      hist[257] = (uint32_t)(k - acc);
+    }
+    __syncthreads();
+    prefix |= hist[256] << shift;
+    mask |= 255u << shift;
+    k = (int)hist[257];
+    __syncthreads();
+  }
+  return prefix;
+}
+// torch.quantile(kl, 0.75) (linear interpolation) -> qc_ood -> dual step on log_alpha (cpq.py:183-195)
+// kl, qcmin are [S, B] (S-major).  stat_extra[0] = exp(log_alpha_old) * (mean qc_ood - qc_thres)
+static __global__ void k_cpq_ood(const float* __restrict__ kl, const float* __restrict__ qcmin, int S, int B,
+                                 float qfrac, float qc_thres, float alpha_lr, DevState* ds, float* stat_extra,
+                                 float* stat_alpha) {
+  __shared__ uint32_t hist[258];
+  __shared__ float sh[33];
+  const int n = S * B;
+  const double pos = (double)qfrac * (double)(n - 1);
+  const int lo = (int)floor(pos), hi = (int)ceil(pos);
+  const float w = (float)(pos - (double)lo);
+  const float vlo = key2f(block_select(kl, n, lo, hist));
+  const float vhi = (hi == lo) ? vlo : key2f(block_select(kl, n, hi, hist));
+  const float quant = vlo + w * (vhi - vlo);   // torch lerp, weight < 0.5 form; (>=0.5 differs by <=1ulp)
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += (kl[i] >= quant) ? qcmin[i] : 0.f;
+  const float tot = block_sum(s, sh);
+  if (threadIdx.x == 0) {
+    const float mean_ood = tot / (float)S / (float)B;  // mean over s, then mean over b
+    const float la = ds->log_alpha;
+    stat_extra[0] = expf(la) * (mean_ood - qc_thres);
+    float nla = la + alpha_lr * expf(la) * (qc_thres - mean_ood);
+    nla = fminf(fmaxf(nla, -5.f), 5.f);
+    ds->log_alpha = nla;
+    stat_alpha[0] = expf(nla);
+  }
+}
+
+// CPQ actor loss (cpq.py:203-222): loss = -mean(1[qc<=q_thres] * q); grad only through q's argmin net
+static __global__ void k_cpq_actor_loss(const float* __restrict__ q, int nq, const float* __restrict__ qc, int nqc,
+                                        int B, float q_thres, float* __restrict__ dq, float* stat, float inv_world) {
+  __shared__ float sh[33];
+  float s = 0.f;
+  const float invB = 1.f / (float)B;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    int am = 0; float m = q[(size_t)b * nq];
+    for (int i = 1; i < nq; ++i) { const float v = q[(size_t)b * nq + i]; if (v < m) { m = v; am = i; } }
+    const float gate = row_min(qc + (size_t)b * nqc, nqc) <= q_thres ? 1.f : 0.f;
+    s += gate * m;
+    for (int i = 0; i < nq; ++i) dq[(size_t)b * nq + i] = (i == am) ? -gate * invB * inv_world : 0.f;
+  }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) stat[0] = -s * invB;
+}
+
+// a = scale*tanh(u), u = mu + std*eps: d[mu | raw_log_std] from da (one sample per row)
+static __global__ void k_squash_bwd(const float* __restrict__ da, int ld_da, const float* __restrict__ u,
+                                    const float* __restrict__ mh, const float* __restrict__ eps, int B, int a,
+                                    float scale, float* __restrict__ dmh) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < B * a; e += gridDim.x * blockDim.x) {
+    const int b = e / a, j = e % a;
+    const float t = tanhf(u[e]);
+    const float du = da[(size_t)b * ld_da + j] * scale * (1.f - t * t);
+    const float raw = mh[(size_t)b * 2 * a + a + j];
+    const float sd = expf(fminf(fmaxf(raw, -20.f), 2.f));
+    dmh[(size_t)b * 2 * a + j] = du;
+    dmh[(size_t)b * 2 * a + a + j] = (raw >= -20.f && raw <= 2.f) ? du * eps[e] * sd : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------ BEAR-Lag MMD (bearl.py:283-318)
+#define OSRL_MMD_MAXN 32
+#define OSRL_MMD_MAXA 16
+__device__ __forceinline__ float mmd_k(const float* x, const float* y, int a, float inv2s, int laplacian) {
+  float d = 0.f;
+  for (int j = 0; j < a; ++j) {
+    const float t = x[j] - y[j];
+    d += laplacian ? fabsf(t) : t * t;
+  }
+  return expf(-d * inv2s);
+}
+// x = raw VAE decodes [B,N,a]; y = raw actor samples u [B,N,a]; mmd [B]
+static __global__ void k_mmd_fwd(const float* __restrict__ x, const float* __restrict__ y, int B, int N, int a,
+                                 float sigma, int laplacian, float* __restrict__ mmd) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float inv2s = 1.f / (2.f * sigma);
+  const float* xb = x + (size_t)b * N * a;
+  const float* yb = y + (size_t)b * N * a;
+  // the three kernel means are O(1) and their combination is O(1e-3): accumulate in double so the
+  // cancellation does not amplify fp32 summation error (torch's pairwise mean is similarly accurate)
+  double kxx = 0.0, kyy = 0.0, kxy = 0.0;
+  for (int i = 0; i < N; ++i)
+    for (int m = 0; m < N; ++m) {
+      kxx += (double)mmd_k(xb + i * a, xb + m * a, a, inv2s, laplacian);
+      kyy += (double)mmd_k(yb + i * a, yb + m * a, a, inv2s, laplacian);
+      kxy += (double)mmd_k(xb + i * a, yb + m * a, a, inv2s, laplacian);
+    }
+  const double nn = (double)(N * N);
+  mmd[b] = sqrtf((float)(kxx / nn + kyy / nn - 2.0 * (kxy / nn) + 1e-6));
+}
+
+// BEAR actor loss + PID + dual step (bearl.py:240-262).  q/qc: all nets of each double critic.
+static __global__ void k_bear_actor_loss(const float* __restrict__ q, int nq, const float* __restrict__ qc, int nqc,
+                                         const float* __restrict__ mmd, int B, float qc_thres, float kp, float ki,
+                                         float kd, float mmd_thresh, float alpha_lr, int start_step, DevState* ds,
+                                         float* __restrict__ dq, float* __restrict__ dqc, float* stat /*[5]*/,
+                                         float* mmd_coef, float inv_world) {
+  __shared__ float sh[33];
+  __shared__ float mult_s, gate_s, ealpha_s;
+  float sq = 0.f, sc = 0.f, sm = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    sq += row_min(q + (size_t)b * nq, nq);
+    sc += row_min(qc + (size_t)b * nqc, nqc) - qc_thres;
+    sm += mmd[b] - mmd_thresh;
+  }
+  const float q_mean = block_sum(sq, sh) / (float)B;
+  const float e_new = block_sum(sc, sh) / (float)B;
+  const float mmd_mean_c = block_sum(sm, sh) / (float)B;  // mean(mmd - thresh)
+  if (threadIdx.x == 0) {
+    const float e_diff = fmaxf(e_new - ds->pid_e_old, 0.f);
+    const float e_int = fmaxf(ds->pid_e_int + e_new, 0.f);
+    ds->pid_e_int = e_int;
+    ds->pid_e_old = e_new;
+    mult_s = fmaxf(kp * fmaxf(e_new, 0.f) + ki * e_int + kd * e_diff, 0.f);
+    gate_s = ds->n_train_steps >= start_step ? 1.f : 0.f;
+    ealpha_s = expf(ds->log_alpha);
+  }
+  __syncthreads();
+  const float mult = mult_s, gate = gate_s, ealpha = ealpha_s;
+  const float invB = 1.f / (float)B * inv_world;
+  float pen = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    int am = 0; float m = q[(size_t)b * nq];
+    for (int i = 1; i < nq; ++i) { const float v = q[(size_t)b * nq + i]; if (v < m) { m = v; am = i; } }
+    for (int i = 0; i < nq; ++i) dq[(size_t)b * nq + i] = (i == am) ? -gate * invB : 0.f;
+    int ac = 0; float c = qc[(size_t)b * nqc];
+    for (int i = 1; i < nqc; ++i) { const float v = qc[(size_t)b * nqc + i]; if (v < c) { c = v; ac = i; } }
+    for (int i = 0; i < nqc; ++i) dqc[(size_t)b * nqc + i] = (i == ac) ? mult * invB : 0.f;
+    pen += (c - qc_thres) * mult;
+  }
+  const float qc_pen = block_sum(pen, sh) / (float)B;
+  if (threadIdx.x == 0) {
+    stat[0] = -gate * q_mean + ealpha * mmd_mean_c + qc_pen;  // loss/actor_loss
+    stat[1] = mmd_mean_c + mmd_thresh;                         // loss/mmd_loss
+    stat[2] = qc_pen;                                          // loss/qc_penalty
+    stat[3] = mult;                                            // loss/lagrangian
+    mmd_coef[0] = ealpha * invB;                               // d loss / d mmd[b]
+    float nla = ds->log_alpha + alpha_lr * ealpha * mmd_mean_c;
+    nla = fminf(fmaxf(nla, -5.f), 5.f);
+    ds->log_alpha = nla;
+    ds->n_train_steps += 1;
+    stat[4] = expf(nla);                                       // loss/alpha_value
+  }
+}
+
+// d loss / d [mu | raw_log_std] of the actor from (i) the MMD term on all N samples and
+// (ii) the Q terms on sample 0 (da = d loss / d tanh(u[b,0]))
+static __global__ void k_bear_actor_bwd(const float* __restrict__ x, const float* __restrict__ y,
+                                        const float* __restrict__ mmd, const float* __restrict__ mmd_coef,
+                                        const float* __restrict__ da1, const float* __restrict__ da2, int ld_da,
+                                        const float* __restrict__ mh, const float* __restrict__ eps, int B, int N,
+                                        int a, float sigma, int laplacian, float* __restrict__ dmh) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float inv2s = 1.f / (2.f * sigma);
+  const float* xb = x + (size_t)b * N * a;
+  const float* yb = y + (size_t)b * N * a;
+  const float nn = (float)(N * N);
+  const float gm = mmd_coef[0] / (2.f * mmd[b]);  // d loss / d (mmd^2 argument)
+  double dmu[OSRL_MMD_MAXA], dls[OSRL_MMD_MAXA];  // double: the k(y,y) and k(x,y) terms nearly cancel
+  for (int j = 0; j < a; ++j) { dmu[j] = 0.0; dls[j] = 0.0; }
+  for (int n = 0; n < N; ++n) {
+    double du[OSRL_MMD_MAXA];
+    for (int j = 0; j < a; ++j) du[j] = 0.0;
+    for (int m = 0; m < N; ++m) {
+      const float kyy = mmd_k(yb + n * a, yb + m * a, a, inv2s, laplacian);
+      const float kxy = mmd_k(xb + m * a, yb + n * a, a, inv2s, laplacian);
+      for (int j = 0; j < a; ++j) {
+        const float dyy = yb[n * a + j] - yb[m * a + j];
+        const float dxy = xb[m * a + j] - yb[n * a + j];
+        float gyy, gxy;  // d k / d y_n[j]
+        if (laplacian) {
+          gyy = -kyy * inv2s * (dyy > 0.f ? 1.f : (dyy < 0.f ? -1.f : 0.f));
+          gxy = kxy * inv2s * (dxy > 0.f ? 1.f : (dxy < 0.f ? -1.f : 0.f));
+        } else {
+          gyy = -kyy * 2.f * inv2s * dyy;
+          gxy = kxy * 2.f * inv2s * dxy;
+        }
+        // mean k(y,y): y_n appears in row n and column n -> factor 2;  -2 * mean k(x,y)
+        du[j] += (double)gm * (2.0 * (double)gyy - 2.0 * (double)gxy) / (double)nn;
+      }
+    }
+    for (int j = 0; j < a; ++j) {
+      if (n == 0) {
+        const float t = tanhf(yb[j]);
+        du[j] += (double)((da1[(size_t)b * ld_da + j] + da2[(size_t)b * ld_da + j]) * (1.f - t * t));
+      }
+      dmu[j] += du[j];
+      dls[j] += du[j] * (double)eps[((size_t)b * N + n) * a + j];
+    }
+  }
+  for (int j = 0; j < a; ++j) {
+    const float raw = mh[(size_t)b * 2 * a + a + j];
+    const float sd = expf(fminf(fmaxf(raw, -20.f), 2.f));
+    dmh[(size_t)b * 2 * a + j] = (float)dmu[j];
+    dmh[(size_t)b * 2 * a + a + j] = (raw >= -20.f && raw <= 2.f) ? (float)(dls[j] * (double)sd) : 0.f;
   }
 }
 

@@ -151,6 +151,19 @@ class Engine:
             out[d.name.decode()] = t
         return out
 
+    def read_section(self, section: str) -> "OrderedDict[str, torch.Tensor]":
+        """Trained-parameter-shaped tensors of another arena section: 'grad', 'adam_m', 'adam_v'."""
+        sec = {"param": 0, "target": 1, "grad": 2, "adam_m": 3, "adam_v": 4}[section]
+        out = OrderedDict()
+        for d in self.table:
+            if d.section != 0:
+                continue
+            shape = (d.rows, d.cols) if d.cols else (d.rows,)
+            t = torch.empty(shape, dtype=torch.float32)
+            check(self.lib.osrl_debug_read(self.h, sec, d.offset, t.numel(), C.c_void_p(t.data_ptr())))
+            out[d.name.decode()] = t
+        return out
+
     def sync_targets(self):
         check(self.lib.osrl_sync_targets(self.h))
 
@@ -262,6 +275,16 @@ class Engine:
             check(self.lib.osrl_last_noise(self.h, i, C.c_void_p(a.ctypes.data), cnt))
             out[name] = a
         return out
+
+    def profile(self, reps: int = 20):
+        """Per-launch (name, mean ms, algorithmic bytes, algorithmic flops) of one step, eager launches."""
+        n = C.c_int()
+        check(self.lib.osrl_profile(self.h, 1, C.byref(n), None, None, None, None, 0, C.c_void_p(self._stream())))
+        k = n.value
+        names, ms = (C.c_char_p * k)(), (C.c_double * k)()
+        by, fl = (C.c_double * k)(), (C.c_double * k)()
+        check(self.lib.osrl_profile(self.h, int(reps), C.byref(n), names, ms, by, fl, k, C.c_void_p(self._stream())))
+        return [(names[i].decode(), float(ms[i]), float(by[i]), float(fl[i])) for i in range(k)]
 
     @property
     def launches(self) -> int:

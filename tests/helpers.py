@@ -1,5 +1,5 @@
 """Shared helpers of the parity tests (the oracle is the checker, never the product)."""
-import dataclasses
+import copy
 import json
 import os
 
@@ -27,18 +27,48 @@ def make_oracle(algo, cfg_dict, init_seed=0):
     return cls(cfgcls(**cfg_dict))
 
 
-def engine_kwargs(algo, cfg_dict):
-    return dict(cfg_dict)
-
-
-def batch_tuple(algo, b):
-    t = {k: torch.as_tensor(np.asarray(v)) for k, v in b.items()}
+def batch_tuple(algo, b, dtype=torch.float32):
+    t = {k: torch.as_tensor(np.asarray(v)).to(dtype) for k, v in b.items()}
     if algo == "bc":
         return (t["observations"], t["actions"])
     return (t["observations"], t["next_observations"], t["actions"], t["rewards"], t["costs"], t["done"])
 
 
-def rel_delta_err(p_eng, p_ref, p_init):
-    """max |p_eng - p_ref| relative to the largest parameter delta of that tensor."""
-    d = (p_ref - p_init).abs().max().item()
-    return (p_eng - p_ref).abs().max().item() / (d + 1e-12)
+def to_double(orc):
+    """float64 twin of an oracle at its current state (conditioning probe)."""
+    o = copy.deepcopy(orc)
+    for k in list(o.params):
+        o.params[k] = o.params[k].detach().double()
+    for st in (o.opt.values() if isinstance(o.opt, dict) else [o.opt]):
+        st.m = {k: v.double() for k, v in st.m.items()}
+        st.v = {k: v.double() for k, v in st.v.items()}
+    if hasattr(o, "pid"):
+        o.pid.e_old, o.pid.e_int = o.pid.e_old.double(), o.pid.e_int.double()
+    if hasattr(o, "log_alpha"):
+        o.log_alpha = o.log_alpha.double()
+    return o
+
+
+def probe_step(orc, algo, batch, noise=None):
+    """One reference step in fp32 (the reference path) and one in fp64 from the same state with the same
+    noise.  Returns (stats32, stats64, grads32, grads64, params_before, params64_after).  The fp32/fp64 gap
+    measures how well-conditioned each quantity is: a ReLU unit whose pre-activation rounds to +-0, or an
+    Adam update with |g| ~ eps, makes the reference itself irreproducible at 1e-5."""
+    o64 = to_double(orc)
+    before = {k: v.detach().clone() for k, v in orc.params.items()}
+    s32 = orc.step(*batch_tuple(algo, batch), noise=noise)
+    nz = {k: v.double() for k, v in orc.last_noise.items()}
+    with algos.precision(torch.float64):
+        s64 = o64.step(*batch_tuple(algo, batch, torch.float64), noise=nz)
+    g32 = {k: v.detach() for k, v in orc.last_grads.items()}
+    g64 = {k: v.detach() for k, v in o64.last_grads.items()}
+    return s32, s64, g32, g64, before, {k: v.detach() for k, v in o64.params.items()}
+
+
+def maxrel(a, b):
+    """max |a-b| / max |b|"""
+    return float((a.double() - b.double()).abs().max()) / (float(b.double().abs().max()) + 1e-300)
+
+
+def l2rel(a, b):
+    return float((a.double() - b.double()).norm()) / (float(b.double().norm()) + 1e-300)
