@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- gradient-steps/sec of the OSRL per-step hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload = BASELINE.json configs[1]: BCQ-Lag, OfflineCarCircle-v0-shaped transitions (obs 8, act 2),
+batch 256 per GPU, hidden [256,256] x2, VAE 400, 10 sampled actions, 2+2 double-Q nets, fp32.
+One "step" = VAE + critic + cost-critic + actor updates + Polyak (reference: BCQLTrainer.train_one_step,
+osrl/algorithms/bcql.py:283-306, fed by the loop body examples/train/train_bcql.py:142-148).
+
+ours      : `value` -- K steps with the dataset resident in HBM (minibatch drawn on the device), timed
+            with CUDA events between barriers, max over ranks.  `e2e` -- the same step through the
+            public trainer API with HOST (pinned) minibatches: H2D of the 6 batch tensors and D2H of
+            the step's stats inside the timed region.
+reference : the reference's CPU implementation of the same step (the oracle port of the PyTorch path,
+            all host threads), rank 0 only.
+Data-parallel (N>1): one process per GPU (torchrun), per-GPU batch fixed at 256 (weak scaling), gradients
+all-reduced with NCCL before every optimiser update; `value` = N x synchronous steps/s, i.e. batch-256
+gradient-step equivalents per second over the whole job.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+CFG = dict(state_dim=8, action_dim=2, max_action=1.0, a_hidden_sizes=[256, 256], c_hidden_sizes=[256, 256],
+           vae_hidden_sizes=400, sample_action_num=10, gamma=0.99, tau=0.005, phi=0.05, lmbda=0.75, beta=0.5,
+           PID=[0.1, 0.003, 0.001], num_q=2, num_qc=2, cost_limit=10, episode_len=300, actor_lr=1e-3, critic_lr=1e-3,
+           vae_lr=1e-3)
+BATCH = 256
+DATASET_ROWS = 2_000_000          # 2e6 x 96 B packed = 192 MB per GPU  (> 126 MB L2)
+REWARD_SCALE, COST_SCALE = 0.1, 1.0
+# algorithmic bytes per step = 24*P_train + 8*P_target + batch bytes (fp32)
+P_TRAIN, P_TARGET = 954_452, 620_042
+STEP_BYTES = 24 * P_TRAIN + 8 * P_TARGET + BATCH * (2 * 8 + 2 + 3) * 4
+STEP_FLOPS = 7.285e9
+WORKLOAD = "BCQ-Lag OfflineCarCircle-v0-shaped (obs 8, act 2) batch=256/GPU fp32 (BASELINE.json configs[1])"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_dataset(rows: int, seed: int):
+    from oracle import synth
+    eps = rows // 300
+    return synth.make_dataset(8, 2, 300, eps, seed=seed)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def init_params():
+    from tests.helpers import make_oracle
+    return make_oracle("bcql", CFG, 0)
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    orc = init_params()
+    rng = np.random.default_rng(0)
+    batches = [synth.make_batch(rng, BATCH, 8, 2) for _ in range(8)]
+    keys = ("observations", "next_observations", "actions", "rewards", "costs", "done")
+    tb = [[torch.from_numpy(b[k]) for k in keys] for b in batches]
+    torch.manual_seed(0)
+    for i in range(max(1, min(args.warmup, 5))):
+        orc.step(*tb[i % len(tb)])
+    t0 = time.perf_counter()
+    orc.step(*tb[0])
+    one = time.perf_counter() - t0
+    k = max(3, min(args.steps, int(120.0 / max(one, 1e-4))))   # bounded sample: <= ~2 min of CPU work
+    t0 = time.perf_counter()
+    for i in range(k):
+        orc.step(*tb[i % len(tb)])
+    dt = time.perf_counter() - t0
+    v = k / dt
+    sample = f"{k} train steps (oracle port of bcql.py:283-306, torch CPU fp32) on fixed pre-collated batches"
+    print(json.dumps({
+        "impl": "reference", "metric": "gradient-steps/sec", "value": v, "unit": "steps/s", "n_gpus": args.gpus,
+        "steps": k, "warmup": args.warmup, "ms_per_step": 1e3 * dt / k, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": BATCH, "parallelism": "cpu"},
+        "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch.distributed as dist
+    from osrl_b200 import Engine, comm_unique_id
+    from osrl_b200.algorithms import BCQL, BCQLTrainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torchrun (one process per GPU)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    orc = init_params()
+    eng = Engine("bcql", batch_size=BATCH, device=local, seed=1234, world_size=world, rank=rank, **CFG)
+    eng.load_params(orc.params)
+    if world > 1:
+        ids = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        eng.init_comm(ids[0])
+    data = make_dataset(DATASET_ROWS, seed=100 + rank)      # each rank owns its own shard (weak scaling)
+    eng.upload_dataset(data, REWARD_SCALE, COST_SCALE)
+
+    K, W = args.steps, max(args.warmup, 3)
+    # ---- device-resident path
+    eng.steps(W)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.steps(K)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launches - l0
+    clk = clocks.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    sync_steps_per_s = K / ms * 1e3
+    value = sync_steps_per_s * world
+
+    # ---- end-to-end through the public trainer API with host minibatches
+    torch.manual_seed(0)
+    model = BCQL(8, 2, 1.0, CFG["a_hidden_sizes"], CFG["c_hidden_sizes"], CFG["vae_hidden_sizes"],
+                 CFG["sample_action_num"], CFG["gamma"], CFG["tau"], CFG["phi"], CFG["lmbda"], CFG["beta"], CFG["PID"],
+                 CFG["num_q"], CFG["num_qc"], CFG["cost_limit"], CFG["episode_len"], device=f"cuda:{local}")
+
+    class _Store:
+        def __init__(self):
+            self.last = None
+
+        def store(self, tab=None, **kw):
+            self.last = kw
+
+    logger = _Store()
+    trainer = BCQLTrainer(model, None, logger, actor_lr=CFG["actor_lr"], critic_lr=CFG["critic_lr"],
+                          vae_lr=CFG["vae_lr"], reward_scale=REWARD_SCALE, cost_scale=COST_SCALE,
+                          device=f"cuda:{local}", seed=99)
+    if world > 1:
+        model._bind(BATCH, trainer._lrs, seed=99, world_size=world, rank=rank)
+        ids = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        model.engine.init_comm(ids[0])
+    KE = min(K, 1000)
+    rng = np.random.default_rng(7 + rank)
+    n = data["observations"].shape[0]
+    done = np.logical_or(data["terminals"], data["timeouts"]).astype(np.float32)
+    nb = 64
+    host = []
+    for _ in range(nb):
+        idx = rng.integers(0, n, BATCH)
+        host.append([torch.from_numpy(a).pin_memory() for a in (
+            data["observations"][idx], data["next_observations"][idx], data["actions"][idx],
+            data["rewards"][idx] * np.float32(REWARD_SCALE), data["costs"][idx] * np.float32(COST_SCALE), done[idx])])
+    h2d = sum(t.numel() * 4 for t in host[0])
+    for i in range(W):
+        trainer.train_one_step(*host[i % nb])
+    barrier()
+    e0.record()
+    for i in range(KE):
+        trainer.train_one_step(*host[i % nb])     # H2D of 6 tensors + step + D2H of the stats (logger.store)
+    e1.record()
+    barrier()
+    ms_e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e = float(t.item())
+    e2e_v = KE / ms_e * 1e3 * world
+    d2h = 4 * len(eng.stat_names)
+    assert logger.last is not None and np.isfinite(list(logger.last.values())).all()
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel timing (CUDA events around every launch, this stream) -> roofline of the dominant kernel
+    peak, peak_src = measured_peaks()
+    roof = None
+    if world == 1:
+        prof = eng.profile(30)
+        agg = {}
+        for name, pms, by, fl in prof:
+            base = name.split("<")[0]
+            a = agg.setdefault(base, [0.0, 0.0, 0.0, 0])
+            a[0] += pms; a[1] += by; a[2] += fl; a[3] += 1
+        tot = sum(a[0] for a in agg.values())
+        dom = max(agg, key=lambda k_: agg[k_][0])
+        d = agg[dom]
+        achieved = d[1] / (d[0] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "launches_per_step": d[3], "share_of_step_time": d[0] / tot,
+                "bytes_per_step_algorithmic": d[1], "avg_launch_us": 1e3 * d[0] / d[3],
+                "fp32_tflops_achieved": d[2] / (d[0] * 1e-3) / 1e12,
+                "step_level": {"bytes_per_step": STEP_BYTES, "achieved": STEP_BYTES * sync_steps_per_s / 1e9,
+                               "frac": STEP_BYTES * sync_steps_per_s / 1e9 / peak,
+                               "flops_per_step": STEP_FLOPS, "tflops": STEP_FLOPS * sync_steps_per_s / 1e12},
+                "note": "k_gemm_tasks operands are L2-resident (weights+activations ~20 MB); it is FFMA-issue "
+                        "bound, not HBM bound -- see DESIGN.md and profiles/"}
+
+    # ---- CPU baseline: the oracle port of the reference step on the host cores (bounded sample)
+    cpu = None
+    if world == 1:
+        from oracle import synth
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        r2 = np.random.default_rng(0)
+        keys = ("observations", "next_observations", "actions", "rewards", "costs", "done")
+        tb = [[torch.from_numpy(b[k]) for k in keys] for b in (synth.make_batch(r2, BATCH, 8, 2) for _ in range(4))]
+        for i in range(3):
+            orc.step(*tb[i % 4])
+        t0 = time.perf_counter()
+        kk = 0
+        while time.perf_counter() - t0 < 12.0 and kk < 2000:
+            orc.step(*tb[kk % 4])
+            kk += 1
+        dt = time.perf_counter() - t0
+        cpu = {"value": kk / dt, "unit": "steps/s", "cores": cores, "kind": "port",
+               "sample": f"{kk} BCQ-Lag train steps (batch 256) of the oracle port on {cores} host threads, "
+                         "pre-collated batches (no DataLoader)"}
+
+    out = {
+        "metric": "gradient-steps/sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "per_gpu_batch": BATCH,
+                   "parallelism": f"dp{world}", "synchronous_steps_per_s": sync_steps_per_s,
+                   "value_is": "data-parallel ranks x synchronous steps/s (batch-256 step equivalents)",
+                   "dataset_rows_per_gpu": DATASET_ROWS,
+                   "l2": "inputs larger than L2: the resident dataset is 192 MB per GPU and rows are drawn at "
+                         "random; parameters/optimizer state (19 MB) are reused every step by construction"},
+        "clocks": clk, "gpu_launches": int(launches),
+        "e2e": {"value": e2e_v, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "steps": KE, "api": "osrl_b200.algorithms.BCQLTrainer.train_one_step (pinned host tensors) + stats read"},
+    }
+    if roof is not None:
+        out["roofline"] = roof
+    if cpu is not None:
+        out["cpu_baseline"] = cpu
+    print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -72,6 +72,8 @@ class BCOracle:
         loss = F.mse_loss(pred, actions)  # bc.py:47
         g = C.grads_of(loss, p, self.g_actor)
         C.require_grad(p, self.g_actor, False)
+        if getattr(self, "dp", None) is not None:
+            g = self.dp.reduce_grads(g)
         self.last_grads = dict(g)
         self.opt.step(p, g)
         return {"loss/actor_loss": loss.item()}
@@ -155,6 +157,8 @@ class BCQLOracle:
     def _update(self, name: str, loss: torch.Tensor) -> None:
         g = C.grads_of(loss, self.params, self.g[name])
         C.require_grad(self.params, self.g[name], False)
+        if getattr(self, "dp", None) is not None:
+            g = self.dp.reduce_grads(g)
         self.last_grads = getattr(self, "last_grads", {})
         self.last_grads.update(g)
         self.opt[name].step(self.params, g)
@@ -202,7 +206,7 @@ class BCQLOracle:
         qc1, qc2, _, _ = C.double_q_predict(p, "cost_critic", cfg.num_qc, self.nc, observations, act_pi)
         qc_pi, q_pi = torch.min(qc1, qc2), torch.min(q1, q2)
         with torch.no_grad():
-            mult = self.pid.control(qc_pi)
+            mult = self.pid.control(qc_pi, getattr(self, "dp", None) and self.dp.mean)
         qc_pen = ((qc_pi - self.qc_thres) * mult).mean()
         loss_a = -q_pi.mean() + qc_pen
         stats["loss/actor_loss"] = loss_a.item()
@@ -288,6 +292,8 @@ class CPQOracle:
     def _update(self, name, loss):
         g = C.grads_of(loss, self.params, self.g[name])
         C.require_grad(self.params, self.g[name], False)
+        if getattr(self, "dp", None) is not None:
+            g = self.dp.reduce_grads(g)
         self.last_grads = getattr(self, "last_grads", {})
         self.last_grads.update(g)
         self.opt[name].step(self.params, g)
@@ -440,6 +446,8 @@ class BEARLOracle:
     def _update(self, name, loss):
         g = C.grads_of(loss, self.params, self.g[name])
         C.require_grad(self.params, self.g[name], False)
+        if getattr(self, "dp", None) is not None:
+            g = self.dp.reduce_grads(g)
         self.last_grads = getattr(self, "last_grads", {})
         self.last_grads.update(g)
         self.opt[name].step(self.params, g)
@@ -503,7 +511,7 @@ class BEARLOracle:
         qc1, qc2, _, _ = C.double_q_predict(p, "cost_critic", cfg.num_qc, self.nc, observations, samp[:, 0, :])
         qc_val, q_val = torch.min(qc1, qc2), torch.min(q1, q2)
         with torch.no_grad():
-            mult = self.pid.control(qc_val)
+            mult = self.pid.control(qc_val, getattr(self, "dp", None) and self.dp.mean)
         qc_pen = ((qc_val - self.qc_thres) * mult).mean()
         if self.n_train_steps >= cfg.start_update_policy_step:
             loss_a = (-q_val + self.log_alpha.exp() * (mmd_loss - cfg.target_mmd_thresh)).mean()
@@ -515,8 +523,10 @@ class BEARLOracle:
         stats["loss/qc_penalty"] = qc_pen.item()
         stats["loss/lagrangian"] = mult.item()
         self._update("actor", loss_a)
-        self.log_alpha = self.log_alpha + cfg.alpha_lr * self.log_alpha.exp() * (
-            mmd_loss - cfg.target_mmd_thresh).mean().detach()
+        mmd_mean = (mmd_loss - cfg.target_mmd_thresh).mean().detach()
+        if getattr(self, "dp", None) is not None:
+            mmd_mean = self.dp.mean(mmd_mean)
+        self.log_alpha = self.log_alpha + cfg.alpha_lr * self.log_alpha.exp() * mmd_mean
         self.log_alpha = self.log_alpha.clamp(-5.0, 5.0)
         self.n_train_steps += 1
         stats["loss/alpha_value"] = self.log_alpha.exp().item()
@@ -526,3 +536,27 @@ class BEARLOracle:
         C.polyak(p, "actor_old", "actor", cfg.tau)
         self.last_noise = used
         return stats
+
+
+# =========================================================================== data-parallel restatement
+class DataParallel:
+    """What the N-rank engine does, restated with torch.distributed on any backend: every rank steps on
+    its B/N rows, gradients are summed and divided by N before each optimiser update, and the two
+    cross-batch scalars (PID error net.py:380, mean MMD bearl.py:261) are averaged over ranks."""
+
+    def __init__(self, dist):
+        self.dist = dist
+        self.world = dist.get_world_size()
+
+    def reduce_grads(self, g):
+        out = {}
+        for k, v in g.items():
+            t = v.clone()
+            self.dist.all_reduce(t)
+            out[k] = t / self.world
+        return out
+
+    def mean(self, x):
+        t = x.detach().clone().reshape(1)
+        self.dist.all_reduce(t)
+        return (t / self.world).reshape(())

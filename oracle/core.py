@@ -186,8 +186,10 @@ class PID:
         self.e_old = torch.zeros(())
         self.e_int = torch.zeros(())
 
-    def control(self, qc: torch.Tensor) -> torch.Tensor:
+    def control(self, qc: torch.Tensor, reduce=None) -> torch.Tensor:
         e_new = torch.mean(qc - self.thres)
+        if reduce is not None:  # data-parallel restatement: the mean runs over the global batch
+            e_new = reduce(e_new)
         e_diff = F.relu(e_new - self.e_old)
         self.e_int = F.relu(self.e_int + e_new)
         self.e_old = e_new

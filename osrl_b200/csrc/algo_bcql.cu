@@ -154,8 +154,15 @@ void build_bcql(Engine& e) {
     const int nq = cr.n, nqc = cc.n;
     DevState* ds = e.ds;
     float* st3 = e.stats + 3;
+    const float* gmean = nullptr;
+    if (e.world > 1) {  // PID error is a mean over the GLOBAL batch (net.py:380): 4-byte all-reduce before the backward
+      float* part = e.ws(4);
+      KOP(p, e, 0.0, (k_rowmin_mean<<<1, 1024, 0, s>>>(pqcv, nqc, B, thres, iw, part)));
+      emit_allreduce(e, p, part, 1);
+      gmean = part;
+    }
     KOP(p, e, 0.0, (k_bcql_actor_loss<<<1, 1024, 0, s>>>(pqv, nq, pqcv, nqc, B, thres, kp, ki, kd, ds, dpq, dpqc, st3, iw,
-                                                   nullptr)));
+                                                   gmean)));
   }
   float* da_q = e.ws((size_t)B * a); float* da_qc = e.ws((size_t)B * a);
   {

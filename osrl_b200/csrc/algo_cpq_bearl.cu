@@ -276,8 +276,16 @@ void build_bearl(Engine& e) {
     DevState* ds = e.ds;
     float* st3 = e.stats + 3;
     KOP(p, e, 0.0, (k_mmd_fwd<<<(B + 63) / 64, 64, 0, s>>>(raw_vae, raw, B, N, a, sigma, lap, mmdv)));
+    const float* gmean = nullptr;
+    if (e.world > 1) {  // PID error (net.py:380) and mean MMD (bearl.py:261) are means over the GLOBAL batch
+      float* part = e.ws(4);
+      KOP(p, e, 0.0, (k_rowmin_mean<<<1, 1024, 0, s>>>(pqcv, nqc, B, thres, iw, part)));
+      KOP(p, e, 0.0, (k_mean_sub<<<1, 1024, 0, s>>>(mmdv, B, mth, iw, part + 1)));
+      emit_allreduce(e, p, part, 2);
+      gmean = part;
+    }
     KOP(p, e, 0.0, (k_bear_actor_loss<<<1, 1024, 0, s>>>(pqv, nq, pqcv, nqc, mmdv, B, thres, kp, ki, kd, mth, alr, start, ds,
-                                                   dpq, dpqc, st3, mmd_coef, iw)));
+                                                   dpq, dpqc, st3, mmd_coef, iw, gmean)));
   }
   float* da_q = e.ws((size_t)B * a); float* da_qc = e.ws((size_t)B * a);
   {

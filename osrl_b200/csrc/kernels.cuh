@@ -346,6 +346,27 @@ static __global__ void k_critic_loss(const float* __restrict__ q, const float* _
   if (threadIdx.x == 0) stat[0] = s * inv + (extra ? extra_const_ptr_mul * extra[0] : 0.f);
 }
 
+// ------------------------------------------------------------------ data-parallel partial means (summed by NCCL)
+// out[0] = scale * mean_b( min_i q[b,i] - sub )      (PID error, net.py:380, over the GLOBAL batch)
+static __global__ void k_rowmin_mean(const float* __restrict__ q, int n, int B, float sub, float scale, float* out) {
+  __shared__ float sh[33];
+  float s = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    float m = q[(size_t)b * n];
+    for (int i = 1; i < n; ++i) m = fminf(m, q[(size_t)b * n + i]);
+    s += m - sub;
+  }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) out[0] = scale * s / (float)B;
+}
+static __global__ void k_mean_sub(const float* __restrict__ x, int B, float sub, float scale, float* out) {
+  __shared__ float sh[33];
+  float s = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) s += x[b] - sub;
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) out[0] = scale * s / (float)B;
+}
+
 // ------------------------------------------------------------------ BCQ-Lag actor loss + PID (bcql.py:181-208, net.py:376-387)
 // q [B,nq], qc [B,nqc] (all nets of each double critic).  q_pi = min over all nets; gradient flows to the argmin.
 static __global__ void k_bcql_actor_loss(const float* __restrict__ q, int nq, const float* __restrict__ qc, int nqc, int B,
@@ -604,7 +625,7 @@ static __global__ void k_bear_actor_loss(const float* __restrict__ q, int nq, co
                                          const float* __restrict__ mmd, int B, float qc_thres, float kp, float ki,
                                          float kd, float mmd_thresh, float alpha_lr, int start_step, DevState* ds,
                                          float* __restrict__ dq, float* __restrict__ dqc, float* stat /*[5]*/,
-                                         float* mmd_coef, float inv_world) {
+                                         float* mmd_coef, float inv_world, const float* global2) {
   __shared__ float sh[33];
   __shared__ float mult_s, gate_s, ealpha_s;
   float sq = 0.f, sc = 0.f, sm = 0.f;
@@ -614,8 +635,10 @@ static __global__ void k_bear_actor_loss(const float* __restrict__ q, int nq, co
     sm += mmd[b] - mmd_thresh;
   }
   const float q_mean = block_sum(sq, sh) / (float)B;
-  const float e_new = block_sum(sc, sh) / (float)B;
-  const float mmd_mean_c = block_sum(sm, sh) / (float)B;  // mean(mmd - thresh)
+  float e_new = block_sum(sc, sh) / (float)B;
+  float mmd_mean_c = block_sum(sm, sh) / (float)B;  // mean(mmd - thresh)
+  const float mmd_mean_local = mmd_mean_c;
+  if (global2) { e_new = global2[0]; mmd_mean_c = global2[1]; }  // data-parallel: means over the global batch
   if (threadIdx.x == 0) {
     const float e_diff = fmaxf(e_new - ds->pid_e_old, 0.f);
     const float e_int = fmaxf(ds->pid_e_int + e_new, 0.f);
@@ -640,8 +663,8 @@ static __global__ void k_bear_actor_loss(const float* __restrict__ q, int nq, co
   }
   const float qc_pen = block_sum(pen, sh) / (float)B;
   if (threadIdx.x == 0) {
-    stat[0] = -gate * q_mean + ealpha * mmd_mean_c + qc_pen;  // loss/actor_loss
-    stat[1] = mmd_mean_c + mmd_thresh;                         // loss/mmd_loss
+    stat[0] = -gate * q_mean + ealpha * mmd_mean_local + qc_pen;  // loss/actor_loss
+    stat[1] = mmd_mean_local + mmd_thresh;                     // loss/mmd_loss
     stat[2] = qc_pen;                                          // loss/qc_penalty
     stat[3] = mult;                                            // loss/lagrangian
     mmd_coef[0] = ealpha * invB;                               // d loss / d mmd[b]

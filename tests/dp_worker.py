@@ -1,0 +1,107 @@
+"""Data-parallel equivalence worker (run under torch.distributed, gloo on CPU or nccl on GPUs).
+
+N ranks x (B/N rows, rank-partitioned batch and noise)  ==  one rank on the concatenated batch
+(SURVEY.md section 8e).  Backend gloo: oracle-with-DataParallel vs single oracle (host-side logic, CPU).
+Backend nccl: the CUDA engine with its NCCL gradient all-reduce vs the single oracle.
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from oracle import algos, synth  # noqa: E402
+from tests.helpers import batch_tuple, l2rel, make_oracle  # noqa: E402
+
+CFGS = {
+    "bcql": dict(state_dim=8, action_dim=2, max_action=1.0, a_hidden_sizes=[32, 32], c_hidden_sizes=[32, 32],
+                 vae_hidden_sizes=48, sample_action_num=10, num_q=2, num_qc=2, actor_lr=1e-3, critic_lr=1e-3,
+                 vae_lr=1e-3, cost_limit=0.05),   # low threshold -> the PID multiplier is active
+    "bearl": dict(state_dim=8, action_dim=2, max_action=1.0, a_hidden_sizes=[32, 32], c_hidden_sizes=[32, 32],
+                  vae_hidden_sizes=48, sample_action_num=10, num_q=2, num_qc=2, actor_lr=1e-3, critic_lr=1e-3,
+                  vae_lr=1e-3, start_update_policy_step=0, cost_limit=0.05),
+    "bc": dict(state_dim=28, action_dim=2, max_action=1.0, a_hidden_sizes=[32, 32], actor_lr=1e-3),
+}
+# noise slot -> rows per batch row (slots are [B*rows, cols] b-major, so a rank takes a contiguous block)
+KEYS = ("observations", "next_observations", "actions", "rewards", "costs", "done")
+
+
+def shard(x, rank, world):
+    n = x.shape[0] // world
+    return x[rank * n:(rank + 1) * n]
+
+
+def run(algo: str, backend: str, steps: int = 3, Bg: int = 32):
+    rank, world = dist.get_rank(), dist.get_world_size()
+    cfg = CFGS[algo]
+    B = Bg // world
+    full = make_oracle(algo, cfg, 0)              # single-rank reference on the concatenated batch
+    init = {k: v.clone() for k, v in full.params.items()}
+    rng = np.random.default_rng(11)
+    torch.manual_seed(5)
+    if backend == "nccl":
+        from osrl_b200 import Engine, comm_unique_id
+        dev = int(os.environ.get("LOCAL_RANK", rank))
+        torch.cuda.set_device(dev)
+        eng = Engine(algo, batch_size=B, device=dev, seed=1, world_size=world, rank=rank, **cfg)
+        eng.load_params(init)
+        ids = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        eng.init_comm(ids[0])
+    else:
+        part = make_oracle(algo, cfg, 0)
+        part.dp = algos.DataParallel(dist)
+    worst = 0.0
+    for s in range(steps):
+        b = synth.make_batch(rng, Bg, cfg["state_dim"], cfg["action_dim"])
+        full.step(*batch_tuple(algo, b))
+        nz_full = full.last_noise
+        bl = {k: shard(v, rank, world) for k, v in b.items()}
+        nl = {}
+        for k, v in nz_full.items():
+            flat = v.reshape(Bg, -1) if v.shape[0] == Bg else v.reshape(Bg, -1)
+            nl[k] = shard(flat, rank, world).reshape(-1, *v.shape[1:]) if v.dim() > 1 else shard(v, rank, world)
+            if v.dim() >= 2 and v.shape[0] != Bg:   # [B*S, L] style: b-major blocks
+                per = v.shape[0] // Bg
+                nl[k] = v.reshape(Bg, per, *v.shape[1:])[rank * B:(rank + 1) * B].reshape(B * per, *v.shape[1:])
+        if backend == "nccl":
+            eng.step(bl, {k: v for k, v in nl.items() if k in eng.noise_layout})
+            got = eng.read_params()
+        else:
+            part.step(*batch_tuple(algo, bl), noise=nl)
+            got = {k: v.detach() for k, v in part.params.items()}
+        for k, ref in full.params.items():
+            ref = ref.detach()
+            err = float((got[k] - ref).norm())
+            bound = 1e-3 * float((ref - init[k]).norm()) + 4e-7 * float(ref.norm()) + 1e-9
+            worst = max(worst, err / bound)
+    ok = torch.tensor([1.0 if worst <= 1.0 else 0.0])
+    if backend == "nccl":
+        ok = ok.cuda()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(json.dumps({"algo": algo, "backend": backend, "world": world, "worst_ratio": worst, "ok": bool(ok.item())}))
+    return bool(ok.item())
+
+
+def _mp_entry(rank, world, algo, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    ok = run(algo, "gloo")
+    if rank == 0:
+        q.put(ok)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":   # torchrun entry (GPU): python -m torch.distributed.run ... tests/dp_worker.py bcql
+    algo_list = sys.argv[1:] or ["bcql"]
+    dist.init_process_group("nccl")
+    good = all(run(a, "nccl") for a in algo_list)
+    dist.destroy_process_group()
+    sys.exit(0 if good else 1)
