@@ -1,5 +1,6 @@
 // Engine runtime + C ABI (see include/osrl_b200.h).
 #include "engine.h"
+#include "gemm_mma.cuh"
 
 #include <dlfcn.h>
 
@@ -74,10 +75,36 @@ static void prepare_gemm() {
   OSRL_CUDA(cudaFuncSetAttribute(k_gemm_tasks<BM, BN, BK, TM, TN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  Cfg::SMEM_BYTES));
 }
+// tensor-core (3xTF32 mma.sync) tile shapes: {BM, BN, BK, WARPS_M, WARPS_N, NSTAGE}
+#define OSRL_MMA_CFG0 128, 64, 16, 4, 2, 4
+#define OSRL_MMA_CFG1 64, 64, 32, 2, 4, 4
+#define OSRL_MMA_CFG2 32, 32, 32, 2, 2, 6
+template <int BM, int BN, int BK, int WM, int WN, int NS>
+static void launch_mma(const GemmTask* d, int ntasks, int tiles, cudaStream_t s) {
+  using Cfg = MmaCfg<BM, BN, BK, WM, WN, NS>;
+  k_gemm_mma<BM, BN, BK, WM, WN, NS><<<tiles, Cfg::NT, Cfg::SMEM_BYTES, s>>>(d, ntasks);
+}
+template <int BM, int BN, int BK, int WM, int WN, int NS>
+static void prepare_mma() {
+  using Cfg = MmaCfg<BM, BN, BK, WM, WN, NS>;
+  OSRL_CUDA(cudaFuncSetAttribute(k_gemm_mma<BM, BN, BK, WM, WN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::SMEM_BYTES));
+}
+// OSRL_GEMM=ffma selects the CUDA-core kernel (gemm.cuh); default is the 3xTF32 tensor-core kernel
+static bool use_mma() {
+  static const bool v = [] {
+    const char* e = getenv("OSRL_GEMM");
+    return !(e && std::string(e) == "ffma");
+  }();
+  return v;
+}
 void prepare_kernels() {
   prepare_gemm<OSRL_GEMM_CFG0>();
   prepare_gemm<OSRL_GEMM_CFG1>();
   prepare_gemm<OSRL_GEMM_CFG2>();
+  prepare_mma<OSRL_MMA_CFG0>();
+  prepare_mma<OSRL_MMA_CFG1>();
+  prepare_mma<OSRL_MMA_CFG2>();
 }
 static int count_tiles(std::vector<GemmTask>& ts, int BM, int BN, bool assign) {
   int tot = 0;
@@ -113,10 +140,19 @@ void emit_gemm(Engine& e, Program& p, const std::vector<GemmTask>& tasks_in) {
   }
   static const char* names[3] = {"k_gemm_tasks<128,64,16,8,4,4>", "k_gemm_tasks<64,64,32,4,4,4>",
                                  "k_gemm_tasks<32,32,32,2,2,6>"};
-  p.add(names[cfg], bytes, flops, true, [=](cudaStream_t s) {
-    if (cfg == 0) launch_gemm<OSRL_GEMM_CFG0>(d, nt, tiles, s);
-    else if (cfg == 1) launch_gemm<OSRL_GEMM_CFG1>(d, nt, tiles, s);
-    else launch_gemm<OSRL_GEMM_CFG2>(d, nt, tiles, s);
+  static const char* mnames[3] = {"k_gemm_mma<128,64,16,4,2,4>", "k_gemm_mma<64,64,32,2,4,4>",
+                                  "k_gemm_mma<32,32,32,2,2,6>"};
+  const bool mma = use_mma();
+  p.add(mma ? mnames[cfg] : names[cfg], bytes, flops, true, [=](cudaStream_t s) {
+    if (mma) {
+      if (cfg == 0) launch_mma<OSRL_MMA_CFG0>(d, nt, tiles, s);
+      else if (cfg == 1) launch_mma<OSRL_MMA_CFG1>(d, nt, tiles, s);
+      else launch_mma<OSRL_MMA_CFG2>(d, nt, tiles, s);
+    } else {
+      if (cfg == 0) launch_gemm<OSRL_GEMM_CFG0>(d, nt, tiles, s);
+      else if (cfg == 1) launch_gemm<OSRL_GEMM_CFG1>(d, nt, tiles, s);
+      else launch_gemm<OSRL_GEMM_CFG2>(d, nt, tiles, s);
+    }
     ep->launches++;
   });
 }
