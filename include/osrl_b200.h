@@ -119,6 +119,23 @@ typedef struct osrl_noise {
   const float* slot[OSRL_MAX_NOISE];
 } osrl_noise;
 
+/* One collated SequenceDataset minibatch = the positional arguments of CDTTrainer.train_one_step
+ * (cdt.py:343-344): states [B,T,o], actions [B,T,a], returns [B,T], costs_return [B,T], time_steps [B,T]
+ * int64, mask [B,T] (float32 here; the reference yields float64), episode_cost [B] (unused without
+ * cost_prefix, may be NULL), costs [B,T]. */
+typedef struct osrl_seq_batch {
+  int32_t rows, seq_len;
+  int32_t on_host;
+  const float* states;
+  const float* actions;
+  const float* returns;
+  const float* costs_return;
+  const int64_t* time_steps;
+  const float* mask;
+  const float* episode_cost;
+  const float* costs;
+} osrl_seq_batch;
+
 typedef struct osrl_engine osrl_engine;
 
 int osrl_abi_version(void);
@@ -149,6 +166,9 @@ int osrl_gather(osrl_engine* e, const int64_t* idx, int n, int idx_on_host, osrl
 /* Replaces <Algo>Trainer.train_one_step (bc.py:103-109, bcql.py:283-306, cpq.py:294-313,
  * bearl.py:389-412): all sub-updates + Polyak for one minibatch, no host sync. */
 int osrl_step(osrl_engine* e, const osrl_batch* batch, const osrl_noise* noise, void* stream);
+/* Replaces CDTTrainer.train_one_step (cdt.py:343-418): forward, losses, backward, clip_grad_norm_, AdamW with
+ * LR warm-up, temperature Adam -- one sequence minibatch, no host sync. */
+int osrl_step_seq(osrl_engine* e, const osrl_seq_batch* batch, void* stream);
 /* k steps with minibatches drawn on the device from the resident dataset (replaces the loop
  * body train_bcql.py:142-148 including DataLoader draw and .to(device)). */
 int osrl_steps(osrl_engine* e, int k, void* stream);

@@ -192,8 +192,9 @@ class CDTOracle:
         # clip_grad_norm_ (cdt.py:399)
         total = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(v) for v in g.values()]))
         coef = torch.clamp(cfg.clip_grad / (total + 1e-6), max=1.0)
+        self.last_grads = g                       # raw gradients (what the engine keeps in its G section)
+        self.last_clip_coef = float(coef)
         g = {k: v * coef for k, v in g.items()}
-        self.last_grads = g
         lr = cfg.learning_rate * min((self.steps + 1) / cfg.lr_warmup_steps, 1)       # LambdaLR, cdt.py:327-330
         self.opt.step(p, g, lr=lr)
         # temperature Adam (cdt.py:402-407), float64 scalar

@@ -58,6 +58,12 @@ class Batch(C.Structure):
                 ("costs", C.c_void_p), ("done", C.c_void_p)]
 
 
+class SeqBatch(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("seq_len", C.c_int32), ("on_host", C.c_int32), ("states", C.c_void_p),
+                ("actions", C.c_void_p), ("returns", C.c_void_p), ("costs_return", C.c_void_p),
+                ("time_steps", C.c_void_p), ("mask", C.c_void_p), ("episode_cost", C.c_void_p), ("costs", C.c_void_p)]
+
+
 class Noise(C.Structure):
     _fields_ = [("on_host", C.c_int32), ("slot", C.c_void_p * OSRL_MAX_NOISE)]
 
@@ -76,6 +82,7 @@ SYMBOLS = [
     ("osrl_buffer_upload", C.c_int, [C.c_void_p, C.POINTER(DatasetView)]),
     ("osrl_gather", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(Batch), C.c_void_p]),
     ("osrl_step", C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Noise), C.c_void_p]),
+    ("osrl_step_seq", C.c_int, [C.c_void_p, C.POINTER(SeqBatch), C.c_void_p]),
     ("osrl_steps", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     ("osrl_stat_names", C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_int)]),
     ("osrl_stats", C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int), C.c_void_p]),

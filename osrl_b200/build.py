@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libosrl_b200.so")
-SOURCES = ["plan.cu", "engine.cu", "blocks.cu", "algo_bcql.cu", "algo_cpq_bearl.cu"]
-HEADERS = ["engine.h", "gemm.cuh", "gemm_mma.cuh", "kernels.cuh", os.path.join("..", "..", "include", "osrl_b200.h")]
+SOURCES = ["plan.cu", "engine.cu", "blocks.cu", "algo_bcql.cu", "algo_cpq_bearl.cu", "algo_cdt.cu"]
+HEADERS = ["engine.h", "gemm.cuh", "gemm_mma.cuh", "kernels.cuh", "cdt_kernels.cuh", os.path.join("..", "..", "include", "osrl_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -1,0 +1,372 @@
+// CDT kernels (sm_100a): LayerNorm fwd/bwd, 40-token causal+padding attention fwd/bwd, token
+// embedding glue, head losses, gradient-norm clip.  Replaces TransformerBlock (net.py:391-441),
+// CDT.forward (cdt.py:166-265) and the loss part of CDTTrainer.train_one_step (cdt.py:343-418).
+// The linear projections (98 % of CDT's FLOPs) run on the shared multi-task GEMM.
+#pragma once
+#include "kernels.cuh"
+
+namespace osrl {
+
+// ------------------------------------------------------------------ token glue
+// te[bt,:] = timestep_emb[time_steps[bt],:] (cdt.py:180); ctg_t = 50 - ctg (cost_transform, cdt.py:79,187)
+static __global__ void k_cdt_prep(const long long* __restrict__ ts, const float* __restrict__ ctg, int BT, int E,
+                                  const float* __restrict__ table, int table_rows, float* __restrict__ te,
+                                  float* __restrict__ ctg_t) {
+  const int n = BT * E;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int bt = e / E, c = e % E;
+    long long r = ts[bt];
+    r = r < 0 ? 0 : (r >= table_rows ? table_rows - 1 : r);
+    te[e] = table[(size_t)r * E + c];
+    if (c == 0) ctg_t[bt] = 50.f - ctg[bt];
+  }
+}
+// d timestep_emb[ts[bt], :] += sum over the 4 tokens of step bt of d x0   (embedding backward)
+static __global__ void k_cdt_te_scatter(const long long* __restrict__ ts, const float* __restrict__ dx0, int BT, int E,
+                                        int table_rows, float* __restrict__ gtable) {
+  const int n = BT * E;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const int bt = e / E, c = e % E;
+    long long r = ts[bt];
+    r = r < 0 ? 0 : (r >= table_rows ? table_rows - 1 : r);
+    const float* p = dx0 + (size_t)bt * 4 * E + c;
+    atomicAdd(gtable + (size_t)r * E + c, p[0] + p[E] + p[2 * E] + p[3 * E]);
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm (eps 1e-5, biased variance)
+static __global__ void k_ln_fwd(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
+                                float* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int rows,
+                                int E) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= rows) return;
+  const float* xr = x + (size_t)w * E;
+  float s = 0.f;
+  for (int c = lane; c < E; c += 32) s += xr[c];
+  s = warp_sum(s);
+  const float mu = s / (float)E;
+  float v = 0.f;
+  for (int c = lane; c < E; c += 32) { const float d = xr[c] - mu; v += d * d; }
+  v = warp_sum(v);
+  const float rs = rsqrtf(v / (float)E + 1e-5f);
+  if (lane == 0) { mean[w] = mu; rstd[w] = rs; }
+  float* yr = y + (size_t)w * E;
+  for (int c = lane; c < E; c += 32) yr[c] = (xr[c] - mu) * rs * g[c] + b[c];
+}
+// dx (= or +=) and per-block partial sums of d gamma / d beta.  blockDim = 256 (8 warps), E = 32*PER <= 512.
+#define OSRL_LN_MAXE 512
+template <int PER>
+static __global__ void k_ln_bwd(const float* __restrict__ dy, const float* __restrict__ x,
+                                const float* __restrict__ mean, const float* __restrict__ rstd,
+                                const float* __restrict__ g, float* __restrict__ dx, int accumulate,
+                                float* __restrict__ part_dg, float* __restrict__ part_db, int rows, int E) {
+  __shared__ float sg[OSRL_LN_MAXE], sb[OSRL_LN_MAXE];
+  for (int c = threadIdx.x; c < E; c += blockDim.x) { sg[c] = 0.f; sb[c] = 0.f; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float ag[PER], ab[PER];
+  constexpr int per = PER;
+#pragma unroll
+  for (int q = 0; q < per; ++q) { ag[q] = 0.f; ab[q] = 0.f; }
+  for (int r = blockIdx.x * wpb + wib; r < rows; r += gridDim.x * wpb) {
+    const float mu = mean[r], rs = rstd[r];
+    const float* xr = x + (size_t)r * E;
+    const float* dr = dy + (size_t)r * E;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < per; ++q) {
+      const int c = lane + 32 * q;
+      const float xh = (xr[c] - mu) * rs, dg = dr[c] * g[c];
+      s1 += dg; s2 += dg * xh;
+      ag[q] += dr[c] * xh; ab[q] += dr[c];
+    }
+    s1 = warp_sum(s1) / (float)E; s2 = warp_sum(s2) / (float)E;
+    float* dxr = dx + (size_t)r * E;
+#pragma unroll
+    for (int q = 0; q < per; ++q) {
+      const int c = lane + 32 * q;
+      const float xh = (xr[c] - mu) * rs;
+      const float v = rs * (dr[c] * g[c] - s1 - xh * s2);
+      dxr[c] = accumulate ? dxr[c] + v : v;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < per; ++q) { atomicAdd(&sg[lane + 32 * q], ag[q]); atomicAdd(&sb[lane + 32 * q], ab[q]); }
+  __syncthreads();
+  for (int c = threadIdx.x; c < E; c += blockDim.x) {
+    part_dg[(size_t)blockIdx.x * E + c] = sg[c];
+    part_db[(size_t)blockIdx.x * E + c] = sb[c];
+  }
+}
+static __global__ void k_ln_param_reduce(const float* __restrict__ part_dg, const float* __restrict__ part_db, int nblk,
+                                         int E, float* __restrict__ dg, float* __restrict__ db) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= E) return;
+  float a = 0.f, b = 0.f;
+  for (int k = 0; k < nblk; ++k) { a += part_dg[(size_t)k * E + c]; b += part_db[(size_t)k * E + c]; }
+  dg[c] = a; db[c] = b;
+}
+
+// ------------------------------------------------------------------ attention (nn.MultiheadAttention, net.py:406-441)
+// qkv [B, L, 3E] (q | k | v, head h at columns h*D..), key j is attendable by query i iff j <= i and
+// the step of token j is valid (key_padding_mask = ~mask repeated over the 4 tokens of a step, cdt.py:203-205).
+// One CTA per batch element, one thread per (head, query/key row).
+template <int D>
+static __global__ void k_attn_fwd(const float* __restrict__ qkv, const float* __restrict__ mask, int L, int H,
+                                  int tok_per_step, float* __restrict__ out, float* __restrict__ lse) {
+  extern __shared__ float sm[];
+  const int E = H * D, b = blockIdx.x, T = L / tok_per_step;
+  float* Ks = sm;              // [L][E]
+  float* Vs = sm + L * E;      // [L][E]
+  const float* base = qkv + (size_t)b * L * 3 * E;
+  for (int e = threadIdx.x; e < L * E; e += blockDim.x) {
+    const int j = e / E, c = e % E;
+    Ks[e] = base[(size_t)j * 3 * E + E + c];
+    Vs[e] = base[(size_t)j * 3 * E + 2 * E + c];
+  }
+  __syncthreads();
+  const int h = threadIdx.x / L, i = threadIdx.x % L;
+  if (h >= H) return;
+  float q[D], acc[D];
+#pragma unroll
+  for (int c = 0; c < D; ++c) { q[c] = base[(size_t)i * 3 * E + h * D + c]; acc[c] = 0.f; }
+  const float scale = rsqrtf((float)D);
+  float m = -INFINITY, l = 0.f;
+  for (int j = 0; j <= i; ++j) {
+    if (mask[(size_t)b * T + j / tok_per_step] <= 0.f) continue;
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < D; ++c) s = fmaf(q[c], Ks[j * E + h * D + c], s);
+    s *= scale;
+    const float mn = fmaxf(m, s);
+    const float corr = expf(m - mn), p = expf(s - mn);
+    l = l * corr + p;
+#pragma unroll
+    for (int c = 0; c < D; ++c) acc[c] = acc[c] * corr + p * Vs[j * E + h * D + c];
+    m = mn;
+  }
+  const float inv = 1.f / l;
+#pragma unroll
+  for (int c = 0; c < D; ++c) out[((size_t)b * L + i) * E + h * D + c] = acc[c] * inv;
+  lse[((size_t)b * H + h) * L + i] = m + logf(l);
+}
+
+template <int D>
+static __global__ void k_attn_bwd(const float* __restrict__ qkv, const float* __restrict__ mask, int L, int H,
+                                  int tok_per_step, const float* __restrict__ out, const float* __restrict__ dout,
+                                  const float* __restrict__ lse, float* __restrict__ dqkv) {
+  extern __shared__ float sm[];
+  const int E = H * D, b = blockIdx.x, T = L / tok_per_step;
+  float* Qs = sm;
+  float* Ks = sm + L * E;
+  float* Vs = sm + 2 * L * E;
+  float* dOs = sm + 3 * L * E;
+  float* Ls = sm + 4 * L * E;      // [H*L] log-sum-exp
+  float* Ds = Ls + H * L;          // [H*L] rowsum(dO * O)
+  const float* base = qkv + (size_t)b * L * 3 * E;
+  for (int e = threadIdx.x; e < L * E; e += blockDim.x) {
+    const int j = e / E, c = e % E;
+    Qs[e] = base[(size_t)j * 3 * E + c];
+    Ks[e] = base[(size_t)j * 3 * E + E + c];
+    Vs[e] = base[(size_t)j * 3 * E + 2 * E + c];
+    dOs[e] = dout[((size_t)b * L + j) * E + c];
+  }
+  const int h = threadIdx.x / L, i = threadIdx.x % L;
+  const bool active = h < H;
+  const float scale = rsqrtf((float)D);
+  if (active) {
+    float d = 0.f;
+#pragma unroll
+    for (int c = 0; c < D; ++c)
+      d += dout[((size_t)b * L + i) * E + h * D + c] * out[((size_t)b * L + i) * E + h * D + c];
+    Ds[h * L + i] = d;
+    Ls[h * L + i] = lse[((size_t)b * H + h) * L + i];
+  }
+  __syncthreads();
+  float* dbase = dqkv + (size_t)b * L * 3 * E;
+  if (active) {
+    // ---- dq for query row i
+    float dq[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) dq[c] = 0.f;
+    const float li = Ls[h * L + i], di = Ds[h * L + i];
+    for (int j = 0; j <= i; ++j) {
+      if (mask[(size_t)b * T + j / tok_per_step] <= 0.f) continue;
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        s = fmaf(Qs[i * E + h * D + c], Ks[j * E + h * D + c], s);
+        dp = fmaf(dOs[i * E + h * D + c], Vs[j * E + h * D + c], dp);
+      }
+      const float p = expf(s * scale - li);
+      const float ds = p * (dp - di) * scale;
+#pragma unroll
+      for (int c = 0; c < D; ++c) dq[c] = fmaf(ds, Ks[j * E + h * D + c], dq[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) dbase[(size_t)i * 3 * E + h * D + c] = dq[c];
+    // ---- dk, dv for key row j = i
+    const int j = i;
+    float dk[D], dv[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) { dk[c] = 0.f; dv[c] = 0.f; }
+    if (mask[(size_t)b * T + j / tok_per_step] > 0.f) {
+      for (int r = j; r < L; ++r) {
+        float s = 0.f, dp = 0.f;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          s = fmaf(Qs[r * E + h * D + c], Ks[j * E + h * D + c], s);
+          dp = fmaf(dOs[r * E + h * D + c], Vs[j * E + h * D + c], dp);
+        }
+        const float p = expf(s * scale - Ls[h * L + r]);
+        const float ds = p * (dp - Ds[h * L + r]) * scale;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          dk[c] = fmaf(ds, Qs[r * E + h * D + c], dk[c]);
+          dv[c] = fmaf(p, dOs[r * E + h * D + c], dv[c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      dbase[(size_t)j * 3 * E + E + h * D + c] = dk[c];
+      dbase[(size_t)j * 3 * E + 2 * E + h * D + c] = dv[c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ head losses (cdt.py:357-394, 402-418)
+// mh [BT, 2a] = (mu | log_std) on the state tokens; ah [BT, 2+o] = (cost logits | next-state prediction) on
+// the action tokens.  Single CTA.  Writes d mh, d ah, the 9 logged stats, and steps log_temperature (Adam).
+__device__ __forceinline__ double block_sum_d(double v, double* sh /*[33]*/) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    double x = (l < (int)(blockDim.x >> 5)) ? sh[l] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (l == 0) sh[32] = x;
+  }
+  __syncthreads();
+  return sh[32];
+}
+static __global__ void k_cdt_loss(const float* __restrict__ mh, const float* __restrict__ ah,
+                                  const float* __restrict__ actions, const float* __restrict__ costs,
+                                  const float* __restrict__ states, const float* __restrict__ mask, int B, int T, int a,
+                                  int o, float w_cost, float w_state, float target_entropy, float base_lr, int warmup,
+                                  int group, DevState* ds, float* __restrict__ dmh, float* __restrict__ dah,
+                                  float* __restrict__ stat) {
+  __shared__ double sh[33];
+  const int BT = B * T, wa = 2 + o;
+  const double HALF_LOG_2PI = 0.91893853320467274178;
+  double s_valid = 0, s_lp = 0, s_ent = 0, s_nll = 0, s_corr = 0, s_sl = 0;
+  for (int r = threadIdx.x; r < BT; r += blockDim.x) {
+    const float m = mask[r];
+    if (m > 0.f) {
+      s_valid += 1.0;
+      for (int j = 0; j < a; ++j) {
+        const float mu = mh[(size_t)r * 2 * a + j], ls = mh[(size_t)r * 2 * a + a + j];
+        const float d = actions[(size_t)r * a + j] - mu;
+        const float var = expf(2.f * ls);
+        s_lp += (double)(-(d * d) / (2.f * var) - ls) - HALF_LOG_2PI;
+        s_ent += 0.5 + HALF_LOG_2PI + (double)ls;
+      }
+    }
+    const float z0 = ah[(size_t)r * wa], z1 = ah[(size_t)r * wa + 1];
+    const float mx = fmaxf(z0, z1);
+    const float lse = mx + logf(expf(z0 - mx) + expf(z1 - mx));
+    const int c = (int)costs[r];
+    s_nll += (double)((lse - (c ? z1 : z0)) * m);
+    const int pred = z1 > z0 ? 1 : 0;
+    s_corr += (pred == c) ? (double)m : 0.0;
+    if ((r % T) < T - 1) {
+      double e = 0;
+      for (int j = 0; j < o; ++j) {
+        const float d = ah[(size_t)r * wa + 2 + j] - states[(size_t)(r + 1) * o + j];
+        e += (double)d * d;
+      }
+      s_sl += e * (double)m;
+    }
+  }
+  const double n_valid = block_sum_d(s_valid, sh);
+  const double ll = block_sum_d(s_lp, sh) / (n_valid * a);
+  const double ent = block_sum_d(s_ent, sh) / (n_valid * a);
+  const double cost_loss = block_sum_d(s_nll, sh) / (double)BT;
+  const double acc = block_sum_d(s_corr, sh) / n_valid;
+  const double state_loss = (T > 1) ? block_sum_d(s_sl, sh) / ((double)B * (T - 1) * o) : 0.0;
+  const double temp = exp(ds->log_temperature);
+  const double act_loss = -(ll + temp * ent);
+  const float ca = (float)(1.0 / (n_valid * a));
+  const float tf = (float)temp;
+  const float cc = w_cost / (float)BT;
+  const float cs = (T > 1) ? w_state * 2.f / ((float)B * (T - 1) * o) : 0.f;
+  for (int r = threadIdx.x; r < BT; r += blockDim.x) {
+    const float m = mask[r] > 0.f ? 1.f : 0.f;
+    for (int j = 0; j < a; ++j) {
+      const float mu = mh[(size_t)r * 2 * a + j], ls = mh[(size_t)r * 2 * a + a + j];
+      const float d = actions[(size_t)r * a + j] - mu;
+      const float iv = expf(-2.f * ls);
+      dmh[(size_t)r * 2 * a + j] = -m * ca * d * iv;
+      dmh[(size_t)r * 2 * a + a + j] = -m * ca * ((d * d * iv - 1.f) + tf);
+    }
+    const float z0 = ah[(size_t)r * wa], z1 = ah[(size_t)r * wa + 1];
+    const float mx = fmaxf(z0, z1);
+    const float e0 = expf(z0 - mx), e1 = expf(z1 - mx);
+    const float inv = 1.f / (e0 + e1);
+    const int c = (int)costs[r];
+    const float mm = mask[r];
+    dah[(size_t)r * wa] = cc * mm * (e0 * inv - (c == 0 ? 1.f : 0.f));
+    dah[(size_t)r * wa + 1] = cc * mm * (e1 * inv - (c == 1 ? 1.f : 0.f));
+    for (int j = 0; j < o; ++j) {
+      float g = 0.f;
+      if ((r % T) < T - 1) g = cs * mm * (ah[(size_t)r * wa + 2 + j] - states[(size_t)(r + 1) * o + j]);
+      dah[(size_t)r * wa + 2 + j] = g;
+    }
+  }
+  if (threadIdx.x == 0) {
+    stat[0] = (float)(-ll);          // nll
+    stat[1] = (float)ent;            // ent
+    stat[2] = (float)temp;           // ent_reg
+    stat[3] = (float)(act_loss + w_cost * cost_loss + w_state * state_loss);  // all_loss
+    stat[4] = (float)act_loss;
+    stat[5] = (float)cost_loss;
+    stat[6] = (float)acc;
+    stat[7] = (float)state_loss;
+    const int t = ds->adam_t[group];                     // already incremented for this step
+    const double f = (double)(t + 1) / (double)warmup;
+    stat[8] = (float)((double)base_lr * (f < 1.0 ? f : 1.0));   // scheduler.get_last_lr() after scheduler.step()
+    // temperature: Adam(lr 1e-4) on temp * (entropy - target).detach()   (cdt.py:402-407)
+    const double g = temp * (ent - (double)target_entropy);
+    const int tt = t;                                     // temperature optimiser steps in lock-step
+    const double m1 = ds->temp_m + (1.0 - 0.9) * (g - ds->temp_m);
+    const double v1 = 0.999 * ds->temp_v + (1.0 - 0.999) * g * g;
+    const double denom = sqrt(v1) / sqrt(1.0 - pow(0.999, (double)tt)) + 1e-8;
+    ds->log_temperature = ds->log_temperature - (1e-4 / (1.0 - pow(0.9, (double)tt))) * m1 / denom;
+    ds->temp_m = m1;
+    ds->temp_v = v1;
+  }
+}
+
+// ------------------------------------------------------------------ clip_grad_norm_ (cdt.py:399)
+static __global__ void k_sumsq_partial(const float* __restrict__ g, long long n, float* __restrict__ part) {
+  __shared__ float sh[33];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    s += g[i] * g[i];
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+static __global__ void k_clip_coef(const float* __restrict__ part, int n, float max_norm, float* coef) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s = 0;
+  for (int i = 0; i < n; ++i) s += (double)part[i];
+  const float total = (float)sqrt(s);
+  const float c = max_norm / (total + 1e-6f);
+  coef[0] = c < 1.f ? c : 1.f;
+}
+
+}  // namespace osrl

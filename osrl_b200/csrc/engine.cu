@@ -91,12 +91,9 @@ static void prepare_mma() {
                                  Cfg::SMEM_BYTES));
 }
 // OSRL_GEMM=ffma selects the CUDA-core kernel (gemm.cuh); default is the 3xTF32 tensor-core kernel
-static bool use_mma() {
-  static const bool v = [] {
-    const char* e = getenv("OSRL_GEMM");
-    return !(e && std::string(e) == "ffma");
-  }();
-  return v;
+static bool use_mma() {   // read when an engine's program is built
+  const char* e = getenv("OSRL_GEMM");
+  return !(e && std::string(e) == "ffma");
 }
 void prepare_kernels() {
   prepare_gemm<OSRL_GEMM_CFG0>();
@@ -182,7 +179,7 @@ void emit_copy(Engine& e, Program& p, const std::vector<CopyTask>& tasks) {
     ep->launches++;
   });
 }
-void emit_adam(Engine& e, Program& p, int group, int64_t begin, int64_t end, bool polyak) {
+void emit_adam(Engine& e, Program& p, int group, int64_t begin, int64_t end, bool polyak, const float* clip_coef) {
   const Group& g = e.plan.groups[group];
   const int64_t n4 = (end - begin) / 4;
   const int blocks = (int)std::min<int64_t>((n4 + 255) / 256, 148 * 8);
@@ -193,7 +190,7 @@ void emit_adam(Engine& e, Program& p, int group, int64_t begin, int64_t end, boo
   p.add(polyak ? "k_adam+polyak" : "k_adam", bytes, 0.0, true, [=](cudaStream_t s) {
     k_adam<<<blocks, 256, 0, s>>>(ep->P + begin, ep->G + begin, ep->M + begin, ep->V + begin, ep->T + begin, n4, ep->ds,
                                   group, (float)g.beta1, (float)g.beta2, (float)(1.0 - g.beta1), (float)(1.0 - g.beta2),
-                                  g.eps, g.wd, tau, polyak ? 1 : 0, 1.f, nullptr);
+                                  g.eps, g.wd, tau, polyak ? 1 : 0, 1.f, clip_coef);
     ep->launches++;
   });
 }
@@ -308,6 +305,7 @@ static void build_program(Engine& e) {
     case OSRL_ALGO_BCQL: build_bcql(e); break;
     case OSRL_ALGO_CPQ: build_cpq(e); break;
     case OSRL_ALGO_BEARL: build_bearl(e); break;
+    case OSRL_ALGO_CDT: build_cdt(e); break;
     default: throw Err(OSRL_ERR_UNSUPPORTED, "algorithm not supported");
   }
 }
@@ -338,7 +336,7 @@ static Engine* create(const osrl_config& cfg, int device) {
     if (cfg.algo == OSRL_ALGO_CDT) {
       DevState h;
       memset(&h, 0, sizeof(h));
-      h.log_temperature = logf(cfg.init_temperature);
+      h.log_temperature = log((double)cfg.init_temperature);
       OSRL_CUDA(cudaMemcpy(e->ds, &h, sizeof(h), cudaMemcpyHostToDevice));
     }
     std::vector<AdamGroupCfg> gc;
@@ -348,6 +346,13 @@ static Engine* create(const osrl_config& cfg, int device) {
     e->b_obs = e->ws((size_t)B * o); e->b_nobs = e->ws((size_t)B * o); e->b_act = e->ws((size_t)B * a);
     e->b_rew = e->ws(B); e->b_cost = e->ws(B); e->b_done = e->ws(B);
     e->b_idx = (int64_t*)e->ws((size_t)B * 2);
+    if (cfg.algo == OSRL_ALGO_CDT) {
+      OSRL_REQUIRE(cfg.world_size == 1, "CDT data-parallel is not built yet");
+      const size_t BT = (size_t)B * cfg.seq_len;
+      e->s_states = e->ws(BT * o); e->s_actions = e->ws(BT * a); e->s_returns = e->ws(BT); e->s_ctg = e->ws(BT);
+      e->s_mask = e->ws(BT); e->s_costs = e->ws(BT);
+      e->s_ts = (long long*)e->ws(BT * 2);
+    }
     std::vector<NoiseSlot> slots;
     int si = 0;
     for (auto& ns : e->plan.noise) {
@@ -612,6 +617,7 @@ int osrl_step(osrl_engine* h, const osrl_batch* b, const osrl_noise* nz, void* s
   OSRL_TRY
   OSRL_REQUIRE(h && b, "null argument");
   Engine& e = *h->e;
+  OSRL_REQUIRE(e.plan.cfg.algo != OSRL_ALGO_CDT, "CDT steps take a sequence batch: use osrl_step_seq");
   OSRL_REQUIRE(b->rows == e.B, "batch rows != engine batch_size");
   OSRL_REQUIRE(b->observations && b->actions, "observations/actions required");
   const bool bc = e.plan.cfg.algo == OSRL_ALGO_BC;
@@ -658,10 +664,37 @@ int osrl_step(osrl_engine* h, const osrl_batch* b, const osrl_noise* nz, void* s
   OSRL_CATCH
 }
 
+int osrl_step_seq(osrl_engine* h, const osrl_seq_batch* b, void* stream) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && b, "null argument");
+  Engine& e = *h->e;
+  OSRL_REQUIRE(e.plan.cfg.algo == OSRL_ALGO_CDT, "osrl_step_seq is the CDT entry point");
+  OSRL_REQUIRE(b->rows == e.B && b->seq_len == e.plan.cfg.seq_len, "batch rows / seq_len differ from the engine config");
+  OSRL_REQUIRE(b->states && b->actions && b->returns && b->costs_return && b->time_steps && b->mask && b->costs,
+               "incomplete sequence batch");
+  OSRL_CUDA(cudaSetDevice(e.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t BT = (size_t)e.B * b->seq_len;
+  const int o = e.plan.cfg.obs_dim, a = e.plan.cfg.act_dim;
+  const cudaMemcpyKind kind = b->on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  OSRL_CUDA(cudaMemcpyAsync(e.s_states, b->states, BT * o * sizeof(float), kind, s));
+  OSRL_CUDA(cudaMemcpyAsync(e.s_actions, b->actions, BT * a * sizeof(float), kind, s));
+  OSRL_CUDA(cudaMemcpyAsync(e.s_returns, b->returns, BT * sizeof(float), kind, s));
+  OSRL_CUDA(cudaMemcpyAsync(e.s_ctg, b->costs_return, BT * sizeof(float), kind, s));
+  OSRL_CUDA(cudaMemcpyAsync(e.s_ts, b->time_steps, BT * sizeof(long long), kind, s));
+  OSRL_CUDA(cudaMemcpyAsync(e.s_mask, b->mask, BT * sizeof(float), kind, s));
+  OSRL_CUDA(cudaMemcpyAsync(e.s_costs, b->costs, BT * sizeof(float), kind, s));
+  if (!e.g_body) e.g_body = capture(e, false);
+  OSRL_CUDA(cudaGraphLaunch(e.g_body, s));
+  e.launches += kernels_per_step(e, false);
+  OSRL_CATCH
+}
+
 int osrl_steps(osrl_engine* h, int k, void* stream) {
   OSRL_TRY
   OSRL_REQUIRE(h && k >= 0, "bad argument");
   Engine& e = *h->e;
+  OSRL_REQUIRE(e.plan.cfg.algo != OSRL_ALGO_CDT, "device-side sequence sampling is not built yet: use osrl_step_seq");
   OSRL_REQUIRE(e.ds_rows, "osrl_steps needs a resident dataset (osrl_buffer_upload)");
   OSRL_CUDA(cudaSetDevice(e.device));
   cudaStream_t s = (cudaStream_t)stream;
@@ -725,7 +758,7 @@ int osrl_scalars_set(osrl_engine* h, const double* in, int n) {
   DevState d;
   OSRL_CUDA(cudaMemcpy(&d, e.ds, sizeof(d), cudaMemcpyDeviceToHost));
   d.step = (unsigned long long)in[0]; d.pid_e_old = (float)in[1]; d.pid_e_int = (float)in[2];
-  d.log_alpha = (float)in[3]; d.n_train_steps = (int)in[4]; d.log_temperature = (float)in[5];
+  d.log_alpha = (float)in[3]; d.n_train_steps = (int)in[4]; d.log_temperature = in[5];
   for (int i = 0; i < 4; ++i) d.adam_t[i] = (int)in[6 + i];
   OSRL_CUDA(cudaMemcpy(e.ds, &d, sizeof(d), cudaMemcpyHostToDevice));
   OSRL_CATCH

@@ -47,6 +47,16 @@ struct EnsLay {
 struct VaeLay { Lin e1, e2, heads /*[2L, V]: mean rows then log_std rows*/, d1, d2, d3; };
 struct SqActorLay { MlpLay trunk; Lin heads; /*[2a, H]: mu rows then log_std rows*/ };
 
+struct CdtLay {  // CDT parameter offsets (cdt.py:45-148)
+  int E = 0, te_rows = 0;
+  int64_t emb_norm_w = 0, emb_norm_b = 0, out_norm_w = 0, out_norm_b = 0, te = 0;
+  Lin state_emb, action_emb, cost_emb, return_emb;
+  struct Blk { int64_t n1w, n1b, n2w, n2b; Lin in_proj, out_proj, fc1, fc2; };
+  std::vector<Blk> blocks;
+  Lin act_head;  // [2a, E]: mu rows then log_std rows (DiagGaussianActor, net.py:509-533)
+  Lin aux_head;  // [2+o, E]: cost_pred_head rows then state_pred_head rows
+};
+
 struct ParamEntry {
   std::string name;
   int64_t rows, cols, offset;
@@ -72,6 +82,8 @@ struct Plan {
   SqActorLay sq_actor;    // CPQ / BEAR-Lag
   EnsLay critic, cost_critic;
   VaeLay vae;
+  CdtLay cdt;
+  int g_cdt = -1;
   int g_actor = -1, g_critic = -1, g_cost = -1, g_vae = -1;
   double qc_thres = 0.0, q_thres = 0.0;
   std::vector<std::string> stat_names;
@@ -122,6 +134,10 @@ struct Engine {
   int B = 0;
   float *b_obs = nullptr, *b_nobs = nullptr, *b_act = nullptr, *b_rew = nullptr, *b_cost = nullptr, *b_done = nullptr;
   int64_t* b_idx = nullptr;
+  // CDT sequence minibatch staging (device): [B*T, .] row-major
+  float *s_states = nullptr, *s_actions = nullptr, *s_returns = nullptr, *s_ctg = nullptr, *s_mask = nullptr,
+        *s_costs = nullptr;
+  long long* s_ts = nullptr;
   // noise slots
   std::vector<float*> noise_buf;
   NoiseSlot *d_slots_all = nullptr, *d_slots_dyn = nullptr;
@@ -164,7 +180,8 @@ GemmTask task_wgrad(const float* dY, int lddy, const float* X, int ldx, int rows
 void prepare_kernels();
 void emit_gemm(Engine& e, Program& p, const std::vector<GemmTask>& tasks);
 void emit_copy(Engine& e, Program& p, const std::vector<CopyTask>& tasks);
-void emit_adam(Engine& e, Program& p, int group, int64_t begin, int64_t end, bool polyak);
+void emit_adam(Engine& e, Program& p, int group, int64_t begin, int64_t end, bool polyak,
+               const float* clip_coef = nullptr);
 void emit_allreduce(Engine& e, Program& p, float* buf, int64_t count);
 CopyTask copy_cols(float* dst, int ldd, int dcol0, const float* src, int lds, int scol0, int rows, int cols,
                    int row_div = 1, int row_mod = 1 << 30);
@@ -201,5 +218,6 @@ void build_bc(Engine& e);
 void build_bcql(Engine& e);
 void build_cpq(Engine& e);
 void build_bearl(Engine& e);
+void build_cdt(Engine& e);
 
 }  // namespace osrl

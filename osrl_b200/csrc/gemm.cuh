@@ -20,7 +20,7 @@
 
 namespace osrl {
 
-enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2, ACT_GELU = 3 };
 
 struct GemmTask {
   const float* A;
@@ -48,6 +48,16 @@ struct GemmTask {
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_RELU) return v > 0.f ? v : 0.f;
   if (act == ACT_TANH) return tanhf(v);
+  if (act == ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));  // nn.GELU() exact (erf) form
+  return v;
+}
+// derivative mask of the fused dgrad epilogue; `s` is the stored forward value named by GemmTask::dact_src
+// (post-activation for ReLU/Tanh, PRE-activation for GELU)
+__device__ __forceinline__ float apply_dact(float v, float s, int dact) {
+  if (dact == ACT_RELU) return s > 0.f ? v : 0.f;
+  if (dact == ACT_TANH) return v * (1.f - s * s);
+  if (dact == ACT_GELU)
+    return v * (0.5f * (1.f + erff(s * 0.70710678118654752f)) + s * 0.3989422804014327f * expf(-0.5f * s * s));
   return v;
 }
 
@@ -253,14 +263,14 @@ k_gemm_tasks(const GemmTask* __restrict__ tasks, int ntasks) {
       if (gj >= N) continue;
       float v = acc[i][j];
       if (t.bias) v += t.bias[gj];
+      if (t.aux && t.act == ACT_GELU) t.aux[(size_t)gi * t.ldaux + gj] = v;  // GELU keeps the pre-activation
       v = apply_act(v, t.act);
-      if (t.aux) t.aux[(size_t)gi * t.ldaux + gj] = v;
+      if (t.aux && t.act != ACT_GELU) t.aux[(size_t)gi * t.ldaux + gj] = v;
       v *= t.scale;
       if (t.resid) v += t.resid[(size_t)gi * t.ldr + gj];
       if (t.clamp) v = fminf(fmaxf(v, t.lo), t.hi);
       if (t.dact) {
-        const float s = t.dact_src[(size_t)gi * t.ld_dact + gj];
-        v = (t.dact == ACT_RELU) ? (s > 0.f ? v : 0.f) : v * (1.f - s * s);
+        v = apply_dact(v, t.dact_src[(size_t)gi * t.ld_dact + gj], t.dact);
       }
       t.C[(size_t)gi * t.ldc + gj] = v;
     }

@@ -220,14 +220,14 @@ __device__ __forceinline__ void gemm_mma_body(const GemmTask& t, float* __restri
         if (gi >= M || gj >= N) continue;
         float v = acc[i][j][q];
         if (t.bias) v += t.bias[gj];
+        if (t.aux && t.act == ACT_GELU) t.aux[(size_t)gi * t.ldaux + gj] = v;  // GELU keeps the pre-activation
         v = apply_act(v, t.act);
-        if (t.aux) t.aux[(size_t)gi * t.ldaux + gj] = v;
+        if (t.aux && t.act != ACT_GELU) t.aux[(size_t)gi * t.ldaux + gj] = v;
         v *= t.scale;
         if (t.resid) v += t.resid[(size_t)gi * t.ldr + gj];
         if (t.clamp) v = fminf(fmaxf(v, t.lo), t.hi);
         if (t.dact) {
-          const float s = t.dact_src[(size_t)gi * t.ld_dact + gj];
-          v = (t.dact == ACT_RELU) ? (s > 0.f ? v : 0.f) : v * (1.f - s * s);
+          v = apply_dact(v, t.dact_src[(size_t)gi * t.ld_dact + gj], t.dact);
         }
         t.C[(size_t)gi * t.ldc + gj] = v;
       }

@@ -17,8 +17,8 @@ struct DevState {
   float pid_e_old, pid_e_int;         // LagrangianPIDController state (net.py:373-374)
   float log_alpha;                    // CPQ / BEAR dual variable (cpq.py:93, bearl.py:112)
   int n_train_steps;                  // BEAR policy-update gate (bearl.py:249)
-  float log_temperature;              // CDT (cdt.py:144)
-  float temp_m, temp_v;               // Adam state of log_temperature
+  double log_temperature;             // CDT: float64 leaf outside state_dict (cdt.py:144)
+  double temp_m, temp_v;              // Adam state of log_temperature
   float scratch[16];
 };
 

@@ -246,6 +246,74 @@ Plan make_plan(const osrl_config& cfg) {
       }
       break;
     }
+    case OSRL_ALGO_CDT: {
+      const int E = cfg.embedding_dim, T = cfg.seq_len, NL = cfg.num_layers, H = cfg.num_heads;
+      OSRL_REQUIRE(E > 0 && E % 32 == 0 && E <= 512, "embedding_dim must be a multiple of 32, <= 512");
+      OSRL_REQUIRE(H > 0 && E % H == 0 && (E / H == 8 || E / H == 16 || E / H == 32), "head dim must be 8, 16 or 32");
+      OSRL_REQUIRE(T > 0 && NL > 0 && cfg.episode_len > 0, "bad CDT config");
+      OSRL_REQUIRE(cfg.use_rew && cfg.use_cost && cfg.cost_transform && cfg.stochastic,
+                   "this build covers the reference's configured CDT mode: use_rew, use_cost, cost_transform, stochastic");
+      OSRL_REQUIRE(cfg.attention_dropout == 0.f && cfg.residual_dropout == 0.f && cfg.embedding_dropout == 0.f,
+                   "CDT dropout > 0 is not built yet (round 2); construct the model with dropout 0");
+      CdtLay& L_ = p.cdt;
+      L_.E = E;
+      L_.te_rows = cfg.episode_len + T;
+      const int64_t b0 = al.top;
+      L_.emb_norm_w = al.take(E); L_.emb_norm_b = al.take(E);
+      L_.out_norm_w = al.take(E); L_.out_norm_b = al.take(E);
+      L_.te = al.take((int64_t)L_.te_rows * E);
+      L_.state_emb = alloc_lin(al, o, E);
+      L_.action_emb = alloc_lin(al, a, E);
+      L_.cost_emb = alloc_lin(al, 1, E);
+      L_.return_emb = alloc_lin(al, 1, E);
+      for (int i = 0; i < NL; ++i) {
+        CdtLay::Blk b;
+        b.n1w = al.take(E); b.n1b = al.take(E); b.n2w = al.take(E); b.n2b = al.take(E);
+        b.in_proj = alloc_lin(al, E, 3 * E);
+        b.out_proj = alloc_lin(al, E, E);
+        b.fc1 = alloc_lin(al, E, 4 * E);
+        b.fc2 = alloc_lin(al, 4 * E, E);
+        L_.blocks.push_back(b);
+      }
+      L_.act_head = alloc_lin(al, E, 2 * a);
+      L_.aux_head = alloc_lin(al, E, 2 + o);
+      p.g_cdt = add_group(p, "cdt", b0, al.top, cfg.learning_rate, false);
+      Group& g = p.groups[p.g_cdt];
+      g.beta1 = std::round((double)cfg.adam_beta1 * 1e6) / 1e6;   // floats from the ABI -> the python doubles
+      g.beta2 = std::round((double)cfg.adam_beta2 * 1e6) / 1e6;
+      g.wd = cfg.weight_decay;
+      g.warmup = cfg.lr_warmup_steps;
+      auto& t = p.table;
+      const int G_ = p.g_cdt;
+      t.push_back({"emb_norm.weight", E, 0, L_.emb_norm_w, 0, G_});
+      t.push_back({"emb_norm.bias", E, 0, L_.emb_norm_b, 0, G_});
+      t.push_back({"out_norm.weight", E, 0, L_.out_norm_w, 0, G_});
+      t.push_back({"out_norm.bias", E, 0, L_.out_norm_b, 0, G_});
+      t.push_back({"timestep_emb.weight", L_.te_rows, E, L_.te, 0, G_});
+      emit_lin(t, "state_emb", L_.state_emb.w, L_.state_emb.b, E, o, 0, G_);
+      emit_lin(t, "action_emb", L_.action_emb.w, L_.action_emb.b, E, a, 0, G_);
+      emit_lin(t, "cost_emb", L_.cost_emb.w, L_.cost_emb.b, E, 1, 0, G_);
+      emit_lin(t, "return_emb", L_.return_emb.w, L_.return_emb.b, E, 1, 0, G_);
+      for (int i = 0; i < NL; ++i) {
+        const CdtLay::Blk& b = L_.blocks[i];
+        const std::string pre = "blocks." + std::to_string(i) + ".";
+        t.push_back({pre + "norm1.weight", E, 0, b.n1w, 0, G_});
+        t.push_back({pre + "norm1.bias", E, 0, b.n1b, 0, G_});
+        t.push_back({pre + "norm2.weight", E, 0, b.n2w, 0, G_});
+        t.push_back({pre + "norm2.bias", E, 0, b.n2b, 0, G_});
+        t.push_back({pre + "attention.in_proj_weight", 3 * E, E, b.in_proj.w, 0, G_});
+        t.push_back({pre + "attention.in_proj_bias", 3 * E, 0, b.in_proj.b, 0, G_});
+        emit_lin(t, pre + "attention.out_proj", b.out_proj.w, b.out_proj.b, E, E, 0, G_);
+        emit_lin(t, pre + "mlp.0", b.fc1.w, b.fc1.b, 4 * E, E, 0, G_);
+        emit_lin(t, pre + "mlp.2", b.fc2.w, b.fc2.b, E, 4 * E, 0, G_);
+      }
+      emit_lin(t, "action_head.mu", L_.act_head.w, L_.act_head.b, a, E, 0, G_);
+      emit_lin(t, "action_head.log_std", L_.act_head.w + (int64_t)a * E, L_.act_head.b + a, a, E, 0, G_);
+      emit_lin(t, "state_pred_head", L_.aux_head.w + 2 * (int64_t)E, L_.aux_head.b + 2, o, E, 0, G_);
+      emit_lin(t, "cost_pred_head", L_.aux_head.w, L_.aux_head.b, 2, E, 0, G_);
+      p.stat_names = {"nll", "ent", "ent_reg", "all_loss", "act_loss", "cost_loss", "cost_acc", "state_loss", "train_lr"};
+      break;
+    }
     default:
       throw Err(OSRL_ERR_UNSUPPORTED, "algorithm id not supported by this build");
   }

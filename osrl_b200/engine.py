@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ALGO, Batch, Config, DatasetView, Noise, ParamDesc, check
+from ._lib import ALGO, Batch, Config, DatasetView, Noise, ParamDesc, SeqBatch, check
 
 _BATCH_KEYS = ("observations", "next_observations", "actions", "rewards", "costs", "done")
 
@@ -34,6 +34,14 @@ def make_config(algo: str, *, batch_size: int, seed: int = 0, world_size: int = 
     cfg.start_update_policy_step = 20000
     cfg.actor_lr = cfg.critic_lr = cfg.vae_lr = 1e-4
     cfg.alpha_lr = 1e-4 if algo == "cpq" else 1e-3
+    # CDT defaults (cdt.py:45-70, 291-310; the mode every reference task config uses)
+    cfg.seq_len, cfg.embedding_dim, cfg.num_layers, cfg.num_heads = 10, 128, 4, 8
+    cfg.use_rew = cfg.use_cost = cfg.cost_transform = cfg.stochastic = 1
+    cfg.init_temperature, cfg.learning_rate, cfg.weight_decay = 0.1, 1e-4, 1e-4
+    cfg.adam_beta1, cfg.adam_beta2, cfg.clip_grad, cfg.lr_warmup_steps = 0.9, 0.999, 0.25, 10000
+    if algo == "cdt":
+        cfg.episode_len = 1000
+        cfg.target_entropy = -float(kw.get("action_dim", 0))
     for k, v in kw.items():
         k = ren.get(k, k)
         if k in ("a_hidden_sizes", "c_hidden_sizes"):
@@ -49,6 +57,8 @@ def make_config(algo: str, *, batch_size: int, seed: int = 0, world_size: int = 
             cfg.pid_kp, cfg.pid_ki, cfg.pid_kd = [float(x) for x in v]
         elif k == "kernel":
             cfg.mmd_kernel = {"gaussian": 0, "laplacian": 1}[v]
+        elif k == "betas":
+            cfg.adam_beta1, cfg.adam_beta2 = float(v[0]), float(v[1])
         elif k in ("device", "episode_len_unused"):
             continue
         elif hasattr(cfg, k):
@@ -238,6 +248,27 @@ class Engine:
             nz_ptr = C.byref(nz)
         check(self.lib.osrl_step(self.h, C.byref(b), nz_ptr, C.c_void_p(self._stream())))
         self._keep = keep  # pinned/device sources must outlive the async copies
+
+    def step_seq(self, batch: dict) -> None:
+        """One CDT train_one_step on a collated SequenceDataset batch (host or device tensors)."""
+        keep, kinds = [], set()
+        b = SeqBatch()
+        b.rows, b.seq_len = self.batch_size, self.cfg.seq_len
+        for k in ("states", "actions", "returns", "costs_return", "mask", "costs"):
+            t, p, on_host = _as_f32(batch[k], self.device)
+            keep.append(t); kinds.add(on_host)
+            setattr(b, k, p)
+        ts = batch["time_steps"]
+        if isinstance(ts, np.ndarray):
+            ts = torch.from_numpy(np.ascontiguousarray(ts))
+        ts = ts.to(torch.int64).contiguous()
+        keep.append(ts); kinds.add(0 if ts.is_cuda else 1)
+        b.time_steps = ts.data_ptr()
+        if len(kinds) != 1:
+            raise ValueError("all batch tensors must live on the same side (host or this GPU)")
+        b.on_host = kinds.pop()
+        check(self.lib.osrl_step_seq(self.h, C.byref(b), C.c_void_p(self._stream())))
+        self._keep = keep
 
     def steps(self, k: int) -> None:
         """k steps sampled on the device from the resident dataset."""

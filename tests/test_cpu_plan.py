@@ -23,11 +23,13 @@ def test_library_exports_every_declared_symbol(lib_built):
     assert lib_built.osrl_abi_version() == 1
 
 
-@pytest.mark.parametrize("case", ["bc_small", "bcql_small", "cpq_small", "bearl_small", "bcql_full"])
+@pytest.mark.parametrize("case", ["bc_small", "bcql_small", "cpq_small", "bearl_small", "bcql_full", "cdt_small"])
 def test_plan_matches_reference_state_dict(lib_built, case):
     from osrl_b200 import plan
     z, meta = load_golden(case)
     cfg = dict(meta["cfg"])
+    if meta["algo"] == "cdt":
+        cfg["target_entropy"] = -float(cfg["action_dim"])
     table = plan(meta["algo"], **cfg)
     names = [t[0] for t in table]
     assert names == meta["keys"]
