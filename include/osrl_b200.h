@@ -136,6 +136,22 @@ typedef struct osrl_seq_batch {
   const float* costs;
 } osrl_seq_batch;
 
+/* Host-side view of a trajectory dataset: what SequenceDataset holds after process_sequence_dataset
+ * (dataset.py:137-183): per-transition arrays in trajectory order + CSR offsets, per-transition suffix sums
+ * (returns / cost_returns), and the trajectory sampling distribution (compute_cost_sample_prob, dataset.py:439-459;
+ * NULL = uniform). */
+typedef struct osrl_seq_dataset_view {
+  int64_t n, n_traj;
+  const float* observations;   /* [n, obs_dim] */
+  const float* actions;        /* [n, act_dim] */
+  const float* returns;        /* [n] reward-to-go, unscaled */
+  const float* cost_returns;   /* [n] cost-to-go, unscaled */
+  const float* costs;          /* [n] */
+  const int64_t* traj_offsets; /* [n_traj + 1] */
+  const double* sample_prob;   /* [n_traj] or NULL */
+  float reward_scale, cost_scale;
+} osrl_seq_dataset_view;
+
 typedef struct osrl_engine osrl_engine;
 
 int osrl_abi_version(void);
@@ -162,6 +178,16 @@ int osrl_buffer_upload(osrl_engine* e, const osrl_dataset_view* view);
  * `n` rows by index into six device/host outputs (bit-exact row copies). */
 int osrl_gather(osrl_engine* e, const int64_t* idx, int n, int idx_on_host, osrl_batch* out /* writable ptrs */,
                 void* stream);
+
+/* Replaces SequenceDataset.__init__ residency (dataset.py:668-747) / __prepare_sample (dataset.py:749-775): packs
+ * the trajectories once into HBM; osrl_seq_gather builds [n, T, .] windows for explicit (trajectory, start) pairs
+ * (bit-exact, zero padded, mask, time_steps) into DEVICE buffers; osrl_seq_alias_table / osrl_last_sequences
+ * expose the sampler's alias table and the pairs the last osrl_steps() step drew. */
+int osrl_seq_buffer_upload(osrl_engine* e, const osrl_seq_dataset_view* view);
+int osrl_seq_gather(osrl_engine* e, const int32_t* traj_idx, const int32_t* start_idx, int n, osrl_seq_batch* out,
+                    void* stream);
+int osrl_seq_alias_table(osrl_engine* e, float* prob_out, int32_t* alias_out, int cap);
+int osrl_last_sequences(osrl_engine* e, int32_t* traj_out, int32_t* start_out, int cap);
 
 /* Replaces <Algo>Trainer.train_one_step (bc.py:103-109, bcql.py:283-306, cpq.py:294-313,
  * bearl.py:389-412): all sub-updates + Polyak for one minibatch, no host sync. */

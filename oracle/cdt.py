@@ -227,7 +227,7 @@ def split_trajectories(dataset: dict):
     trajs, start = [], 0
     n = dataset["rewards"].shape[0]
     for i in range(n):
-        if dataset["terminals"][i] or dataset["timeouts"][i] or i == n - 1:
+        if dataset["terminals"][i] or dataset["timeouts"][i]:   # a trailing unfinished episode is dropped (:160)
             sl = slice(start, i + 1)
             ep = {k: np.asarray(dataset[k][sl], dtype=np.float32) for k in ("observations", "actions", "rewards", "costs")}
             ep["returns"] = discounted_cumsum(ep["rewards"], 1.0)

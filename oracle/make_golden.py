@@ -275,3 +275,34 @@ def main_cdt():
 
 if __name__ == "__main__" and "cdt" in sys.argv[1:]:
     main_cdt()
+
+
+def check_sequence_sampler():
+    """Pin oracle.cdt.sequence_sample / split_trajectories against the reference's SequenceDataset
+    (dataset.py:668-775) on a seeded synthetic dataset, including the cost-based sample_prob."""
+    from oracle import cdt as ocdt
+    osrl = ref_shim.import_reference()
+    d = synth.make_dataset(6, 3, 41, 13, seed=9)
+    d["timeouts"][-7:] = False          # trailing unfinished episode must be dropped
+    ct = lambda x: 70 - x
+    ref = osrl.common.dataset.SequenceDataset({k: v.copy() for k, v in d.items()}, seq_len=10, reward_scale=0.1,
+                                              cost_scale=1.0, augment_percent=0, cost_sample=True, cost_transform=ct)
+    tr = ocdt.split_trajectories(d)
+    assert len(tr) == len(ref.dataset)
+    p = np.array([ct(t["cost_returns"][0]) for t in tr])     # float32, like dataset.py:452-458
+    p[p < 0] = 0
+    p /= np.sum(p)
+    assert p.dtype == ref.sample_prob.dtype and np.array_equal(p, ref.sample_prob)
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        t = int(rng.integers(0, len(tr)))
+        s = int(rng.integers(0, tr[t]["rewards"].shape[0]))
+        a = ref._SequenceDataset__prepare_sample(t, s)
+        b = ocdt.sequence_sample(tr, t, s, 10, 0.1, 1.0)
+        for x, y in zip(a, b):
+            assert np.array_equal(np.asarray(x), np.asarray(y)) and np.asarray(x).dtype == np.asarray(y).dtype, (t, s)
+    print("[golden] sequence sampler: oracle == reference on 200 (trajectory, start) pairs")
+
+
+if __name__ == "__main__" and "cdt" in sys.argv[1:]:
+    check_sequence_sampler()

@@ -46,3 +46,21 @@ def transition_sample(dataset: dict, idx, reward_scale: float = 1.0, cost_scale:
     done = np.logical_or(dataset["terminals"], dataset["timeouts"]).astype(np.float32)  # dataset.py:815-816
     return (dataset["observations"][idx, :], dataset["next_observations"][idx, :], dataset["actions"][idx, :],
             dataset["rewards"][idx] * reward_scale, dataset["costs"][idx] * cost_scale, done[idx])
+
+
+def philox_sequences(seed: int, step: int, rank: int, rows: int, prob: np.ndarray, alias: np.ndarray,
+                     traj_offsets: np.ndarray):
+    """The engine's on-device trajectory draw (cdt_kernels.cuh draw_sequence) restated: alias-table categorical
+    over trajectories + uniform start index, both from one Philox4x32-10 block per batch row."""
+    n_traj = prob.shape[0]
+    i = np.arange(rows, dtype=np.uint32)
+    c1 = np.full(rows, step & 0xFFFFFFFF, dtype=np.uint32)
+    c2 = np.full(rows, 2 | (((step >> 32) & 0xFFFFFF) << 8), dtype=np.uint32)
+    c3 = np.full(rows, rank, dtype=np.uint32)
+    x0, x1, x2, _ = philox4x32_10(i, c1, c2, c3, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    slot = ((x0.astype(np.uint64) * np.uint64(n_traj)) >> np.uint64(32)).astype(np.int64)
+    u = (x1 >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    traj = np.where(u < prob[slot].astype(np.float32), slot, alias[slot].astype(np.int64))
+    lens = (traj_offsets[traj + 1] - traj_offsets[traj]).astype(np.uint64)
+    start = ((x2.astype(np.uint64) * lens) >> np.uint64(32)).astype(np.int64)
+    return traj.astype(np.int32), start.astype(np.int32)

@@ -64,6 +64,13 @@ class SeqBatch(C.Structure):
                 ("time_steps", C.c_void_p), ("mask", C.c_void_p), ("episode_cost", C.c_void_p), ("costs", C.c_void_p)]
 
 
+class SeqDatasetView(C.Structure):
+    _fields_ = [("n", C.c_int64), ("n_traj", C.c_int64), ("observations", C.c_void_p), ("actions", C.c_void_p),
+                ("returns", C.c_void_p), ("cost_returns", C.c_void_p), ("costs", C.c_void_p),
+                ("traj_offsets", C.c_void_p), ("sample_prob", C.c_void_p), ("reward_scale", C.c_float),
+                ("cost_scale", C.c_float)]
+
+
 class Noise(C.Structure):
     _fields_ = [("on_host", C.c_int32), ("slot", C.c_void_p * OSRL_MAX_NOISE)]
 
@@ -83,6 +90,10 @@ SYMBOLS = [
     ("osrl_gather", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(Batch), C.c_void_p]),
     ("osrl_step", C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Noise), C.c_void_p]),
     ("osrl_step_seq", C.c_int, [C.c_void_p, C.POINTER(SeqBatch), C.c_void_p]),
+    ("osrl_seq_buffer_upload", C.c_int, [C.c_void_p, C.POINTER(SeqDatasetView)]),
+    ("osrl_seq_gather", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(SeqBatch), C.c_void_p]),
+    ("osrl_seq_alias_table", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    ("osrl_last_sequences", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     ("osrl_steps", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     ("osrl_stat_names", C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_int)]),
     ("osrl_stats", C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int), C.c_void_p]),

@@ -1,0 +1,135 @@
+"""CDT / CDTTrainer with the reference's signatures (osrl/algorithms/cdt.py:45-418), for the mode every
+reference task config uses: time_emb, use_rew, use_cost, cost_transform, stochastic head, 1-layer action
+head, no cost prefix / cost features.  Dropout must be 0 in this build."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ._base import EngineModel, EngineTrainer
+
+
+class _Block(nn.Module):
+    """Parameter shell of TransformerBlock (net.py:391-441)."""
+
+    def __init__(self, seq_len, embedding_dim, num_heads):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(embedding_dim)
+        self.norm2 = nn.LayerNorm(embedding_dim)
+        self.attention = nn.MultiheadAttention(embedding_dim, num_heads, 0.0, batch_first=True)
+        self.mlp = nn.Sequential(nn.Linear(embedding_dim, 4 * embedding_dim), nn.GELU(),
+                                 nn.Linear(4 * embedding_dim, embedding_dim), nn.Dropout(0.0))
+        self.register_buffer("causal_mask", ~torch.tril(torch.ones(seq_len, seq_len)).to(bool))
+
+
+class _DiagGaussianActor(nn.Module):
+    def __init__(self, hidden_dim, act_dim):
+        super().__init__()
+        self.mu = nn.Linear(hidden_dim, act_dim)
+        self.log_std = nn.Linear(hidden_dim, act_dim)
+        for m in (self.mu, self.log_std):   # net.py:521-528 (consumes RNG like the reference)
+            nn.init.orthogonal_(m.weight.data)
+            m.bias.data.fill_(0.0)
+
+
+class CDT(EngineModel):
+    algo = "cdt"
+
+    def __init__(self, state_dim: int, action_dim: int, max_action: float, seq_len: int = 10, episode_len: int = 1000,
+                 embedding_dim: int = 128, num_layers: int = 4, num_heads: int = 8, attention_dropout: float = 0.0,
+                 residual_dropout: float = 0.0, embedding_dropout: float = 0.0, time_emb: bool = True,
+                 use_rew: bool = False, use_cost: bool = False, cost_transform: bool = False,
+                 add_cost_feat: bool = False, mul_cost_feat: bool = False, cat_cost_feat: bool = False,
+                 action_head_layers: int = 1, cost_prefix: bool = False, stochastic: bool = False,
+                 init_temperature=0.1, target_entropy=None, device: str = "cuda:0"):
+        super().__init__()
+        if not (time_emb and use_rew and use_cost and cost_transform and stochastic) or add_cost_feat or \
+                mul_cost_feat or cat_cost_feat or cost_prefix or action_head_layers != 1:
+            raise NotImplementedError("osrl_b200 CDT covers the configured reference mode (time_emb, use_rew, use_cost, "
+                                      "cost_transform, stochastic, action_head_layers=1, no prefix / cost features)")
+        if attention_dropout or residual_dropout or embedding_dropout:
+            raise NotImplementedError("CDT dropout > 0 is not built yet; pass 0 for the three dropouts")
+        self.seq_len, self.embedding_dim, self.state_dim, self.action_dim = seq_len, embedding_dim, state_dim, action_dim
+        self.episode_len, self.max_action, self.stochastic, self.device = episode_len, max_action, stochastic, device
+        self.num_layers, self.num_heads = num_layers, num_heads
+        self.init_temperature = init_temperature
+        self.target_entropy = -float(action_dim) if target_entropy is None else float(target_entropy)
+        # registration / construction order of the reference (cdt.py:85-141), then _init_weights (:148-164)
+        self.emb_norm = nn.LayerNorm(embedding_dim)
+        self.out_norm = nn.LayerNorm(embedding_dim)
+        self.timestep_emb = nn.Embedding(episode_len + seq_len, embedding_dim)
+        self.state_emb = nn.Linear(state_dim, embedding_dim)
+        self.action_emb = nn.Linear(action_dim, embedding_dim)
+        self.cost_emb = nn.Linear(1, embedding_dim)
+        self.return_emb = nn.Linear(1, embedding_dim)
+        self.blocks = nn.ModuleList([_Block(4 * seq_len, embedding_dim, num_heads) for _ in range(num_layers)])
+        self.action_head = _DiagGaussianActor(embedding_dim, action_dim)
+        self.state_pred_head = nn.Linear(embedding_dim, state_dim)
+        self.cost_pred_head = nn.Linear(embedding_dim, 2)
+        self.apply(self._init_weights)
+
+    @staticmethod
+    def _init_weights(module: nn.Module):
+        if isinstance(module, (nn.Linear, nn.Embedding)):
+            torch.nn.init.normal_(module.weight, mean=0.0, std=0.02)
+            if isinstance(module, nn.Linear) and module.bias is not None:
+                torch.nn.init.zeros_(module.bias)
+        elif isinstance(module, nn.LayerNorm):
+            torch.nn.init.zeros_(module.bias)
+            torch.nn.init.ones_(module.weight)
+
+    def temperature(self):
+        e = self.engine
+        return torch.tensor(np.exp(e.scalars()["log_temperature"]) if e else self.init_temperature)
+
+    def _hyper(self):
+        return dict(state_dim=self.state_dim, action_dim=self.action_dim, max_action=self.max_action,
+                    seq_len=self.seq_len, episode_len=self.episode_len, embedding_dim=self.embedding_dim,
+                    num_layers=self.num_layers, num_heads=self.num_heads, use_rew=1, use_cost=1, cost_transform=1,
+                    stochastic=1, init_temperature=self.init_temperature, target_entropy=self.target_entropy)
+
+
+class CDTTrainer(EngineTrainer):
+    def __init__(self, model: CDT, env=None, logger=None, learning_rate: float = 1e-4, weight_decay: float = 1e-4,
+                 betas: Tuple[float, ...] = (0.9, 0.999), clip_grad: float = 0.25, lr_warmup_steps: int = 10000,
+                 reward_scale: float = 1.0, cost_scale: float = 1.0, loss_cost_weight: float = 0.0,
+                 loss_state_weight: float = 0.0, cost_reverse: bool = False, no_entropy: bool = False,
+                 device="cuda:0", **kw):
+        super().__init__(model, env, logger, reward_scale, cost_scale, device, **kw)
+        if no_entropy:
+            raise NotImplementedError("no_entropy=True is not built")
+        self.clip_grad, self.cost_weight, self.state_weight = clip_grad, loss_cost_weight, loss_state_weight
+        self._lrs = dict(learning_rate=learning_rate, weight_decay=weight_decay, betas=tuple(betas),
+                         clip_grad=0.0 if clip_grad is None else clip_grad, lr_warmup_steps=lr_warmup_steps,
+                         loss_cost_weight=loss_cost_weight, loss_state_weight=loss_state_weight)
+        self.stochastic, self.max_action = model.stochastic, model.max_action
+
+    def _store(self, stats):
+        self.logger.store(tab="train", **stats)
+
+    def set_dataset(self, seq_dataset):
+        """A SequenceDataset -> resident in HBM (fast path)."""
+        self._dataset = seq_dataset
+        if self.model.engine is not None:
+            seq_dataset.to_engine(self.model.engine)
+
+    def _engine(self, batch_size: int):
+        eng = self.model.engine
+        if eng is None:
+            eng = self.model._bind(batch_size, self._lrs, seed=self.seed)
+            if self._dataset is not None:
+                self._dataset.to_engine(eng)
+        elif eng.batch_size != batch_size:
+            raise RuntimeError(f"engine was built for batch_size={eng.batch_size}, got a batch of {batch_size}")
+        return eng
+
+    def train_one_step(self, states, actions, returns, costs_return, time_steps, mask, episode_cost, costs):
+        eng = self._engine(states.shape[0])
+        eng.step_seq({"states": states, "actions": actions, "returns": returns, "costs_return": costs_return,
+                      "time_steps": time_steps, "mask": mask, "costs": costs})
+        self._n += 1
+        if self.log_every and self._n % self.log_every == 0:
+            self._store(eng.stats())

@@ -1,12 +1,13 @@
 """Minibatch sources with the reference's class names (osrl/common/dataset.py:633-847).
 
-``TransitionDataset`` keeps the reference's constructor and iterator contract (so it can be
-handed to ``torch.utils.data.DataLoader`` by the unchanged example scripts), and additionally
-knows how to make itself resident in HBM: ``trainer.set_dataset(ds.dataset, ...)`` /
-``ds.to_engine(engine)`` packs it once and all later draws happen on the device
-(``osrl_steps``).
+Both keep the reference's constructor and iterator contract (so they can be handed to
+``torch.utils.data.DataLoader`` by the unchanged example scripts) and additionally know how to make
+themselves resident in HBM (``to_engine`` / ``trainer.set_dataset``): the data is packed once and all later
+draws happen on the device (``osrl_steps``).
 """
 from __future__ import annotations
+
+import random
 
 import numpy as np
 from torch.utils.data import IterableDataset
@@ -46,8 +47,71 @@ class TransitionDataset(IterableDataset):
             yield self.sample(np.random.choice(self.dataset_size, p=self.sample_prob))
 
 
-class SequenceDataset(IterableDataset):
-    """Placeholder for the CDT trajectory sampler (dataset.py:633-787); built with the CDT path."""
+def _suffix_sums(x: np.ndarray, offsets: np.ndarray) -> np.ndarray:
+    """Per-trajectory reward-to-go (discounted_cumsum with gamma=1, dataset.py:19-27), vectorised: a reversed
+    float32 running sum restarted at every trajectory end (same left-to-right order of additions per step)."""
+    out = np.empty_like(x)
+    for s, e in zip(offsets[:-1], offsets[1:]):
+        out[s:e] = np.cumsum(x[s:e][::-1], dtype=np.float32)[::-1]
+    return out
 
-    def __init__(self, *a, **k):
-        raise NotImplementedError("SequenceDataset is part of the CDT path, which this build does not include yet")
+
+class SequenceDataset(IterableDataset):
+    """Trajectory windows for CDT.  Covers the sampling modes that need no Pareto-frontier augmentation
+    (augment_percent=0, random_aug=0, pf_only/pf_sample off -- those require the un-vendored `oapackage`):
+    uniform or cost-based trajectory sampling (cost_sample, dataset.py:439-459) and uniform start index."""
+
+    def __init__(self, dataset: dict, seq_len: int = 10, reward_scale: float = 1.0, cost_scale: float = 1.0,
+                 deg: int = 3, pf_sample: bool = False, max_rew_decrease: float = 1.0, beta: float = 1.0,
+                 augment_percent: float = 0, max_reward: float = 1000.0, min_reward: float = 5,
+                 cost_reverse: bool = False, pf_only: bool = False, rmin: float = 0, cost_bins: int = 60, npb: int = 5,
+                 cost_sample: bool = False, cost_transform=lambda x: 50 - x, prob: float = 0.4,
+                 start_sampling: bool = False, random_aug: float = 0, **_unused):
+        if pf_only or pf_sample or augment_percent > 0 or random_aug > 0 or start_sampling:
+            raise NotImplementedError("Pareto-frontier / random augmentation and start-index sampling are one-time "
+                                      "CPU preprocessing outside the hot path and are not rebuilt here")
+        self.seq_len, self.reward_scale, self.cost_scale = seq_len, reward_scale, cost_scale
+        ends = np.flatnonzero(np.logical_or(dataset["terminals"], dataset["timeouts"]))
+        n = int(ends[-1]) + 1 if ends.size else 0          # a trailing unfinished episode is dropped (:160-168)
+        self.offsets = np.concatenate([[0], ends + 1]).astype(np.int64)
+        costs = np.asarray(dataset["costs"][:n], dtype=np.float32)
+        if cost_reverse:
+            costs = 1.0 - costs
+        self.flat = {
+            "observations": np.asarray(dataset["observations"][:n], dtype=np.float32),
+            "actions": np.asarray(dataset["actions"][:n], dtype=np.float32),
+            "costs": costs,
+        }
+        self.flat["returns"] = _suffix_sums(np.asarray(dataset["rewards"][:n], dtype=np.float32), self.offsets)
+        self.flat["cost_returns"] = _suffix_sums(costs, self.offsets)
+        self.sample_prob = None
+        if cost_sample:
+            p = np.array([cost_transform(self.flat["cost_returns"][s]) for s in self.offsets[:-1]])  # float32 (:452-458)
+            p[p < 0] = 0
+            p /= np.sum(p)
+            self.sample_prob = p
+        print(f"original data: {len(self.offsets) - 1}, augment data: 0, total: {len(self.offsets) - 1}")
+
+    def __len__(self):
+        return len(self.offsets) - 1
+
+    def to_engine(self, engine) -> None:
+        """Pack into HBM once (osrl_seq_buffer_upload); windows are then drawn on the device."""
+        engine.upload_seq_dataset(dict(self.flat, traj_offsets=self.offsets, sample_prob=self.sample_prob),
+                                  self.reward_scale, self.cost_scale)
+
+    def sample(self, traj_idx: int, start_idx: int):
+        s, e = self.offsets[traj_idx], self.offsets[traj_idx + 1]
+        lo, hi = s + start_idx, min(s + start_idx + self.seq_len, e)
+        n, T = hi - lo, self.seq_len
+        pad = lambda x: np.concatenate([x, np.zeros((T - n,) + x.shape[1:], dtype=x.dtype)], 0) if n < T else x
+        f = self.flat
+        mask = np.hstack([np.ones(n), np.zeros(T - n)])
+        return (pad(f["observations"][lo:hi]), pad(f["actions"][lo:hi]), pad(f["returns"][lo:hi] * self.reward_scale),
+                pad(f["cost_returns"][lo:hi] * self.cost_scale), np.arange(start_idx, start_idx + T), mask,
+                f["cost_returns"][s] * self.cost_scale, pad(f["costs"][lo:hi]))
+
+    def __iter__(self):
+        while True:
+            t = np.random.choice(len(self), p=self.sample_prob)
+            yield self.sample(t, random.randint(0, int(self.offsets[t + 1] - self.offsets[t]) - 1))

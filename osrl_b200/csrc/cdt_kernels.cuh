@@ -34,6 +34,53 @@ static __global__ void k_cdt_te_scatter(const long long* __restrict__ ts, const 
   }
 }
 
+// ------------------------------------------------------------------ trajectory buffer: sample + gather
+// Replaces SequenceDataset.__iter__/__prepare_sample + collate + .to(device) (dataset.py:749-787).
+// Packed transition row: [obs(o) | act(a) | return_to_go*reward_scale | cost_to_go*cost_scale | cost | pad].
+// traj ~ Categorical(sample_prob) through an alias table, start ~ U[0, len-1] (Philox), T rows from `start`,
+// zero-padded past the trajectory end with mask = 0; time_steps = start + t (not clipped, dataset.py:755).
+enum { STREAM_SEQ = 2 };
+__host__ __device__ __forceinline__ void draw_sequence(uint64_t seed, uint64_t step, uint32_t rank, uint32_t i,
+                                                       const float* prob, const int* alias, const long long* off,
+                                                       int n_traj, int& traj, int& start) {
+  uint32_t c[4] = {i, (uint32_t)step, (uint32_t)STREAM_SEQ | ((uint32_t)(step >> 32) << 8), rank};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const int slot = (int)(((uint64_t)c[0] * (uint64_t)n_traj) >> 32);
+  const float u = (float)(c[1] >> 8) * (1.0f / 16777216.0f);
+  traj = (u < prob[slot]) ? slot : alias[slot];
+  const long long len = off[traj + 1] - off[traj];
+  start = (int)(((uint64_t)c[2] * (uint64_t)len) >> 32);
+}
+static __global__ void k_seq_gather(const float* __restrict__ rows_, const long long* __restrict__ off, int n_traj,
+                                    int stride, int o, int a, int T, const float* __restrict__ prob,
+                                    const int* __restrict__ alias, const int* __restrict__ traj_in,
+                                    const int* __restrict__ start_in, uint64_t seed, const DevState* st, uint32_t rank,
+                                    int B, float* states, float* actions, float* returns, float* ctg, long long* ts,
+                                    float* mask, float* costs, int* traj_out, int* start_out) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= B * T) return;
+  const int b = w / T, t = w % T;
+  int traj, start;
+  if (traj_in) { traj = traj_in[b]; start = start_in[b]; }
+  else draw_sequence(seed, st->step, rank, (uint32_t)b, prob, alias, off, n_traj, traj, start);
+  if (t == 0 && lane == 0) {
+    if (traj_out) traj_out[b] = traj;
+    if (start_out) start_out[b] = start;
+  }
+  const long long len = off[traj + 1] - off[traj];
+  const bool valid = (long long)start + t < len;
+  const float* __restrict__ row = rows_ + (off[traj] + start + t) * (long long)stride;
+  for (int c = lane; c < o; c += 32) states[(size_t)w * o + c] = valid ? row[c] : 0.f;
+  for (int c = lane; c < a; c += 32) actions[(size_t)w * a + c] = valid ? row[o + c] : 0.f;
+  if (lane == 0) {
+    returns[w] = valid ? row[o + a] : 0.f;
+    ctg[w] = valid ? row[o + a + 1] : 0.f;
+    costs[w] = valid ? row[o + a + 2] : 0.f;
+    mask[w] = valid ? 1.f : 0.f;
+    ts[w] = (long long)start + t;
+  }
+}
+
 // ------------------------------------------------------------------ LayerNorm (eps 1e-5, biased variance)
 static __global__ void k_ln_fwd(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
                                 float* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int rows,

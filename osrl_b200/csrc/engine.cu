@@ -1,6 +1,7 @@
 // Engine runtime + C ABI (see include/osrl_b200.h).
 #include "engine.h"
 #include "gemm_mma.cuh"
+#include "cdt_kernels.cuh"
 
 #include <dlfcn.h>
 
@@ -352,6 +353,7 @@ static Engine* create(const osrl_config& cfg, int device) {
       e->s_states = e->ws(BT * o); e->s_actions = e->ws(BT * a); e->s_returns = e->ws(BT); e->s_ctg = e->ws(BT);
       e->s_mask = e->ws(BT); e->s_costs = e->ws(BT);
       e->s_ts = (long long*)e->ws(BT * 2);
+      e->s_traj = (int*)e->ws(B); e->s_start = (int*)e->ws(B);
     }
     std::vector<NoiseSlot> slots;
     int si = 0;
@@ -386,8 +388,24 @@ static void epilogue(Engine& e, cudaStream_t s) {
   k_epilogue<<<1, 32, 0, s>>>(e.ds);
   e.launches++;
 }
+static void launch_seq_gather(Engine& e, cudaStream_t s, const int* traj_in, const int* start_in, int rows,
+                              float* states, float* actions, float* returns, float* ctg, long long* ts, float* mask,
+                              float* costs, int* traj_out, int* start_out) {
+  const osrl_config& c = e.plan.cfg;
+  const int T = c.seq_len;
+  k_seq_gather<<<(rows * T + 7) / 8, 256, 0, s>>>(e.sq_rows, e.sq_off, e.sq_ntraj, e.sq_stride, c.obs_dim, c.act_dim, T,
+                                                  e.sq_prob, e.sq_alias, traj_in, start_in, c.seed, e.ds, (uint32_t)e.rank,
+                                                  rows, states, actions, returns, ctg, ts, mask, costs, traj_out,
+                                                  start_out);
+  e.launches++;
+}
 static void sample_front(Engine& e, cudaStream_t s) {
   const osrl_config& c = e.plan.cfg;
+  if (c.algo == OSRL_ALGO_CDT) {
+    launch_seq_gather(e, s, nullptr, nullptr, e.B, e.s_states, e.s_actions, e.s_returns, e.s_ctg, e.s_ts, e.s_mask,
+                      e.s_costs, e.s_traj, e.s_start);
+    return;
+  }
   const int warps_per_block = 8;
   k_sample_gather<<<(e.B + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, s>>>(
       e.ds_rows, e.ds_n, e.ds_stride, c.obs_dim, c.act_dim, nullptr, c.seed, e.ds, (uint32_t)e.rank, e.B, e.b_obs,
@@ -426,6 +444,30 @@ static cudaGraphExec_t capture(Engine& e, bool sampled) {
 }
 static int kernels_per_step(const Engine& e, bool sampled) {
   return e.body.kernels + 2 + (sampled ? (1 + (e.noise_buf.empty() ? 0 : 1)) : 0);
+}
+
+// Vose alias table for Categorical(p): slot s keeps itself with probability prob[s], else alias[s]
+static void build_alias(const std::vector<double>& p, std::vector<float>& prob, std::vector<int>& alias) {
+  const int n = (int)p.size();
+  prob.assign(n, 1.f);
+  alias.resize(n);
+  std::vector<double> q(n);
+  std::vector<int> small, large;
+  for (int i = 0; i < n; ++i) {
+    q[i] = p[i] * n;
+    alias[i] = i;
+    (q[i] < 1.0 ? small : large).push_back(i);
+  }
+  while (!small.empty() && !large.empty()) {
+    const int s_ = small.back(), l = large.back();
+    small.pop_back();
+    prob[s_] = (float)q[s_];
+    alias[s_] = l;
+    q[l] = (q[l] + q[s_]) - 1.0;
+    if (q[l] < 1.0) { large.pop_back(); small.push_back(l); }
+  }
+  for (int i : small) prob[i] = 1.f;
+  for (int i : large) prob[i] = 1.f;
 }
 
 }  // namespace osrl
@@ -571,6 +613,96 @@ int osrl_buffer_upload(osrl_engine* h, const osrl_dataset_view* v) {
   OSRL_CATCH
 }
 
+int osrl_seq_buffer_upload(osrl_engine* h, const osrl_seq_dataset_view* v) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && v, "null argument");
+  Engine& e = *h->e;
+  OSRL_REQUIRE(e.plan.cfg.algo == OSRL_ALGO_CDT, "trajectory buffers belong to CDT engines");
+  OSRL_REQUIRE(v->n > 0 && v->n_traj > 0 && v->observations && v->actions && v->returns && v->cost_returns &&
+                   v->costs && v->traj_offsets,
+               "trajectory view incomplete");
+  OSRL_REQUIRE(v->traj_offsets[0] == 0 && v->traj_offsets[v->n_traj] == v->n, "traj_offsets must span [0, n]");
+  OSRL_CUDA(cudaSetDevice(e.device));
+  const int o = e.plan.cfg.obs_dim, a = e.plan.cfg.act_dim;
+  const int stride = (o + a + 3 + 3) / 4 * 4;
+  std::vector<float> packed((size_t)v->n * stride, 0.f);
+  for (int64_t i = 0; i < v->n; ++i) {
+    float* r = packed.data() + (size_t)i * stride;
+    memcpy(r, v->observations + (size_t)i * o, o * sizeof(float));
+    memcpy(r + o, v->actions + (size_t)i * a, a * sizeof(float));
+    r[o + a] = v->returns[i] * v->reward_scale;          // dataset.py:762 (float32 * weak python float)
+    r[o + a + 1] = v->cost_returns[i] * v->cost_scale;   // :763
+    r[o + a + 2] = v->costs[i];
+  }
+  std::vector<double> p(v->n_traj, 1.0 / v->n_traj);
+  if (v->sample_prob) {
+    double tot = 0;
+    for (int i = 0; i < v->n_traj; ++i) { OSRL_REQUIRE(v->sample_prob[i] >= 0, "negative sample_prob"); tot += v->sample_prob[i]; }
+    OSRL_REQUIRE(tot > 0, "sample_prob sums to zero");
+    for (int i = 0; i < v->n_traj; ++i) p[i] = v->sample_prob[i] / tot;
+  }
+  for (int i = 0; i < v->n_traj; ++i) OSRL_REQUIRE(v->traj_offsets[i + 1] > v->traj_offsets[i], "empty trajectory");
+  std::vector<float> prob;
+  std::vector<int> alias;
+  build_alias(p, prob, alias);
+  std::vector<long long> off(v->traj_offsets, v->traj_offsets + v->n_traj + 1);
+  e.sq_rows = e.upload(packed);
+  e.sq_off = e.upload(off);
+  e.sq_prob = e.upload(prob);
+  e.sq_alias = e.upload(alias);
+  e.sq_ntraj = (int)v->n_traj;
+  e.sq_stride = stride;
+  e.ds_rows = e.sq_rows;  // marks "a resident dataset exists" for osrl_steps
+  if (e.g_sampled) { cudaGraphExecDestroy(e.g_sampled); e.g_sampled = nullptr; }
+  OSRL_CATCH
+}
+
+int osrl_seq_alias_table(osrl_engine* h, float* prob_out, int32_t* alias_out, int cap) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && prob_out && alias_out, "null argument");
+  Engine& e = *h->e;
+  OSRL_REQUIRE(e.sq_rows && cap >= e.sq_ntraj, "no trajectory buffer / buffer too small");
+  OSRL_CUDA(cudaSetDevice(e.device));
+  OSRL_CUDA(cudaMemcpy(prob_out, e.sq_prob, e.sq_ntraj * sizeof(float), cudaMemcpyDeviceToHost));
+  OSRL_CUDA(cudaMemcpy(alias_out, e.sq_alias, e.sq_ntraj * sizeof(int), cudaMemcpyDeviceToHost));
+  OSRL_CATCH
+}
+
+int osrl_seq_gather(osrl_engine* h, const int32_t* traj_idx, const int32_t* start_idx, int n, osrl_seq_batch* out,
+                    void* stream) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && traj_idx && start_idx && out, "null argument");
+  Engine& e = *h->e;
+  OSRL_REQUIRE(e.sq_rows, "no trajectory buffer uploaded");
+  OSRL_REQUIRE(!out->on_host, "osrl_seq_gather writes device buffers");
+  OSRL_CUDA(cudaSetDevice(e.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  void *dt = nullptr, *dsx = nullptr;
+  OSRL_CUDA(cudaMalloc(&dt, (size_t)n * sizeof(int)));
+  OSRL_CUDA(cudaMalloc(&dsx, (size_t)n * sizeof(int)));
+  OSRL_CUDA(cudaMemcpyAsync(dt, traj_idx, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+  OSRL_CUDA(cudaMemcpyAsync(dsx, start_idx, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s));
+  launch_seq_gather(e, s, (const int*)dt, (const int*)dsx, n, (float*)out->states, (float*)out->actions,
+                    (float*)out->returns, (float*)out->costs_return, (long long*)out->time_steps, (float*)out->mask,
+                    (float*)out->costs, nullptr, nullptr);
+  OSRL_CUDA(cudaStreamSynchronize(s));
+  cudaFree(dt);
+  cudaFree(dsx);
+  OSRL_CATCH
+}
+
+int osrl_last_sequences(osrl_engine* h, int32_t* traj_out, int32_t* start_out, int cap) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && traj_out && start_out && cap >= h->e->B, "bad argument");
+  Engine& e = *h->e;
+  OSRL_REQUIRE(e.s_traj, "not a CDT engine");
+  OSRL_CUDA(cudaSetDevice(e.device));
+  OSRL_CUDA(cudaDeviceSynchronize());
+  OSRL_CUDA(cudaMemcpy(traj_out, e.s_traj, e.B * sizeof(int), cudaMemcpyDeviceToHost));
+  OSRL_CUDA(cudaMemcpy(start_out, e.s_start, e.B * sizeof(int), cudaMemcpyDeviceToHost));
+  OSRL_CATCH
+}
+
 int osrl_gather(osrl_engine* h, const int64_t* idx, int n, int idx_on_host, osrl_batch* out, void* stream) {
   OSRL_TRY
   OSRL_REQUIRE(h && idx && out, "null argument");
@@ -694,8 +826,8 @@ int osrl_steps(osrl_engine* h, int k, void* stream) {
   OSRL_TRY
   OSRL_REQUIRE(h && k >= 0, "bad argument");
   Engine& e = *h->e;
-  OSRL_REQUIRE(e.plan.cfg.algo != OSRL_ALGO_CDT, "device-side sequence sampling is not built yet: use osrl_step_seq");
-  OSRL_REQUIRE(e.ds_rows, "osrl_steps needs a resident dataset (osrl_buffer_upload)");
+  OSRL_REQUIRE(e.ds_rows, "osrl_steps needs a resident dataset (osrl_buffer_upload / osrl_seq_buffer_upload)");
+  if (e.plan.cfg.algo == OSRL_ALGO_CDT) OSRL_REQUIRE(e.sq_rows, "CDT needs osrl_seq_buffer_upload");
   OSRL_CUDA(cudaSetDevice(e.device));
   cudaStream_t s = (cudaStream_t)stream;
   if (!e.g_sampled) e.g_sampled = capture(e, true);

@@ -138,6 +138,13 @@ struct Engine {
   float *s_states = nullptr, *s_actions = nullptr, *s_returns = nullptr, *s_ctg = nullptr, *s_mask = nullptr,
         *s_costs = nullptr;
   long long* s_ts = nullptr;
+  // resident trajectory buffer (CDT)
+  float* sq_rows = nullptr;
+  long long* sq_off = nullptr;
+  float* sq_prob = nullptr;
+  int* sq_alias = nullptr;
+  int sq_ntraj = 0, sq_stride = 0;
+  int *s_traj = nullptr, *s_start = nullptr;
   // noise slots
   std::vector<float*> noise_buf;
   NoiseSlot *d_slots_all = nullptr, *d_slots_dyn = nullptr;

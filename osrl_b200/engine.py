@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ALGO, Batch, Config, DatasetView, Noise, ParamDesc, SeqBatch, check
+from ._lib import ALGO, Batch, Config, DatasetView, Noise, ParamDesc, SeqBatch, SeqDatasetView, check
 
 _BATCH_KEYS = ("observations", "next_observations", "actions", "rewards", "costs", "done")
 
@@ -195,6 +195,53 @@ class Engine:
         v.reward_scale, v.cost_scale = float(reward_scale), float(cost_scale)
         check(self.lib.osrl_buffer_upload(self.h, C.byref(v)))
         self.dataset_size = int(v.n)
+
+    def upload_seq_dataset(self, trajs: dict, reward_scale: float = 1.0, cost_scale: float = 1.0) -> None:
+        """trajs: flat per-transition arrays in trajectory order (observations, actions, returns, cost_returns,
+        costs), `traj_offsets` [n_traj+1] and optional `sample_prob` [n_traj] -> osrl_seq_buffer_upload."""
+        keep = {k: np.ascontiguousarray(trajs[k], dtype=np.float32)
+                for k in ("observations", "actions", "returns", "cost_returns", "costs")}
+        keep["traj_offsets"] = np.ascontiguousarray(trajs["traj_offsets"], dtype=np.int64)
+        v = SeqDatasetView()
+        v.n, v.n_traj = keep["observations"].shape[0], keep["traj_offsets"].shape[0] - 1
+        for k, a in keep.items():
+            setattr(v, k, a.ctypes.data)
+        if trajs.get("sample_prob") is not None:
+            keep["sample_prob"] = np.ascontiguousarray(trajs["sample_prob"], dtype=np.float64)
+            v.sample_prob = keep["sample_prob"].ctypes.data
+        v.reward_scale, v.cost_scale = float(reward_scale), float(cost_scale)
+        check(self.lib.osrl_seq_buffer_upload(self.h, C.byref(v)))
+        self.n_traj = int(v.n_traj)
+
+    def seq_gather(self, traj_idx, start_idx) -> Dict[str, torch.Tensor]:
+        """[n, T, .] windows for explicit (trajectory, start) pairs -> CUDA tensors (bit-exact copies)."""
+        ti = np.ascontiguousarray(traj_idx, dtype=np.int32)
+        si = np.ascontiguousarray(start_idx, dtype=np.int32)
+        n, T, o, a = ti.shape[0], self.cfg.seq_len, self.cfg.obs_dim, self.cfg.act_dim
+        dev = f"cuda:{self.device}"
+        out = {"states": torch.empty(n, T, o, device=dev), "actions": torch.empty(n, T, a, device=dev),
+               "returns": torch.empty(n, T, device=dev), "costs_return": torch.empty(n, T, device=dev),
+               "time_steps": torch.empty(n, T, dtype=torch.int64, device=dev), "mask": torch.empty(n, T, device=dev),
+               "costs": torch.empty(n, T, device=dev)}
+        b = SeqBatch()
+        b.rows, b.seq_len, b.on_host = n, T, 0
+        for k, t in out.items():
+            setattr(b, k, t.data_ptr())
+        check(self.lib.osrl_seq_gather(self.h, C.c_void_p(ti.ctypes.data), C.c_void_p(si.ctypes.data), n, C.byref(b),
+                                       C.c_void_p(self._stream())))
+        return out
+
+    def alias_table(self):
+        prob = np.empty(self.n_traj, dtype=np.float32)
+        alias = np.empty(self.n_traj, dtype=np.int32)
+        check(self.lib.osrl_seq_alias_table(self.h, C.c_void_p(prob.ctypes.data), C.c_void_p(alias.ctypes.data), self.n_traj))
+        return prob, alias
+
+    def last_sequences(self):
+        t = np.empty(self.batch_size, dtype=np.int32)
+        s = np.empty(self.batch_size, dtype=np.int32)
+        check(self.lib.osrl_last_sequences(self.h, C.c_void_p(t.ctypes.data), C.c_void_p(s.ctypes.data), self.batch_size))
+        return t, s
 
     def gather(self, idx) -> Dict[str, torch.Tensor]:
         """Bit-exact row gather by explicit indices -> six CUDA tensors."""

@@ -133,3 +133,84 @@ def test_cdt_against_live_oracle(lib_built, case, gemm):
     assert strict >= 0.85 * total, (strict, total)
     assert abs(eng.scalars()["log_temperature"] - float(orc.log_temperature)) < 1e-6
     eng.close()
+
+
+def _seq_setup(B=32):
+    from oracle import synth
+    from osrl_b200 import Engine
+    from osrl_b200.common.dataset import SequenceDataset
+    d = synth.make_dataset(6, 3, 41, 25, seed=9)
+    d["timeouts"][-7:] = False
+    ds = SequenceDataset(d, seq_len=10, reward_scale=0.1, cost_scale=1.0, cost_sample=True,
+                         cost_transform=lambda x: 70 - x)
+    eng = Engine("cdt", batch_size=B, device=0, seed=4321, state_dim=6, action_dim=3, max_action=1.0, seq_len=10,
+                 episode_len=100, embedding_dim=32, num_layers=1, num_heads=4, use_rew=1, use_cost=1, cost_transform=1,
+                 stochastic=1, target_entropy=-3.0)
+    ds.to_engine(eng)
+    return d, ds, eng
+
+
+def test_sequence_gather_bit_exact_and_sampler(lib_built):
+    """K0s: windows for explicit (trajectory, start) pairs == SequenceDataset.__prepare_sample bit for bit
+    (slice, float32 scaling, end zero-pad, mask, unclipped time_steps; dataset.py:749-775); the on-device draw
+    == the numpy restatement; the alias table reproduces sample_prob."""
+    from oracle.sampler import philox_sequences
+    d, ds, eng = _seq_setup()
+    tr = ocdt.split_trajectories(d)
+    rng = np.random.default_rng(1)
+    tj = rng.integers(0, len(tr), 300)
+    st = np.array([rng.integers(0, tr[t]["rewards"].shape[0]) for t in tj])
+    tj[:3], st[:3] = [0, len(tr) - 1, 5], [0, 40, 39]
+    out = eng.seq_gather(tj, st)
+    for i, (t, s) in enumerate(zip(tj, st)):
+        want = ocdt.sequence_sample(tr, int(t), int(s), 10, 0.1, 1.0)
+        for k, w in zip(("states", "actions", "returns", "costs_return", "time_steps", "mask"), want[:6]):
+            assert np.array_equal(out[k][i].cpu().numpy().astype(np.asarray(w).dtype), np.asarray(w)), (k, t, s)
+        assert np.array_equal(out["costs"][i].cpu().numpy(), want[7])
+    prob, alias = eng.alias_table()
+    n = len(tr)
+    p = prob.astype(np.float64) / n
+    for s_ in range(n):
+        p[alias[s_]] += (1.0 - prob[s_]) / n
+    assert np.allclose(p, ds.sample_prob, atol=2e-7)
+    for step in range(3):
+        eng.steps(1)
+        t_eng, s_eng = eng.last_sequences()
+        t_ref, s_ref = philox_sequences(4321, step, 0, 32, prob, alias, ds.offsets)
+        assert np.array_equal(t_eng, t_ref) and np.array_equal(s_eng, s_ref)
+        assert all(np.isfinite(v) for v in eng.stats().values())
+    eng.close()
+
+
+def test_cdt_trainer_api_matches_reference_fixture(lib_built):
+    """The public mirror (osrl_b200.algorithms.CDT / CDTTrainer) driven like examples/train/train_cdt.py:181-187
+    reproduces the reference-produced stats of tests/golden/cdt_small.npz."""
+    from osrl_b200.algorithms import CDT, CDTTrainer
+    z, meta = load_golden("cdt_small")
+    c = meta["cfg"]
+
+    class Log:
+        rows = []
+
+        def store(self, tab=None, **kw):
+            self.rows.append(kw)
+
+    torch.manual_seed(0)
+    model = CDT(c["state_dim"], c["action_dim"], 1.0, seq_len=c["seq_len"], episode_len=c["episode_len"],
+                embedding_dim=c["embedding_dim"], num_layers=c["num_layers"], num_heads=c["num_heads"], time_emb=True,
+                use_rew=True, use_cost=True, cost_transform=True, stochastic=True, init_temperature=0.1,
+                target_entropy=-c["action_dim"], device="cuda:0")
+    for k in meta["keys"]:
+        assert torch.equal(model.state_dict()[k], torch.from_numpy(z["init/" + k])), k   # same seed -> same init
+    log = Log()
+    tr = CDTTrainer(model, None, log, learning_rate=c["learning_rate"], weight_decay=c["weight_decay"],
+                    betas=tuple(c["betas"]), clip_grad=c["clip_grad"], lr_warmup_steps=c["lr_warmup_steps"],
+                    loss_cost_weight=c["loss_cost_weight"], loss_state_weight=c["loss_state_weight"], device="cuda:0")
+    for s in range(meta["steps"]):
+        tr.train_one_step(*[torch.from_numpy(z[f"batch{s}/{k}"]) for k in CDT_KEYS])
+        for k, w in zip(meta["stat_keys"], z["stats"][s]):
+            assert abs(log.rows[-1][k] - w) <= 2e-5 * max(abs(w), 1e-3) + 1e-7, (s, k)
+    sd = model.state_dict()     # views of the engine arena
+    k = "blocks.0.mlp.0.weight"
+    ref = torch.from_numpy(z["final/" + k])
+    assert sd[k].is_cuda and float((sd[k].cpu() - ref).norm()) <= 1e-3 * float((ref - torch.from_numpy(z["init/" + k])).norm())
