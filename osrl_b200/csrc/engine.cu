@@ -108,8 +108,8 @@ static int count_tiles(std::vector<GemmTask>& ts, int BM, int BN, bool assign) {
   int tot = 0;
   for (auto& t : ts) {
     const int tm = (t.M + BM - 1) / BM, tn = (t.N + BN - 1) / BN;
-    if (assign) { t.tile0 = tot; t.tiles_n = tn; }
-    tot += tm * tn;
+    if (assign) { t.tile0 = tot; t.tiles_n = tn; t.tiles_mn = tm * tn; }
+    tot += tm * tn * (t.ksplit > 1 ? t.ksplit : 1);
   }
   return tot;
 }
@@ -121,7 +121,31 @@ void emit_gemm(Engine& e, Program& p, const std::vector<GemmTask>& tasks_in) {
     // 16-byte cp.async needs base, leading dimension and the contiguous extent 4-float aligned
     t.a_vec = ((uintptr_t)t.A % 16 == 0) && (t.lda % 4 == 0) && ((t.a_kc ? t.K : t.M) % 4 == 0);
     t.b_vec = ((uintptr_t)t.B % 16 == 0) && (t.ldb % 4 == 0) && ((t.b_kc ? t.K : t.N) % 4 == 0);
+    // split-K for weight gradients over many rows (CDT: K = 81,920 tokens onto a 128x384 tile grid): the
+    // splits add their partials atomically into a pre-zeroed C (contiguous [M, N]) and bias gradient
+    t.ksplit = 1;
+    t.klen = (t.K + 63) / 64 * 64;
+    const bool plain = !t.bias && !t.resid && !t.dact && !t.aux && !t.clamp && t.act == ACT_NONE && t.scale == 1.f;
+    if (plain && t.K >= 8192 && t.ldc == t.N) {
+      const int tiles = ((t.M + 63) / 64) * ((t.N + 63) / 64);
+      int want = std::max(1, 444 / std::max(1, tiles));
+      want = std::min(want, t.K / 1024);
+      if (want > 1) {
+        t.klen = ((t.K + want - 1) / want + 63) / 64 * 64;
+        t.ksplit = (t.K + t.klen - 1) / t.klen;
+      }
+    }
   }
+  for (auto& t : tasks)
+    if (t.ksplit > 1) {   // zero the accumulation targets ahead of the launch
+      float* C = t.C;
+      float* cs = t.colsum;
+      const size_t cb = (size_t)t.M * t.N * sizeof(float), sb = (size_t)t.M * sizeof(float);
+      p.add("memset", 0.0, 0.0, false, [=](cudaStream_t s) {
+        cudaMemsetAsync(C, 0, cb, s);
+        if (cs) cudaMemsetAsync(cs, 0, sb, s);
+      });
+    }
   // largest tile shape that still yields >= ~1 wave-fraction of CTAs (148 SMs)
   int cfg = 2;
   if (count_tiles(tasks, 128, 64, false) >= 120) cfg = 0;

@@ -43,6 +43,9 @@ struct GemmTask {
   int dact;               // 0 none, ACT_RELU: *= (src > 0), ACT_TANH: *= 1 - src^2
   int tile0;              // index of this task's first tile in the launch
   int tiles_n;            // tiles along N
+  int tiles_mn;           // tiles of one k-split (tiles_m * tiles_n)
+  int ksplit;             // >1: split-K -- each split atomically adds its partial into a pre-zeroed C / colsum
+  int klen;               // k extent of one split (multiple of every BK)
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -165,10 +168,12 @@ k_gemm_tasks(const GemmTask* __restrict__ tasks, int ntasks) {
   }
   __syncthreads();
   const GemmTask& t = ts;
-  const int lt = blockIdx.x - t.tile0;
+  const int lt0 = blockIdx.x - t.tile0;
+  const int split = lt0 / t.tiles_mn, lt = lt0 % t.tiles_mn;
   const int m0 = (lt / t.tiles_n) * BM;
   const int n0 = (lt % t.tiles_n) * BN;
-  const int M = t.M, N = t.N, K = t.K;
+  const int kbeg = split * t.klen;
+  const int M = t.M, N = t.N, K = min(t.K, kbeg + t.klen);   // K = end of this CTA's k range
   const float* __restrict__ A = t.A;
   const float* __restrict__ B = t.B;
   const int lda = t.lda, ldb = t.ldb;
@@ -188,13 +193,13 @@ k_gemm_tasks(const GemmTask* __restrict__ tasks, int ntasks) {
   for (int i = 0; i < TM; ++i) rs[i] = 0.f;
   const bool want_colsum = (t.colsum != nullptr) && (n0 == 0) && (tx == 0);
 
-  const int nk = (K + BK - 1) / BK;
+  const int nk = (K - kbeg + BK - 1) / BK;
   // prologue: NSTAGE-1 slabs in flight
 #pragma unroll
   for (int s = 0; s < NSTAGE - 1; ++s) {
     if (s < nk) {
-      stage_operand<BM, BK, NT>(As + s * Cfg::A_STAGE, A, lda, akc, avec, m0, s * BK, M, K, tid);
-      stage_operand<BN, BK, NT>(Bs + s * Cfg::B_STAGE, B, ldb, bkc, bvec, n0, s * BK, N, K, tid);
+      stage_operand<BM, BK, NT>(As + s * Cfg::A_STAGE, A, lda, akc, avec, m0, kbeg + s * BK, M, K, tid);
+      stage_operand<BN, BK, NT>(Bs + s * Cfg::B_STAGE, B, ldb, bkc, bvec, n0, kbeg + s * BK, N, K, tid);
     }
     cp_async_commit();
   }
@@ -206,8 +211,8 @@ k_gemm_tasks(const GemmTask* __restrict__ tasks, int ntasks) {
       const int nx = kt + NSTAGE - 1;
       if (nx < nk) {
         const int sb = nx % NSTAGE;
-        stage_operand<BM, BK, NT>(As + sb * Cfg::A_STAGE, A, lda, akc, avec, m0, nx * BK, M, K, tid);
-        stage_operand<BN, BK, NT>(Bs + sb * Cfg::B_STAGE, B, ldb, bkc, bvec, n0, nx * BK, N, K, tid);
+        stage_operand<BM, BK, NT>(As + sb * Cfg::A_STAGE, A, lda, akc, avec, m0, kbeg + nx * BK, M, K, tid);
+        stage_operand<BN, BK, NT>(Bs + sb * Cfg::B_STAGE, B, ldb, bkc, bvec, n0, kbeg + nx * BK, N, K, tid);
       }
       cp_async_commit();
     }
@@ -256,12 +261,13 @@ k_gemm_tasks(const GemmTask* __restrict__ tasks, int ntasks) {
   for (int i = 0; i < TM; ++i) {
     const int gi = m0 + ty * TM + i;
     if (gi >= M) continue;
-    if (want_colsum) t.colsum[gi] = rs[i];
+    if (want_colsum) { if (t.ksplit > 1) atomicAdd(&t.colsum[gi], rs[i]); else t.colsum[gi] = rs[i]; }
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       const int gj = n0 + (bkc ? tx + j * TXN : tx * TN + j);
       if (gj >= N) continue;
       float v = acc[i][j];
+      if (t.ksplit > 1) { atomicAdd(&t.C[(size_t)gi * t.ldc + gj], v); continue; }
       if (t.bias) v += t.bias[gj];
       if (t.aux && t.act == ACT_GELU) t.aux[(size_t)gi * t.ldaux + gj] = v;  // GELU keeps the pre-activation
       v = apply_act(v, t.act);

@@ -85,13 +85,13 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 
 template <class Cfg, int BM, int BN, int BK, int NSTAGE, bool AKC, bool BKC>
 __device__ __forceinline__ void gemm_mma_body(const GemmTask& t, float* __restrict__ As, float* __restrict__ Bs,
-                                              int m0, int n0) {
+                                              int m0, int n0, int kbeg) {
   constexpr int NT = Cfg::NT, MT = Cfg::MT, NTL = Cfg::NTL;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tq = lane & 3;
   const int wm = (warp / Cfg::WARPS_N) * Cfg::WTM;
   const int wn = (warp % Cfg::WARPS_N) * Cfg::WTN;
-  const int M = t.M, N = t.N, K = t.K;
+  const int M = t.M, N = t.N, K = min(t.K, kbeg + t.klen);   // K = end of this CTA's k range (split-K)
   const float* __restrict__ A = t.A;
   const float* __restrict__ B = t.B;
   const int lda = t.lda, ldb = t.ldb;
@@ -109,12 +109,12 @@ __device__ __forceinline__ void gemm_mma_body(const GemmTask& t, float* __restri
   for (int i = 0; i < MT; ++i) rs[i][0] = rs[i][1] = 0.f;
   const bool want_colsum = (t.colsum != nullptr) && (n0 == 0) && (wn == 0);
 
-  const int nk = (K + BK - 1) / BK;
+  const int nk = (K - kbeg + BK - 1) / BK;
 #pragma unroll
   for (int s = 0; s < NSTAGE - 1; ++s) {
     if (s < nk) {
-      stage_op<BM, BK, NT, AKC>(As + s * Cfg::A_STAGE, A, lda, avec, m0, s * BK, M, K, tid);
-      stage_op<BN, BK, NT, BKC>(Bs + s * Cfg::B_STAGE, B, ldb, bvec, n0, s * BK, N, K, tid);
+      stage_op<BM, BK, NT, AKC>(As + s * Cfg::A_STAGE, A, lda, avec, m0, kbeg + s * BK, M, K, tid);
+      stage_op<BN, BK, NT, BKC>(Bs + s * Cfg::B_STAGE, B, ldb, bvec, n0, kbeg + s * BK, N, K, tid);
     }
     cp_async_commit();
   }
@@ -125,8 +125,8 @@ __device__ __forceinline__ void gemm_mma_body(const GemmTask& t, float* __restri
       const int nx = kt + NSTAGE - 1;
       if (nx < nk) {
         const int sb = nx % NSTAGE;
-        stage_op<BM, BK, NT, AKC>(As + sb * Cfg::A_STAGE, A, lda, avec, m0, nx * BK, M, K, tid);
-        stage_op<BN, BK, NT, BKC>(Bs + sb * Cfg::B_STAGE, B, ldb, bvec, n0, nx * BK, N, K, tid);
+        stage_op<BM, BK, NT, AKC>(As + sb * Cfg::A_STAGE, A, lda, avec, m0, kbeg + nx * BK, M, K, tid);
+        stage_op<BN, BK, NT, BKC>(Bs + sb * Cfg::B_STAGE, B, ldb, bvec, n0, kbeg + nx * BK, N, K, tid);
       }
       cp_async_commit();
     }
@@ -205,7 +205,7 @@ __device__ __forceinline__ void gemm_mma_body(const GemmTask& t, float* __restri
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         v += __shfl_xor_sync(0xffffffffu, v, 2);
         const int gi = m0 + wm + i * 16 + g + h * 8;
-        if (tq == 0 && gi < M) t.colsum[gi] = v;
+        if (tq == 0 && gi < M) { if (t.ksplit > 1) atomicAdd(&t.colsum[gi], v); else t.colsum[gi] = v; }
       }
   }
   // ---- fused epilogue: c0,c1 -> (row g, cols 2t,2t+1); c2,c3 -> (row g+8, same cols)
@@ -219,6 +219,7 @@ __device__ __forceinline__ void gemm_mma_body(const GemmTask& t, float* __restri
         const int gj = n0 + wn + j * 8 + 2 * tq + (q & 1);
         if (gi >= M || gj >= N) continue;
         float v = acc[i][j][q];
+        if (t.ksplit > 1) { atomicAdd(&t.C[(size_t)gi * t.ldc + gj], v); continue; }
         if (t.bias) v += t.bias[gj];
         if (t.aux && t.act == ACT_GELU) t.aux[(size_t)gi * t.ldaux + gj] = v;  // GELU keeps the pre-activation
         v = apply_act(v, t.act);
@@ -249,15 +250,17 @@ k_gemm_mma(const GemmTask* __restrict__ tasks, int ntasks) {
   }
   __syncthreads();
   const GemmTask& t = ts;
-  const int lt = blockIdx.x - t.tile0;
+  const int lt0 = blockIdx.x - t.tile0;
+  const int split = lt0 / t.tiles_mn, lt = lt0 % t.tiles_mn;
   const int m0 = (lt / t.tiles_n) * BM;
   const int n0 = (lt % t.tiles_n) * BN;
+  const int kbeg = split * t.klen;
   // CTA-uniform dispatch on the operand layouts: each body is fully specialised (no layout branches
   // in the k-loop).  forward: A,B k-contiguous; dgrad: A k-contiguous, B n-contiguous; wgrad: both mn.
-  if (t.a_kc && t.b_kc) gemm_mma_body<Cfg, BM, BN, BK, NSTAGE, true, true>(t, As, Bs, m0, n0);
-  else if (t.a_kc && !t.b_kc) gemm_mma_body<Cfg, BM, BN, BK, NSTAGE, true, false>(t, As, Bs, m0, n0);
-  else if (!t.a_kc && !t.b_kc) gemm_mma_body<Cfg, BM, BN, BK, NSTAGE, false, false>(t, As, Bs, m0, n0);
-  else gemm_mma_body<Cfg, BM, BN, BK, NSTAGE, false, true>(t, As, Bs, m0, n0);
+  if (t.a_kc && t.b_kc) gemm_mma_body<Cfg, BM, BN, BK, NSTAGE, true, true>(t, As, Bs, m0, n0, kbeg);
+  else if (t.a_kc && !t.b_kc) gemm_mma_body<Cfg, BM, BN, BK, NSTAGE, true, false>(t, As, Bs, m0, n0, kbeg);
+  else if (!t.a_kc && !t.b_kc) gemm_mma_body<Cfg, BM, BN, BK, NSTAGE, false, false>(t, As, Bs, m0, n0, kbeg);
+  else gemm_mma_body<Cfg, BM, BN, BK, NSTAGE, false, true>(t, As, Bs, m0, n0, kbeg);
 }
 
 }  // namespace osrl

@@ -14,6 +14,7 @@ eng = Engine("cdt", batch_size=B, device=0, seed=1, state_dim=17, action_dim=6, 
              target_entropy=-6.0, learning_rate=1e-4, lr_warmup_steps=500, loss_cost_weight=0.02)
 eng.load_params(orc.params)
 d = synth.make_dataset(17, 6, 1000, 200, seed=0)
+d["costs"] = (np.random.default_rng(1).random(d["costs"].shape[0]) < 0.03).astype(np.float32)  # ~30 per episode (< 70)
 SequenceDataset(d, seq_len=10, reward_scale=0.1, cost_scale=1.0, cost_sample=True, cost_transform=lambda x: 70 - x).to_engine(eng)
 eng.steps(5); torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
