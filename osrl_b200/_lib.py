@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libosrl_b200.so")
+LIB_PATH = os.path.join(_HERE, os.environ.get("OSRL_B200_LIBNAME", "libosrl_b200.so"))
 
 OSRL_MAX_HIDDEN = 4
 OSRL_MAX_NOISE = 8

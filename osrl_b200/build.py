@@ -8,7 +8,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libosrl_b200.so")
+LIB = os.path.join(HERE, os.environ.get("OSRL_B200_LIBNAME", "libosrl_b200.so"))
 SOURCES = ["plan.cu", "engine.cu", "blocks.cu", "algo_bcql.cu", "algo_cpq_bearl.cu", "algo_cdt.cu"]
 HEADERS = ["engine.h", "gemm.cuh", "gemm_mma.cuh", "kernels.cuh", "cdt_kernels.cuh", os.path.join("..", "..", "include", "osrl_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -39,7 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(CSRC, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [nvcc, *NVCC_FLAGS, "-c", s, "-o", o]
+            cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("OSRL_NVCC_EXTRA", "").split(), "-c", s, "-o", o]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -65,30 +65,37 @@ GemmTask task_wgrad(const float* dY, int lddy, const float* X, int ldx, int rows
 #define OSRL_GEMM_CFG0 128, 64, 16, 8, 4, 4
 #define OSRL_GEMM_CFG1 64, 64, 32, 4, 4, 4
 #define OSRL_GEMM_CFG2 32, 32, 32, 2, 2, 6
-template <int BM, int BN, int BK, int TM, int TN, int NS>
-static void launch_gemm(const GemmTask* d, int ntasks, int tiles, cudaStream_t s) {
-  using Cfg = GemmCfg<BM, BN, BK, TM, TN, NS>;
-  k_gemm_tasks<BM, BN, BK, TM, TN, NS><<<tiles, Cfg::NT, Cfg::SMEM_BYTES, s>>>(d, ntasks);
-}
-template <int BM, int BN, int BK, int TM, int TN, int NS>
-static void prepare_gemm() {
-  using Cfg = GemmCfg<BM, BN, BK, TM, TN, NS>;
-  OSRL_CUDA(cudaFuncSetAttribute(k_gemm_tasks<BM, BN, BK, TM, TN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 Cfg::SMEM_BYTES));
-}
 // tensor-core (3xTF32 mma.sync) tile shapes: {BM, BN, BK, WARPS_M, WARPS_N, NSTAGE}
 #define OSRL_MMA_CFG0 128, 64, 16, 4, 2, 4
 #define OSRL_MMA_CFG1 64, 64, 32, 2, 4, 4
 #define OSRL_MMA_CFG2 32, 32, 32, 2, 2, 6
-template <int BM, int BN, int BK, int WM, int WN, int NS>
+// Every kernel exists in two variants: the basic one (the MLP algorithms: bias/ReLU/Tanh/residual/clamp
+// epilogues) and FULL (adds exact GELU + split-K accumulation, used by the launches of the CDT program that
+// need them).  Keeping the extras out of the basic variant is worth ~20 % on the BCQ-Lag step.
+template <int BM, int BN, int BK, int TM, int TN, int NS, bool FULL>
+static void launch_gemm(const GemmTask* d, int ntasks, int tiles, cudaStream_t s) {
+  using Cfg = GemmCfg<BM, BN, BK, TM, TN, NS>;
+  k_gemm_tasks<BM, BN, BK, TM, TN, NS, FULL><<<tiles, Cfg::NT, Cfg::SMEM_BYTES, s>>>(d, ntasks);
+}
+template <int BM, int BN, int BK, int TM, int TN, int NS>
+static void prepare_gemm() {
+  using Cfg = GemmCfg<BM, BN, BK, TM, TN, NS>;
+  OSRL_CUDA(cudaFuncSetAttribute(k_gemm_tasks<BM, BN, BK, TM, TN, NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::SMEM_BYTES));
+  OSRL_CUDA(cudaFuncSetAttribute(k_gemm_tasks<BM, BN, BK, TM, TN, NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::SMEM_BYTES));
+}
+template <int BM, int BN, int BK, int WM, int WN, int NS, bool FULL>
 static void launch_mma(const GemmTask* d, int ntasks, int tiles, cudaStream_t s) {
   using Cfg = MmaCfg<BM, BN, BK, WM, WN, NS>;
-  k_gemm_mma<BM, BN, BK, WM, WN, NS><<<tiles, Cfg::NT, Cfg::SMEM_BYTES, s>>>(d, ntasks);
+  k_gemm_mma<BM, BN, BK, WM, WN, NS, FULL><<<tiles, Cfg::NT, Cfg::SMEM_BYTES, s>>>(d, ntasks);
 }
 template <int BM, int BN, int BK, int WM, int WN, int NS>
 static void prepare_mma() {
   using Cfg = MmaCfg<BM, BN, BK, WM, WN, NS>;
-  OSRL_CUDA(cudaFuncSetAttribute(k_gemm_mma<BM, BN, BK, WM, WN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  OSRL_CUDA(cudaFuncSetAttribute(k_gemm_mma<BM, BN, BK, WM, WN, NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::SMEM_BYTES));
+  OSRL_CUDA(cudaFuncSetAttribute(k_gemm_mma<BM, BN, BK, WM, WN, NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  Cfg::SMEM_BYTES));
 }
 // OSRL_GEMM=ffma selects the CUDA-core kernel (gemm.cuh); default is the 3xTF32 tensor-core kernel
@@ -165,16 +172,21 @@ void emit_gemm(Engine& e, Program& p, const std::vector<GemmTask>& tasks_in) {
   static const char* mnames[3] = {"k_gemm_mma<128,64,16,4,2,4>", "k_gemm_mma<64,64,32,2,4,4>",
                                   "k_gemm_mma<32,32,32,2,2,6>"};
   const bool mma = use_mma();
+  bool full = false;
+  for (auto& t : tasks) full = full || t.ksplit > 1 || t.act == ACT_GELU || t.dact == ACT_GELU;
   p.add(mma ? mnames[cfg] : names[cfg], bytes, flops, true, [=](cudaStream_t s) {
-    if (mma) {
-      if (cfg == 0) launch_mma<OSRL_MMA_CFG0>(d, nt, tiles, s);
-      else if (cfg == 1) launch_mma<OSRL_MMA_CFG1>(d, nt, tiles, s);
-      else launch_mma<OSRL_MMA_CFG2>(d, nt, tiles, s);
-    } else {
-      if (cfg == 0) launch_gemm<OSRL_GEMM_CFG0>(d, nt, tiles, s);
-      else if (cfg == 1) launch_gemm<OSRL_GEMM_CFG1>(d, nt, tiles, s);
-      else launch_gemm<OSRL_GEMM_CFG2>(d, nt, tiles, s);
+#define OSRL_DISPATCH(FULL_)                                                      \
+    if (mma) {                                                                    \
+      if (cfg == 0) launch_mma<OSRL_MMA_CFG0, FULL_>(d, nt, tiles, s);            \
+      else if (cfg == 1) launch_mma<OSRL_MMA_CFG1, FULL_>(d, nt, tiles, s);       \
+      else launch_mma<OSRL_MMA_CFG2, FULL_>(d, nt, tiles, s);                     \
+    } else {                                                                      \
+      if (cfg == 0) launch_gemm<OSRL_GEMM_CFG0, FULL_>(d, nt, tiles, s);          \
+      else if (cfg == 1) launch_gemm<OSRL_GEMM_CFG1, FULL_>(d, nt, tiles, s);     \
+      else launch_gemm<OSRL_GEMM_CFG2, FULL_>(d, nt, tiles, s);                   \
     }
+    if (full) { OSRL_DISPATCH(true) } else { OSRL_DISPATCH(false) }
+#undef OSRL_DISPATCH
     ep->launches++;
   });
 }

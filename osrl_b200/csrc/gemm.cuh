@@ -51,17 +51,50 @@ struct GemmTask {
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_RELU) return v > 0.f ? v : 0.f;
   if (act == ACT_TANH) return tanhf(v);
-  if (act == ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));  // nn.GELU() exact (erf) form
   return v;
 }
-// derivative mask of the fused dgrad epilogue; `s` is the stored forward value named by GemmTask::dact_src
-// (post-activation for ReLU/Tanh, PRE-activation for GELU)
-__device__ __forceinline__ float apply_dact(float v, float s, int dact) {
-  if (dact == ACT_RELU) return s > 0.f ? v : 0.f;
-  if (dact == ACT_TANH) return v * (1.f - s * s);
-  if (dact == ACT_GELU)
-    return v * (0.5f * (1.f + erff(s * 0.70710678118654752f)) + s * 0.3989422804014327f * expf(-0.5f * s * s));
-  return v;
+
+// ---- "FULL" epilogue extras (CDT): exact-erf GELU and its derivative, kept out of line and compiled only into
+// the FULL kernel variants -- inlined into the common epilogue they get if-converted and cost the ReLU/Tanh
+// layers ~12 % (measured on B200).
+static __device__ __noinline__ float gelu_fwd(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }
+static __device__ __noinline__ float gelu_bwd(float s) {
+  return 0.5f * (1.f + erff(s * 0.70710678118654752f)) + s * 0.3989422804014327f * expf(-0.5f * s * s);
+}
+
+// one output element through the fused epilogue.  FULL adds GELU (aux keeps the PRE-activation, the dgrad mask
+// reads it back) and split-K accumulation.
+template <bool FULL>
+__device__ __forceinline__ void epilogue_store(const GemmTask& t, int gi, int gj, float v) {
+  if constexpr (FULL) {
+    if (t.ksplit > 1) { atomicAdd(&t.C[(size_t)gi * t.ldc + gj], v); return; }
+  }
+  if (t.bias) v += t.bias[gj];
+  if constexpr (FULL) {
+    if (t.act == ACT_GELU) {
+      if (t.aux) t.aux[(size_t)gi * t.ldaux + gj] = v;
+      v = gelu_fwd(v);
+    } else {
+      v = apply_act(v, t.act);
+      if (t.aux) t.aux[(size_t)gi * t.ldaux + gj] = v;
+    }
+  } else {
+    v = apply_act(v, t.act);
+    if (t.aux) t.aux[(size_t)gi * t.ldaux + gj] = v;
+  }
+  v *= t.scale;
+  if (t.resid) v += t.resid[(size_t)gi * t.ldr + gj];
+  if (t.clamp) v = fminf(fmaxf(v, t.lo), t.hi);
+  if (t.dact) {
+    const float s = t.dact_src[(size_t)gi * t.ld_dact + gj];
+    if constexpr (FULL) {
+      if (t.dact == ACT_GELU) v *= gelu_bwd(s);
+      else v = (t.dact == ACT_RELU) ? (s > 0.f ? v : 0.f) : v * (1.f - s * s);
+    } else {
+      v = (t.dact == ACT_RELU) ? (s > 0.f ? v : 0.f) : v * (1.f - s * s);
+    }
+  }
+  t.C[(size_t)gi * t.ldc + gj] = v;
 }
 
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, bool valid) {
@@ -148,7 +181,7 @@ __device__ __forceinline__ void stage_operand(float* __restrict__ s, const float
   }
 }
 
-template <int BM, int BN, int BK, int TM, int TN, int NSTAGE>
+template <int BM, int BN, int BK, int TM, int TN, int NSTAGE, bool FULL>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 k_gemm_tasks(const GemmTask* __restrict__ tasks, int ntasks) {
   using Cfg = GemmCfg<BM, BN, BK, TM, TN, NSTAGE>;
@@ -168,12 +201,11 @@ k_gemm_tasks(const GemmTask* __restrict__ tasks, int ntasks) {
   }
   __syncthreads();
   const GemmTask& t = ts;
-  const int lt0 = blockIdx.x - t.tile0;
-  const int split = lt0 / t.tiles_mn, lt = lt0 % t.tiles_mn;
+  int lt = blockIdx.x - t.tile0, kbeg = 0;
+  if constexpr (FULL) { kbeg = (lt / t.tiles_mn) * t.klen; lt %= t.tiles_mn; }
   const int m0 = (lt / t.tiles_n) * BM;
   const int n0 = (lt % t.tiles_n) * BN;
-  const int kbeg = split * t.klen;
-  const int M = t.M, N = t.N, K = min(t.K, kbeg + t.klen);   // K = end of this CTA's k range
+  const int M = t.M, N = t.N, K = FULL ? min(t.K, kbeg + t.klen) : t.K;   // K = end of this CTA's k range
   const float* __restrict__ A = t.A;
   const float* __restrict__ B = t.B;
   const int lda = t.lda, ldb = t.ldb;
@@ -261,24 +293,15 @@ k_gemm_tasks(const GemmTask* __restrict__ tasks, int ntasks) {
   for (int i = 0; i < TM; ++i) {
     const int gi = m0 + ty * TM + i;
     if (gi >= M) continue;
-    if (want_colsum) { if (t.ksplit > 1) atomicAdd(&t.colsum[gi], rs[i]); else t.colsum[gi] = rs[i]; }
+    if (want_colsum) {
+      if (FULL && t.ksplit > 1) atomicAdd(&t.colsum[gi], rs[i]);
+      else t.colsum[gi] = rs[i];
+    }
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       const int gj = n0 + (bkc ? tx + j * TXN : tx * TN + j);
       if (gj >= N) continue;
-      float v = acc[i][j];
-      if (t.ksplit > 1) { atomicAdd(&t.C[(size_t)gi * t.ldc + gj], v); continue; }
-      if (t.bias) v += t.bias[gj];
-      if (t.aux && t.act == ACT_GELU) t.aux[(size_t)gi * t.ldaux + gj] = v;  // GELU keeps the pre-activation
-      v = apply_act(v, t.act);
-      if (t.aux && t.act != ACT_GELU) t.aux[(size_t)gi * t.ldaux + gj] = v;
-      v *= t.scale;
-      if (t.resid) v += t.resid[(size_t)gi * t.ldr + gj];
-      if (t.clamp) v = fminf(fmaxf(v, t.lo), t.hi);
-      if (t.dact) {
-        v = apply_dact(v, t.dact_src[(size_t)gi * t.ld_dact + gj], t.dact);
-      }
-      t.C[(size_t)gi * t.ldc + gj] = v;
+      epilogue_store<FULL>(t, gi, gj, acc[i][j]);
     }
   }
 }

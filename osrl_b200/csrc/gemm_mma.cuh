@@ -83,7 +83,7 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-template <class Cfg, int BM, int BN, int BK, int NSTAGE, bool AKC, bool BKC>
+template <class Cfg, int BM, int BN, int BK, int NSTAGE, bool AKC, bool BKC, bool FULL>
 __device__ __forceinline__ void gemm_mma_body(const GemmTask& t, float* __restrict__ As, float* __restrict__ Bs,
                                               int m0, int n0, int kbeg) {
   constexpr int NT = Cfg::NT, MT = Cfg::MT, NTL = Cfg::NTL;
@@ -91,7 +91,7 @@ __device__ __forceinline__ void gemm_mma_body(const GemmTask& t, float* __restri
   const int g = lane >> 2, tq = lane & 3;
   const int wm = (warp / Cfg::WARPS_N) * Cfg::WTM;
   const int wn = (warp % Cfg::WARPS_N) * Cfg::WTN;
-  const int M = t.M, N = t.N, K = min(t.K, kbeg + t.klen);   // K = end of this CTA's k range (split-K)
+  const int M = t.M, N = t.N, K = FULL ? min(t.K, kbeg + t.klen) : t.K;   // K = end of this CTA's k range
   const float* __restrict__ A = t.A;
   const float* __restrict__ B = t.B;
   const int lda = t.lda, ldb = t.ldb;
@@ -205,7 +205,10 @@ __device__ __forceinline__ void gemm_mma_body(const GemmTask& t, float* __restri
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         v += __shfl_xor_sync(0xffffffffu, v, 2);
         const int gi = m0 + wm + i * 16 + g + h * 8;
-        if (tq == 0 && gi < M) { if (t.ksplit > 1) atomicAdd(&t.colsum[gi], v); else t.colsum[gi] = v; }
+        if (tq == 0 && gi < M) {
+          if (FULL && t.ksplit > 1) atomicAdd(&t.colsum[gi], v);
+          else t.colsum[gi] = v;
+        }
       }
   }
   // ---- fused epilogue: c0,c1 -> (row g, cols 2t,2t+1); c2,c3 -> (row g+8, same cols)
@@ -218,23 +221,11 @@ __device__ __forceinline__ void gemm_mma_body(const GemmTask& t, float* __restri
         const int gi = m0 + wm + i * 16 + g + (q >> 1) * 8;
         const int gj = n0 + wn + j * 8 + 2 * tq + (q & 1);
         if (gi >= M || gj >= N) continue;
-        float v = acc[i][j][q];
-        if (t.ksplit > 1) { atomicAdd(&t.C[(size_t)gi * t.ldc + gj], v); continue; }
-        if (t.bias) v += t.bias[gj];
-        if (t.aux && t.act == ACT_GELU) t.aux[(size_t)gi * t.ldaux + gj] = v;  // GELU keeps the pre-activation
-        v = apply_act(v, t.act);
-        if (t.aux && t.act != ACT_GELU) t.aux[(size_t)gi * t.ldaux + gj] = v;
-        v *= t.scale;
-        if (t.resid) v += t.resid[(size_t)gi * t.ldr + gj];
-        if (t.clamp) v = fminf(fmaxf(v, t.lo), t.hi);
-        if (t.dact) {
-          v = apply_dact(v, t.dact_src[(size_t)gi * t.ld_dact + gj], t.dact);
-        }
-        t.C[(size_t)gi * t.ldc + gj] = v;
+        epilogue_store<FULL>(t, gi, gj, acc[i][j][q]);
       }
 }
 
-template <int BM, int BN, int BK, int WM_, int WN_, int NSTAGE>
+template <int BM, int BN, int BK, int WM_, int WN_, int NSTAGE, bool FULL>
 __global__ void __launch_bounds__(WM_* WN_ * 32)
 k_gemm_mma(const GemmTask* __restrict__ tasks, int ntasks) {
   using Cfg = MmaCfg<BM, BN, BK, WM_, WN_, NSTAGE>;
@@ -250,17 +241,16 @@ k_gemm_mma(const GemmTask* __restrict__ tasks, int ntasks) {
   }
   __syncthreads();
   const GemmTask& t = ts;
-  const int lt0 = blockIdx.x - t.tile0;
-  const int split = lt0 / t.tiles_mn, lt = lt0 % t.tiles_mn;
+  int lt = blockIdx.x - t.tile0, kbeg = 0;
+  if constexpr (FULL) { kbeg = (lt / t.tiles_mn) * t.klen; lt %= t.tiles_mn; }
   const int m0 = (lt / t.tiles_n) * BM;
   const int n0 = (lt % t.tiles_n) * BN;
-  const int kbeg = split * t.klen;
   // CTA-uniform dispatch on the operand layouts: each body is fully specialised (no layout branches
   // in the k-loop).  forward: A,B k-contiguous; dgrad: A k-contiguous, B n-contiguous; wgrad: both mn.
-  if (t.a_kc && t.b_kc) gemm_mma_body<Cfg, BM, BN, BK, NSTAGE, true, true>(t, As, Bs, m0, n0, kbeg);
-  else if (t.a_kc && !t.b_kc) gemm_mma_body<Cfg, BM, BN, BK, NSTAGE, true, false>(t, As, Bs, m0, n0, kbeg);
-  else if (!t.a_kc && !t.b_kc) gemm_mma_body<Cfg, BM, BN, BK, NSTAGE, false, false>(t, As, Bs, m0, n0, kbeg);
-  else gemm_mma_body<Cfg, BM, BN, BK, NSTAGE, false, true>(t, As, Bs, m0, n0, kbeg);
+  if (t.a_kc && t.b_kc) gemm_mma_body<Cfg, BM, BN, BK, NSTAGE, true, true, FULL>(t, As, Bs, m0, n0, kbeg);
+  else if (t.a_kc && !t.b_kc) gemm_mma_body<Cfg, BM, BN, BK, NSTAGE, true, false, FULL>(t, As, Bs, m0, n0, kbeg);
+  else if (!t.a_kc && !t.b_kc) gemm_mma_body<Cfg, BM, BN, BK, NSTAGE, false, false, FULL>(t, As, Bs, m0, n0, kbeg);
+  else gemm_mma_body<Cfg, BM, BN, BK, NSTAGE, false, true, FULL>(t, As, Bs, m0, n0, kbeg);
 }
 
 }  // namespace osrl
