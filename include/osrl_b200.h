@@ -216,6 +216,11 @@ int osrl_noise_layout(osrl_engine* e, const char** names, int64_t* counts, int c
 int osrl_last_indices(osrl_engine* e, int64_t* host_out, int cap);
 int osrl_last_noise(osrl_engine* e, int slot, float* host_out, int64_t cap);
 
+/* Debug/unit test: C[M,N] = act(A[M,K] * W[N,K]^T + bias) through one GEMM implementation
+ * ("ffma" CUDA cores, "mma" 3xTF32 mma.sync, "tc5" tcgen05/TMEM where eligible); host pointers. */
+int osrl_debug_linear(osrl_engine* e, const char* impl, int M, int N, int K, const float* A, const float* W,
+                      const float* bias, int act, float* C);
+
 /* Debug/parity: read `count` floats at float offset `offset` of an arena section
  * (0 params, 1 targets, 2 gradients of the last step, 3 Adam m, 4 Adam v). */
 int osrl_debug_read(osrl_engine* e, int section, int64_t offset, int64_t count, float* host_out);

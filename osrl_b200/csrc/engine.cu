@@ -1,6 +1,7 @@
 // Engine runtime + C ABI (see include/osrl_b200.h).
 #include "engine.h"
 #include "gemm_mma.cuh"
+#include "gemm_tc5.cuh"
 #include "cdt_kernels.cuh"
 
 #include <dlfcn.h>
@@ -98,10 +99,37 @@ static void prepare_mma() {
   OSRL_CUDA(cudaFuncSetAttribute(k_gemm_mma<BM, BN, BK, WM, WN, NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  Cfg::SMEM_BYTES));
 }
-// OSRL_GEMM=ffma selects the CUDA-core kernel (gemm.cuh); default is the 3xTF32 tensor-core kernel
-static bool use_mma() {   // read when an engine's program is built
+// OSRL_GEMM (read when an engine's program is built): "ffma" = CUDA-core kernel (gemm.cuh); "mma" = 3xTF32
+// mma.sync kernel for everything; default = mma.sync + the tcgen05/TMEM kernel (gemm_tc5.cuh) for the large
+// forward layers.
+static std::string gemm_mode() {
   const char* e = getenv("OSRL_GEMM");
-  return !(e && std::string(e) == "ffma");
+  return e ? std::string(e) : std::string("tc5");
+}
+static bool use_mma() { return gemm_mode() != "ffma"; }
+static bool tc5_eligible(const GemmTask& t) {
+  return t.a_kc && t.b_kc && t.a_vec && t.b_vec && t.ksplit <= 1 && t.M >= 512 && t.K >= 64 && t.N >= 64;
+}
+static void emit_tc5(Engine& e, Program& p, std::vector<GemmTask> tasks) {
+  int tot = 0;
+  double bytes = 0.0, flops = 0.0;
+  bool full = false;
+  for (auto& t : tasks) {
+    const int tm = (t.M + tc5::BM - 1) / tc5::BM, tn = (t.N + tc5::BN - 1) / tc5::BN;
+    t.tile0 = tot; t.tiles_n = tn; t.tiles_mn = tm * tn;
+    tot += tm * tn;
+    bytes += 4.0 * ((double)t.M * t.K + (double)t.K * t.N + (double)t.M * t.N);
+    flops += 2.0 * (double)t.M * t.N * t.K;
+    full = full || t.act == ACT_GELU || t.dact == ACT_GELU;
+  }
+  GemmTask* d = e.upload(tasks);
+  const int nt = (int)tasks.size(), tiles = tot;
+  Engine* ep = &e;
+  p.add("k_gemm_tc5<128,128,32>", bytes, flops, true, [=](cudaStream_t s) {
+    if (full) tc5::k_gemm_tc5<true><<<tiles, tc5::THREADS, tc5::SMEM_BYTES, s>>>(d, nt);
+    else tc5::k_gemm_tc5<false><<<tiles, tc5::THREADS, tc5::SMEM_BYTES, s>>>(d, nt);
+    ep->launches++;
+  });
 }
 void prepare_kernels() {
   prepare_gemm<OSRL_GEMM_CFG0>();
@@ -110,6 +138,8 @@ void prepare_kernels() {
   prepare_mma<OSRL_MMA_CFG0>();
   prepare_mma<OSRL_MMA_CFG1>();
   prepare_mma<OSRL_MMA_CFG2>();
+  OSRL_CUDA(cudaFuncSetAttribute(tc5::k_gemm_tc5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::SMEM_BYTES));
+  OSRL_CUDA(cudaFuncSetAttribute(tc5::k_gemm_tc5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::SMEM_BYTES));
 }
 static int count_tiles(std::vector<GemmTask>& ts, int BM, int BN, bool assign) {
   int tot = 0;
@@ -153,6 +183,15 @@ void emit_gemm(Engine& e, Program& p, const std::vector<GemmTask>& tasks_in) {
         if (cs) cudaMemsetAsync(cs, 0, sb, s);
       });
     }
+  if (gemm_mode() == "tc5") {   // large forward layers -> tcgen05 kernel, the rest stays on mma.sync
+    std::vector<GemmTask> big, rest;
+    for (auto& t : tasks) (tc5_eligible(t) ? big : rest).push_back(t);
+    if (!big.empty()) {
+      emit_tc5(e, p, big);
+      if (rest.empty()) return;
+      tasks = rest;
+    }
+  }
   // largest tile shape that still yields >= ~1 wave-fraction of CTAs (148 SMs)
   int cfg = 2;
   if (count_tiles(tasks, 128, 64, false) >= 120) cfg = 0;
@@ -961,6 +1000,33 @@ int osrl_last_noise(osrl_engine* h, int slot, float* host_out, int64_t cap) {
   OSRL_CUDA(cudaDeviceSynchronize());
   OSRL_CUDA(cudaMemcpy(host_out, e.noise_buf[slot], (size_t)e.plan.noise[slot].second * sizeof(float),
                        cudaMemcpyDeviceToHost));
+  OSRL_CATCH
+}
+
+int osrl_debug_linear(osrl_engine* h, const char* impl, int M, int N, int K, const float* A, const float* W,
+                      const float* bias, int act, float* C) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && impl && A && W && C && M > 0 && N > 0 && K > 0, "bad argument");
+  Engine& e = *h->e;
+  OSRL_CUDA(cudaSetDevice(e.device));
+  const size_t before = e.allocs.size();
+  float* dA = e.ws((size_t)M * K); float* dW = e.ws((size_t)N * K); float* db = e.ws(N); float* dC = e.ws((size_t)M * N);
+  OSRL_CUDA(cudaMemcpy(dA, A, (size_t)M * K * sizeof(float), cudaMemcpyHostToDevice));
+  OSRL_CUDA(cudaMemcpy(dW, W, (size_t)N * K * sizeof(float), cudaMemcpyHostToDevice));
+  if (bias) OSRL_CUDA(cudaMemcpy(db, bias, (size_t)N * sizeof(float), cudaMemcpyHostToDevice));
+  Lin l;
+  l.w = 0; l.b = 0; l.in = K; l.out = N;
+  GemmTask t = task_fwd(dA, K, M, dW, l, dC, N, act);
+  t.bias = bias ? db : nullptr;
+  Program prog;
+  setenv("OSRL_GEMM", impl, 1);
+  try { emit_gemm(e, prog, {t}); } catch (...) { unsetenv("OSRL_GEMM"); throw; }
+  unsetenv("OSRL_GEMM");
+  for (auto& op : prog.ops) op(e.cap_stream);
+  OSRL_CUDA(cudaStreamSynchronize(e.cap_stream));
+  OSRL_CUDA(cudaGetLastError());
+  OSRL_CUDA(cudaMemcpy(C, dC, (size_t)M * N * sizeof(float), cudaMemcpyDeviceToHost));
+  while (e.allocs.size() > before) { cudaFree(e.allocs.back()); e.allocs.pop_back(); }
   OSRL_CATCH
 }
 

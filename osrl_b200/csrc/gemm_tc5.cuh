@@ -1,0 +1,207 @@
+// tcgen05 / TMEM variant of the multi-task GEMM for the large forward layers (sm_100a).
+//
+// C[M,N] = A[M,K] * B[N,K]^T (both k-contiguous: activations x nn.Linear weights), fp32-accurate via
+// 3xTF32: every operand tile is written to shared memory twice, as hi = x with the low 13 mantissa bits
+// cleared and lo = x - hi (exact), and each k-step issues three tcgen05.mma.kind::tf32
+// (hi*hi + lo*hi + hi*lo) into a 128 x BN fp32 accumulator that lives in TMEM.
+//
+//   * CTA tile 128 x 128, BK = 32 floats = one 128-byte swizzle row; 3-stage ring of
+//     {A_hi, A_lo, B_hi, B_lo} (64 KB per stage) in the canonical K-major SWIZZLE_128B layout:
+//         byte(r, c16) = (r/8)*1024 + (r%8)*128 + ((c16 ^ (r%8)) * 16)        (c16 = 16-byte chunk along k)
+//     so coalesced global reads (8 lanes = one 128-byte row) become conflict-free shared stores.
+//   * warps 0-7: producers (global -> registers -> hi/lo -> shared, fence.proxy.async, mbarrier arrive)
+//     and, after the k-loop, the epilogue (tcgen05.ld 32x32b from TMEM -> fused epilogue -> global);
+//     warp 8: one elected lane issues the MMAs and tcgen05.commit's the stage-empty / accumulator-full
+//     mbarriers.  One CTA per SM (192 KB of shared memory).
+#pragma once
+#include "gemm.cuh"
+
+namespace osrl {
+namespace tc5 {
+
+constexpr int BM = 128, BN = 128, BK = 32, NSTAGE = 3;
+constexpr int PRODUCERS = 256, THREADS = PRODUCERS + 32;
+constexpr int TILE_BYTES = BM * BK * 4;                 // 16 KB (BM == BN)
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;             // A_hi, A_lo, B_hi, B_lo
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024; // + alignment slack
+constexpr int TMEM_COLS = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
+// LBO (ignored for swizzled K-major) = 1, SBO = 1024 B between 8-row groups, version 1, layout type 2.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format TF32 (2<<7, 2<<10), K-major A and B,
+// N>>3 at bit 17, M>>4 at bit 24
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_c),
+      "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// split one 16-byte chunk into hi (low 13 mantissa bits cleared = what kind::tf32 reads) and lo = x - hi
+__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
+  hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+  hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+  hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+  hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+  lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+}
+
+template <bool FULL>
+__global__ void __launch_bounds__(THREADS, 1) k_gemm_tc5(const GemmTask* __restrict__ tasks, int ntasks) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ GemmTask ts;
+  __shared__ __align__(8) uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], acc_bar;
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1 KB alignment
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    int ti = 0;
+    const int tile = blockIdx.x;
+    while (ti + 1 < ntasks && tasks[ti + 1].tile0 <= tile) ++ti;
+    ts = tasks[ti];
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], PRODUCERS / 32); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {   // TMEM allocation (one warp), address published through shared memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  const GemmTask& t = ts;
+  const int lt = blockIdx.x - t.tile0;
+  const int m0 = (lt / t.tiles_n) * BM, n0 = (lt % t.tiles_n) * BN;
+  const int M = t.M, N = t.N, K = t.K;
+  const int nk = (K + BK - 1) / BK;
+
+  if (warp < PRODUCERS / 32) {
+    // ------------------------------------------------ producers
+    const float* __restrict__ A = t.A;
+    const float* __restrict__ B = t.B;
+    const int lda = t.lda, ldb = t.ldb;
+    for (int kt = 0; kt < nk; ++kt) {
+      const int s = kt % NSTAGE;
+      if (kt >= NSTAGE) mbar_wait(&empty_bar[s], ((kt / NSTAGE) - 1) & 1);
+      uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+      const int k0 = kt * BK;
+      float4 va[4], vb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {   // 1024 chunks per operand tile, 4 per thread; 8 lanes = one 128-byte row
+        const int c = tid + PRODUCERS * i, r = c >> 3, ck = c & 7;
+        const int gk = k0 + ck * 4;
+        va[i] = (m0 + r < M && gk < K) ? *reinterpret_cast<const float4*>(A + (size_t)(m0 + r) * lda + gk)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[i] = (n0 + r < N && gk < K) ? *reinterpret_cast<const float4*>(B + (size_t)(n0 + r) * ldb + gk)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = tid + PRODUCERS * i, r = c >> 3, ck = c & 7;
+        const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((ck ^ (r & 7)) << 4);
+        float4 hi, lo;
+        split4(va[i], hi, lo);
+        *reinterpret_cast<float4*>(st + off) = hi;
+        *reinterpret_cast<float4*>(st + TILE_BYTES + off) = lo;
+        split4(vb[i], hi, lo);
+        *reinterpret_cast<float4*>(st + 2 * TILE_BYTES + off) = hi;
+        *reinterpret_cast<float4*>(st + 3 * TILE_BYTES + off) = lo;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+    }
+    // ------------------------------------------------ epilogue: TMEM -> registers -> fused epilogue -> global
+    mbar_wait(&acc_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3, half = warp >> 2;          // TMEM lane quarter of this warp / column half
+    const int gi = m0 + q * 32 + lane;
+#pragma unroll
+    for (int cb = 0; cb < 64; cb += 16) {
+      const int col = half * 64 + cb;
+      uint32_t v[16];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (gi < M) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int gj = n0 + col + j;
+          if (gj < N) epilogue_store<FULL>(t, gi, gj, __uint_as_float(v[j]));
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else if (lane == 0) {
+    // ------------------------------------------------ MMA issuer (one thread)
+    for (int kt = 0; kt < nk; ++kt) {
+      const int s = kt % NSTAGE;
+      mbar_wait(&full_bar[s], (kt / NSTAGE) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sb = smem_u32(smem + (size_t)s * STAGE_BYTES);
+      const uint64_t a_hi = make_desc(sb), a_lo = make_desc(sb + TILE_BYTES);
+      const uint64_t b_hi = make_desc(sb + 2 * TILE_BYTES), b_lo = make_desc(sb + 3 * TILE_BYTES);
+#pragma unroll
+      for (int k8 = 0; k8 < BK / 8; ++k8) {          // one MMA consumes K = 8 tf32 = 32 bytes of every row
+        const uint64_t adv = (uint64_t)((k8 * 32) >> 4);
+        mma_tf32_ss(tmem_base, a_lo + adv, b_hi + adv, (kt | k8) != 0);   // small terms first
+        mma_tf32_ss(tmem_base, a_hi + adv, b_lo + adv, 1);
+        mma_tf32_ss(tmem_base, a_hi + adv, b_hi + adv, 1);
+      }
+      commit(&empty_bar[s]);            // arrives when the MMAs above have finished reading this stage
+    }
+    commit(&acc_bar);                   // accumulator complete -> epilogue
+  }
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+}  // namespace tc5
+}  // namespace osrl

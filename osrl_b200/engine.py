@@ -161,6 +161,17 @@ class Engine:
             out[d.name.decode()] = t
         return out
 
+    def debug_linear(self, impl: str, A, W, bias=None, act: int = 0) -> torch.Tensor:
+        """act(A @ W.T + bias) through one GEMM kernel family ('ffma' | 'mma' | 'tc5'); unit-test hook."""
+        A = A.detach().float().cpu().contiguous(); W = W.detach().float().cpu().contiguous()
+        M, K = A.shape; N = W.shape[0]
+        out = torch.empty(M, N)
+        b = bias.detach().float().cpu().contiguous() if bias is not None else None
+        check(self.lib.osrl_debug_linear(self.h, impl.encode(), M, N, K, C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()),
+                                         C.c_void_p(b.data_ptr()) if b is not None else None, int(act),
+                                         C.c_void_p(out.data_ptr())))
+        return out
+
     def read_section(self, section: str) -> "OrderedDict[str, torch.Tensor]":
         """Trained-parameter-shaped tensors of another arena section: 'grad', 'adam_m', 'adam_v'."""
         sec = {"param": 0, "target": 1, "grad": 2, "adam_m": 3, "adam_v": 4}[section]

@@ -22,7 +22,7 @@ def _cfg(meta):
     return ocdt.CDTConfig(**c)
 
 
-def _engine(meta, B, gemm="mma"):
+def _engine(meta, B, gemm="tc5"):
     import os
     from osrl_b200 import Engine
     os.environ["OSRL_GEMM"] = gemm
@@ -75,7 +75,7 @@ def test_cdt_small_golden(lib_built):
     eng.close()
 
 
-@pytest.mark.parametrize("gemm", ["ffma", "mma"])
+@pytest.mark.parametrize("gemm", ["ffma", "mma", "tc5"])
 @pytest.mark.parametrize("case", ["cdt_small", "cdt_full"])
 def test_cdt_against_live_oracle(lib_built, case, gemm):
     z, meta = load_golden(case)

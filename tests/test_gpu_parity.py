@@ -29,10 +29,10 @@ pytestmark = pytest.mark.gpu
 BATCH_KEYS = ("observations", "next_observations", "actions", "rewards", "costs", "done")
 
 
-GEMMS = ["ffma", "mma"]   # OSRL_GEMM: CUDA-core fp32 GEMM / 3xTF32 tensor-core GEMM (the default)
+GEMMS = ["ffma", "mma", "tc5"]   # OSRL_GEMM: CUDA cores / 3xTF32 mma.sync / + tcgen05 for large layers (default)
 
 
-def _engine(meta, B, gemm="mma"):
+def _engine(meta, B, gemm="tc5"):
     import os
     from osrl_b200 import Engine
     os.environ["OSRL_GEMM"] = gemm          # read when the engine builds its step program
@@ -42,7 +42,7 @@ def _engine(meta, B, gemm="mma"):
         os.environ.pop("OSRL_GEMM", None)
 
 
-def _compare_step(tag, eng, s32, s64, g32, g64, before, p64, gemm="mma"):
+def _compare_step(tag, eng, s32, s64, g32, g64, before, p64, gemm="tc5"):
     """Engine (already stepped) vs the fp32 reference step, tolerance scaled by conditioning.
     Gradient outliers (ReLU kinks, see module docstring): the CUDA-core GEMM reproduces the reference's
     pre-activations to ~1e-7, so a kink flip is rare (<=5 % of tensors, <=1e-2); the 3xTF32 GEMM is ~1e-6
@@ -234,5 +234,5 @@ def test_sampled_steps_match_oracle_on_dumped_batch(lib_built):
              "actions": data["actions"][idx], "rewards": data["rewards"][idx] * np.float32(0.1),
              "costs": data["costs"][idx] * np.float32(1.0), "done": done[idx]}
         s32, s64, g32, g64, before, p64 = probe_step(orc, "bcql", b, noise=nz)
-        _compare_step(f"sampled step {s}", eng, s32, s64, g32, g64, before, p64, "mma")
+        _compare_step(f"sampled step {s}", eng, s32, s64, g32, g64, before, p64, "tc5")
     eng.close()
