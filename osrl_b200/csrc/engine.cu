@@ -114,8 +114,10 @@ static void emit_tc5(Engine& e, Program& p, std::vector<GemmTask> tasks) {
   int tot = 0;
   double bytes = 0.0, flops = 0.0;
   bool full = false;
+  const char* env = getenv("OSRL_TC5_BN");
+  const int BNsel = (env && std::string(env) == "128") ? 128 : 64;
   for (auto& t : tasks) {
-    const int tm = (t.M + tc5::BM - 1) / tc5::BM, tn = (t.N + tc5::BN - 1) / tc5::BN;
+    const int tm = (t.M + tc5::BM - 1) / tc5::BM, tn = (t.N + BNsel - 1) / BNsel;
     t.tile0 = tot; t.tiles_n = tn; t.tiles_mn = tm * tn;
     tot += tm * tn;
     bytes += 4.0 * ((double)t.M * t.K + (double)t.K * t.N + (double)t.M * t.N);
@@ -125,9 +127,16 @@ static void emit_tc5(Engine& e, Program& p, std::vector<GemmTask> tasks) {
   GemmTask* d = e.upload(tasks);
   const int nt = (int)tasks.size(), tiles = tot;
   Engine* ep = &e;
-  p.add("k_gemm_tc5<128,128,32>", bytes, flops, true, [=](cudaStream_t s) {
-    if (full) tc5::k_gemm_tc5<true><<<tiles, tc5::THREADS, tc5::SMEM_BYTES, s>>>(d, nt);
-    else tc5::k_gemm_tc5<false><<<tiles, tc5::THREADS, tc5::SMEM_BYTES, s>>>(d, nt);
+  p.add(BNsel == 128 ? "k_gemm_tc5<128,128,32>" : "k_gemm_tc5<128,64,32>", bytes, flops, true, [=](cudaStream_t s) {
+    using S128 = tc5::Shape<128, 3>;
+    using S64 = tc5::Shape<64, 2>;
+    if (BNsel == 128) {
+      if (full) tc5::k_gemm_tc5<128, 3, 1, true><<<tiles, tc5::THREADS, S128::SMEM_BYTES, s>>>(d, nt);
+      else tc5::k_gemm_tc5<128, 3, 1, false><<<tiles, tc5::THREADS, S128::SMEM_BYTES, s>>>(d, nt);
+    } else {
+      if (full) tc5::k_gemm_tc5<64, 2, 2, true><<<tiles, tc5::THREADS, S64::SMEM_BYTES, s>>>(d, nt);
+      else tc5::k_gemm_tc5<64, 2, 2, false><<<tiles, tc5::THREADS, S64::SMEM_BYTES, s>>>(d, nt);
+    }
     ep->launches++;
   });
 }
@@ -138,8 +147,14 @@ void prepare_kernels() {
   prepare_mma<OSRL_MMA_CFG0>();
   prepare_mma<OSRL_MMA_CFG1>();
   prepare_mma<OSRL_MMA_CFG2>();
-  OSRL_CUDA(cudaFuncSetAttribute(tc5::k_gemm_tc5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::SMEM_BYTES));
-  OSRL_CUDA(cudaFuncSetAttribute(tc5::k_gemm_tc5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::SMEM_BYTES));
+  OSRL_CUDA(cudaFuncSetAttribute(tc5::k_gemm_tc5<128, 3, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 tc5::Shape<128, 3>::SMEM_BYTES));
+  OSRL_CUDA(cudaFuncSetAttribute(tc5::k_gemm_tc5<128, 3, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 tc5::Shape<128, 3>::SMEM_BYTES));
+  OSRL_CUDA(cudaFuncSetAttribute(tc5::k_gemm_tc5<64, 2, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 tc5::Shape<64, 2>::SMEM_BYTES));
+  OSRL_CUDA(cudaFuncSetAttribute(tc5::k_gemm_tc5<64, 2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 tc5::Shape<64, 2>::SMEM_BYTES));
 }
 static int count_tiles(std::vector<GemmTask>& ts, int BM, int BN, bool assign) {
   int tot = 0;

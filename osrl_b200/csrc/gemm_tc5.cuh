@@ -19,12 +19,24 @@
 namespace osrl {
 namespace tc5 {
 
-constexpr int BM = 128, BN = 128, BK = 32, NSTAGE = 3;
+constexpr int BM = 128, BK = 32;
 constexpr int PRODUCERS = 256, THREADS = PRODUCERS + 32;
-constexpr int TILE_BYTES = BM * BK * 4;                 // 16 KB (BM == BN)
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;             // A_hi, A_lo, B_hi, B_lo
-constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024; // + alignment slack
-constexpr int TMEM_COLS = 128;
+constexpr int A_TILE_BYTES = BM * BK * 4;               // 16 KB
+// Two shapes: 128x128 tiles, 3 stages, register-prefetched loads, one CTA per SM (192 KB); and 128x64 tiles,
+// 2 stages, two CTAs per SM (2 x 97 KB) so one CTA's prologue / epilogue overlaps the other's k-loop and the
+// tail wave is half as long.
+template <int BN_, int NSTAGE_>
+struct Shape {
+  static constexpr int BN = BN_, NSTAGE = NSTAGE_;
+  static constexpr int B_TILE_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;   // A_hi, A_lo, B_hi, B_lo
+  static constexpr int EPI_BYTES = BM * (BN + 4) * 4;                        // epilogue tile (reuses the ring)
+  static constexpr int RING_BYTES = NSTAGE * STAGE_BYTES > EPI_BYTES ? NSTAGE * STAGE_BYTES : EPI_BYTES;
+  static constexpr int SMEM_BYTES = RING_BYTES + 1024;                       // + alignment slack
+  static constexpr int TMEM_COLS = BN;                                       // power of two >= 32
+  static constexpr uint32_t IDESC =
+      (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -54,18 +66,17 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
 }
-// cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format TF32 (2<<7, 2<<10), K-major A and B,
+// Shape::IDESC = cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format TF32 (2<<7, 2<<10), K-major A and B,
 // N>>3 at bit 17, M>>4 at bit 24
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-
-__device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc,
+                                            uint32_t accumulate) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_c),
-      "l"(da), "l"(db), "r"(IDESC), "r"(accumulate)
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void commit(uint64_t* bar) {
@@ -73,17 +84,25 @@ __device__ __forceinline__ void commit(uint64_t* bar) {
                : "memory");
 }
 
-// split one 16-byte chunk into hi (low 13 mantissa bits cleared = what kind::tf32 reads) and lo = x - hi
+// split one 16-byte chunk into hi = tf32(x) and lo = tf32(x - hi), both round-to-nearest: kind::tf32 would
+// otherwise TRUNCATE the low 13 mantissa bits of what it reads, which costs ~2 bits on the lo term
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
 __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
-  hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-  hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-  hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-  hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-  lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+  hi.x = rna_tf32(v.x); hi.y = rna_tf32(v.y); hi.z = rna_tf32(v.z); hi.w = rna_tf32(v.w);
+  lo.x = rna_tf32(v.x - hi.x); lo.y = rna_tf32(v.y - hi.y); lo.z = rna_tf32(v.z - hi.z); lo.w = rna_tf32(v.w - hi.w);
 }
 
-template <bool FULL>
-__global__ void __launch_bounds__(THREADS, 1) k_gemm_tc5(const GemmTask* __restrict__ tasks, int ntasks) {
+template <int BN_, int NSTAGE_, int MINB, bool FULL>
+__global__ void __launch_bounds__(THREADS, MINB) k_gemm_tc5(const GemmTask* __restrict__ tasks, int ntasks) {
+  using S = Shape<BN_, NSTAGE_>;
+  constexpr int BN = S::BN, NSTAGE = S::NSTAGE, STAGE_BYTES = S::STAGE_BYTES, TMEM_COLS = S::TMEM_COLS;
+  constexpr int A_T = A_TILE_BYTES, B_T = S::B_TILE_BYTES;
+  constexpr bool PREFETCH = (MINB == 1);
+  constexpr int BCH = BN * 8 / PRODUCERS;   // 16-byte chunks of the B tile per producer thread
   extern __shared__ uint8_t smem_raw[];
   __shared__ GemmTask ts;
   __shared__ __align__(8) uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], acc_bar;
@@ -120,21 +139,29 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc5(const GemmTask* __restr
     const float* __restrict__ A = t.A;
     const float* __restrict__ B = t.B;
     const int lda = t.lda, ldb = t.ldb;
-    for (int kt = 0; kt < nk; ++kt) {
-      const int s = kt % NSTAGE;
-      if (kt >= NSTAGE) mbar_wait(&empty_bar[s], ((kt / NSTAGE) - 1) & 1);
-      uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+    // register double buffer: the global loads of slab kt+1 are in flight while slab kt is split and stored,
+    // so a k-step costs the shared-store time, not a global round trip
+    auto load_slab = [&](int kt, float4 (&va)[4], float4 (&vb)[BCH]) {
       const int k0 = kt * BK;
-      float4 va[4], vb[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {   // 1024 chunks per operand tile, 4 per thread; 8 lanes = one 128-byte row
+      for (int i = 0; i < 4; ++i) {   // 1024 chunks of the A tile, 4 per thread; 8 lanes = one 128-byte row
         const int c = tid + PRODUCERS * i, r = c >> 3, ck = c & 7;
         const int gk = k0 + ck * 4;
         va[i] = (m0 + r < M && gk < K) ? *reinterpret_cast<const float4*>(A + (size_t)(m0 + r) * lda + gk)
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < BCH; ++i) {
+        const int c = tid + PRODUCERS * i, r = c >> 3, ck = c & 7;
+        const int gk = k0 + ck * 4;
         vb[i] = (n0 + r < N && gk < K) ? *reinterpret_cast<const float4*>(B + (size_t)(n0 + r) * ldb + gk)
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    };
+    auto store_slab = [&](int kt, const float4 (&va)[4], const float4 (&vb)[BCH]) {
+      const int s = kt % NSTAGE;
+      if (kt >= NSTAGE) mbar_wait(&empty_bar[s], ((kt / NSTAGE) - 1) & 1);
+      uint8_t* st = smem + (size_t)s * STAGE_BYTES;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int c = tid + PRODUCERS * i, r = c >> 3, ck = c & 7;
@@ -142,23 +169,51 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc5(const GemmTask* __restr
         float4 hi, lo;
         split4(va[i], hi, lo);
         *reinterpret_cast<float4*>(st + off) = hi;
-        *reinterpret_cast<float4*>(st + TILE_BYTES + off) = lo;
+        *reinterpret_cast<float4*>(st + A_T + off) = lo;
+      }
+#pragma unroll
+      for (int i = 0; i < BCH; ++i) {
+        const int c = tid + PRODUCERS * i, r = c >> 3, ck = c & 7;
+        const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((ck ^ (r & 7)) << 4);
+        float4 hi, lo;
         split4(vb[i], hi, lo);
-        *reinterpret_cast<float4*>(st + 2 * TILE_BYTES + off) = hi;
-        *reinterpret_cast<float4*>(st + 3 * TILE_BYTES + off) = lo;
+        *reinterpret_cast<float4*>(st + 2 * A_T + off) = hi;
+        *reinterpret_cast<float4*>(st + 2 * A_T + B_T + off) = lo;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[s]);
+    };
+    if constexpr (PREFETCH) {
+      float4 a0[4], b0[BCH], a1[4], b1[BCH];
+      load_slab(0, a0, b0);
+      for (int kt = 0; kt < nk; kt += 2) {
+        if (kt + 1 < nk) load_slab(kt + 1, a1, b1);
+        store_slab(kt, a0, b0);
+        if (kt + 1 < nk) {
+          if (kt + 2 < nk) load_slab(kt + 2, a0, b0);
+          store_slab(kt + 1, a1, b1);
+        }
+      }
+    } else {   // two CTAs per SM: the co-resident CTA covers this one's load latency
+      float4 a0[4], b0[BCH];
+      for (int kt = 0; kt < nk; ++kt) {
+        load_slab(kt, a0, b0);
+        store_slab(kt, a0, b0);
+      }
     }
     // ------------------------------------------------ epilogue: TMEM -> registers -> fused epilogue -> global
     mbar_wait(&acc_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int q = warp & 3, half = warp >> 2;          // TMEM lane quarter of this warp / column half
-    const int gi = m0 + q * 32 + lane;
+    // phase 1: accumulator rows -> shared tile [128][TP] (the stage ring is free: every MMA has completed).
+    // A thread owns one accumulator ROW, so storing straight to global would touch 32 sectors per request
+    // (ncu: 8x write amplification); the tile is re-read row-wise so that lanes hold consecutive columns.
+    constexpr int TP = BN + 4;
+    float* tile = reinterpret_cast<float*>(smem);
 #pragma unroll
-    for (int cb = 0; cb < 64; cb += 16) {
-      const int col = half * 64 + cb;
+    for (int cb = 0; cb < BN / 2; cb += 16) {
+      const int col = half * (BN / 2) + cb;
       uint32_t v[16];
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col;
       asm volatile(
@@ -167,12 +222,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc5(const GemmTask* __restr
             "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (gi < M) {
+      float* dst = tile + (q * 32 + lane) * TP + col;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int gj = n0 + col + j;
-          if (gj < N) epilogue_store<FULL>(t, gi, gj, __uint_as_float(v[j]));
-        }
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                          __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(PRODUCERS) : "memory");   // the 8 epilogue warps only
+    // phase 2: fused epilogue + coalesced stores (32 lanes = 32 consecutive columns of one row)
+    for (int r = warp; r < BM; r += PRODUCERS / 32) {
+      const int gi = m0 + r;
+      if (gi >= M) break;
+#pragma unroll
+      for (int j = 0; j < BN / 32; ++j) {
+        const int gj = n0 + j * 32 + lane;
+        if (gj < N) epilogue_store<FULL>(t, gi, gj, tile[r * TP + j * 32 + lane]);
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -183,14 +247,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc5(const GemmTask* __restr
       mbar_wait(&full_bar[s], (kt / NSTAGE) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t sb = smem_u32(smem + (size_t)s * STAGE_BYTES);
-      const uint64_t a_hi = make_desc(sb), a_lo = make_desc(sb + TILE_BYTES);
-      const uint64_t b_hi = make_desc(sb + 2 * TILE_BYTES), b_lo = make_desc(sb + 3 * TILE_BYTES);
+      const uint64_t a_hi = make_desc(sb), a_lo = make_desc(sb + A_T);
+      const uint64_t b_hi = make_desc(sb + 2 * A_T), b_lo = make_desc(sb + 2 * A_T + B_T);
 #pragma unroll
       for (int k8 = 0; k8 < BK / 8; ++k8) {          // one MMA consumes K = 8 tf32 = 32 bytes of every row
         const uint64_t adv = (uint64_t)((k8 * 32) >> 4);
-        mma_tf32_ss(tmem_base, a_lo + adv, b_hi + adv, (kt | k8) != 0);   // small terms first
-        mma_tf32_ss(tmem_base, a_hi + adv, b_lo + adv, 1);
-        mma_tf32_ss(tmem_base, a_hi + adv, b_hi + adv, 1);
+        mma_tf32_ss(tmem_base, a_lo + adv, b_hi + adv, S::IDESC, (kt | k8) != 0);   // small terms first
+        mma_tf32_ss(tmem_base, a_hi + adv, b_lo + adv, S::IDESC, 1);
+        mma_tf32_ss(tmem_base, a_hi + adv, b_hi + adv, S::IDESC, 1);
       }
       commit(&empty_bar[s]);            // arrives when the MMAs above have finished reading this stage
     }
