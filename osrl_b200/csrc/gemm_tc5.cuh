@@ -33,7 +33,10 @@ struct Shape {
   static constexpr int EPI_BYTES = BM * (BN + 4) * 4;                        // epilogue tile (reuses the ring)
   static constexpr int RING_BYTES = NSTAGE * STAGE_BYTES > EPI_BYTES ? NSTAGE * STAGE_BYTES : EPI_BYTES;
   static constexpr int SMEM_BYTES = RING_BYTES + 1024;                       // + alignment slack
-  static constexpr int TMEM_COLS = BN;                                       // power of two >= 32
+  // three accumulators of BN columns: hi*hi terms alternate between two of them (even / odd k8) and the small
+  // lo*hi + hi*lo corrections get their own, so the tensor core's truncating fp32 accumulation is applied to a
+  // third as many large-magnitude additions (measured: ~3e-6 -> ~1e-6 of max|C| at K = 400)
+  static constexpr int TMEM_COLS = BN == 64 ? 256 : 512;                     // power of two >= 3 * BN
   static constexpr uint32_t IDESC =
       (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 };
@@ -214,19 +217,25 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gemm_tc5(const GemmTask* __re
 #pragma unroll
     for (int cb = 0; cb < BN / 2; cb += 16) {
       const int col = half * (BN / 2) + cb;
-      uint32_t v[16];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-          : "r"(taddr));
+      uint32_t v[3][16];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + col);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(v[a][0]), "=r"(v[a][1]), "=r"(v[a][2]), "=r"(v[a][3]), "=r"(v[a][4]), "=r"(v[a][5]), "=r"(v[a][6]),
+              "=r"(v[a][7]), "=r"(v[a][8]), "=r"(v[a][9]), "=r"(v[a][10]), "=r"(v[a][11]), "=r"(v[a][12]),
+              "=r"(v[a][13]), "=r"(v[a][14]), "=r"(v[a][15])
+            : "r"(taddr));
+      }
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       float* dst = tile + (q * 32 + lane) * TP + col;
+      float f[16];
 #pragma unroll
-      for (int j = 0; j < 16; j += 4)
-        *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                          __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      for (int j = 0; j < 16; ++j)
+        f[j] = (__uint_as_float(v[0][j]) + __uint_as_float(v[1][j])) + __uint_as_float(v[2][j]);
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(PRODUCERS) : "memory");   // the 8 epilogue warps only
     // phase 2: fused epilogue + coalesced stores (32 lanes = 32 consecutive columns of one row)
@@ -252,9 +261,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gemm_tc5(const GemmTask* __re
 #pragma unroll
       for (int k8 = 0; k8 < BK / 8; ++k8) {          // one MMA consumes K = 8 tf32 = 32 bytes of every row
         const uint64_t adv = (uint64_t)((k8 * 32) >> 4);
-        mma_tf32_ss(tmem_base, a_lo + adv, b_hi + adv, S::IDESC, (kt | k8) != 0);   // small terms first
-        mma_tf32_ss(tmem_base, a_hi + adv, b_lo + adv, S::IDESC, 1);
-        mma_tf32_ss(tmem_base, a_hi + adv, b_hi + adv, S::IDESC, 1);
+        mma_tf32_ss(tmem_base + 2 * BN, a_lo + adv, b_hi + adv, S::IDESC, (kt | k8) != 0);
+        mma_tf32_ss(tmem_base + 2 * BN, a_hi + adv, b_lo + adv, S::IDESC, 1);
+        mma_tf32_ss(tmem_base + (k8 & 1) * BN, a_hi + adv, b_hi + adv, S::IDESC, kt != 0 || k8 >= 2);
       }
       commit(&empty_bar[s]);            // arrives when the MMAs above have finished reading this stage
     }

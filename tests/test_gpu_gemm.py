@@ -28,6 +28,7 @@ def test_linear_matches_torch(lib_built, impl):
             ref32 = {0: ref32, 1: ref32.relu(), 2: ref32.tanh()}[act].double()
             err32 = float((ref32 - want64).abs().max()) / scale
             # tcgen05 accumulates all K/8*3 MMAs of a tile in TMEM (truncating adder, no intermediate flush)
-            tol = 6e-6 if impl == "tc5" else 2e-6
+            tol = 2e-6
+            print(f"{impl} {M}x{N}x{K} act {act}: err {err:.2e} torch-fp32 {err32:.2e}")
             assert err <= max(tol, 4 * err32), f"{impl} {M}x{N}x{K} act {act}: err {err:.2e} (torch fp32 {err32:.2e})"
     eng.close()
