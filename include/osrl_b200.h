@@ -221,6 +221,13 @@ int osrl_last_noise(osrl_engine* e, int slot, float* host_out, int64_t cap);
 int osrl_debug_linear(osrl_engine* e, const char* impl, int M, int N, int K, const float* A, const float* W,
                       const float* bias, int act, float* C);
 
+/* Debug/unit test: C[M,N] = op(A) * op(B) through one GEMM implementation, any operand layout the step uses:
+ * a_kc=1: A is [M,K] row-major (k contiguous), a_kc=0: A is [K,M]; b_kc=1: B is [N,K], b_kc=0: B is [K,N].
+ * colsum (optional, [M]) receives sum_k A(i,k) -- the bias-gradient by-product of a weight-gradient GEMM.
+ * Host pointers.  (Forward = 1,1; dgrad = 1,0; wgrad = 0,0.) */
+int osrl_debug_gemm(osrl_engine* e, const char* impl, int M, int N, int K, const float* A, int a_kc, const float* B,
+                    int b_kc, float* C, float* colsum);
+
 /* Debug/parity: read `count` floats at float offset `offset` of an arena section
  * (0 params, 1 targets, 2 gradients of the last step, 3 Adam m, 4 Adam v). */
 int osrl_debug_read(osrl_engine* e, int section, int64_t offset, int64_t count, float* host_out);

@@ -106,6 +106,8 @@ SYMBOLS = [
     ("osrl_last_noise", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
     ("osrl_debug_linear", C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int, C.c_void_p]),
+    ("osrl_debug_gemm", C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                  C.c_void_p, C.c_void_p]),
     ("osrl_debug_read", C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p]),
     ("osrl_profile", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_char_p), C.POINTER(C.c_double),
                                C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_void_p]),

@@ -2,6 +2,7 @@
 #include "engine.h"
 #include "gemm_mma.cuh"
 #include "gemm_tc5.cuh"
+#include "gemm_thin.cuh"
 #include "cdt_kernels.cuh"
 
 #include <dlfcn.h>
@@ -107,6 +108,41 @@ static std::string gemm_mode() {
   return e ? std::string(e) : std::string("tc5");
 }
 static bool use_mma() { return gemm_mode() != "ffma"; }
+// problems with an extent <= 16 (first / last MLP layers and their gradients) -> gemm_thin.cuh.  OSRL_THIN=0 keeps
+// them on the tiled kernels (A/B timing, tests).
+static int thin_kind(const GemmTask& t) {
+  static const bool on = [] { const char* v = getenv("OSRL_THIN"); return !(v && v[0] == '0'); }();
+  if (!on || gemm_mode() == "ffma") return THIN_NONE;
+  if (t.act == ACT_GELU || t.dact == ACT_GELU) return THIN_NONE;
+  if (t.K <= 16) return t.colsum ? THIN_NONE : THIN_K;
+  if (!t.a_kc && !t.b_kc) {   // batch reduction: 16 k-groups per CTA walk K serially, long K stays on split-K tiles
+    if (t.K > 4096) return THIN_NONE;
+    if (t.N <= 16) return THIN_R_WIDE_M;
+    if (t.M <= 16) return THIN_R_WIDE_N;
+    return THIN_NONE;
+  }
+  if (t.N <= 16 && t.a_kc && !t.colsum) return THIN_N;
+  return THIN_NONE;
+}
+static void emit_thin(Engine& e, Program& p, std::vector<GemmTask> tasks) {
+  int tot = 0;
+  double bytes = 0.0, flops = 0.0;
+  for (auto& t : tasks) {
+    int tn = 1;
+    const int n = thin_tiles(t, t.thin, &tn);
+    t.tile0 = tot; t.tiles_n = tn; t.tiles_mn = n; t.ksplit = 1;
+    tot += n;
+    bytes += 4.0 * ((double)t.M * t.K + (double)t.K * t.N + (double)t.M * t.N);
+    flops += 2.0 * (double)t.M * t.N * t.K;
+  }
+  GemmTask* d = e.upload(tasks);
+  const int nt = (int)tasks.size(), tiles = tot;
+  Engine* ep = &e;
+  p.add("k_gemm_thin", bytes, flops, true, [=](cudaStream_t s) {
+    k_gemm_thin<<<tiles, THIN_THREADS, 0, s>>>(d, nt);
+    ep->launches++;
+  });
+}
 static bool tc5_eligible(const GemmTask& t) {
   return t.a_kc && t.b_kc && t.a_vec && t.b_vec && t.ksplit <= 1 && t.M >= 512 && t.K >= 64 && t.N >= 64;
 }
@@ -167,9 +203,18 @@ static int count_tiles(std::vector<GemmTask>& ts, int BM, int BN, bool assign) {
 }
 void emit_gemm(Engine& e, Program& p, const std::vector<GemmTask>& tasks_in) {
   if (tasks_in.empty()) return;
-  std::vector<GemmTask> tasks = tasks_in;
+  std::vector<GemmTask> tasks;
+  {
+    std::vector<GemmTask> thin;
+    for (auto t : tasks_in) {
+      OSRL_REQUIRE(t.M > 0 && t.N > 0 && t.K > 0, "empty gemm task");
+      t.thin = thin_kind(t);
+      (t.thin ? thin : tasks).push_back(t);
+    }
+    if (!thin.empty()) emit_thin(e, p, thin);
+    if (tasks.empty()) return;
+  }
   for (auto& t : tasks) {
-    OSRL_REQUIRE(t.M > 0 && t.N > 0 && t.K > 0, "empty gemm task");
     // 16-byte cp.async needs base, leading dimension and the contiguous extent 4-float aligned
     t.a_vec = ((uintptr_t)t.A % 16 == 0) && (t.lda % 4 == 0) && ((t.a_kc ? t.K : t.M) % 4 == 0);
     t.b_vec = ((uintptr_t)t.B % 16 == 0) && (t.ldb % 4 == 0) && ((t.b_kc ? t.K : t.N) % 4 == 0);
@@ -1041,6 +1086,35 @@ int osrl_debug_linear(osrl_engine* h, const char* impl, int M, int N, int K, con
   OSRL_CUDA(cudaStreamSynchronize(e.cap_stream));
   OSRL_CUDA(cudaGetLastError());
   OSRL_CUDA(cudaMemcpy(C, dC, (size_t)M * N * sizeof(float), cudaMemcpyDeviceToHost));
+  while (e.allocs.size() > before) { cudaFree(e.allocs.back()); e.allocs.pop_back(); }
+  OSRL_CATCH
+}
+
+int osrl_debug_gemm(osrl_engine* h, const char* impl, int M, int N, int K, const float* A, int a_kc, const float* B,
+                    int b_kc, float* C, float* colsum) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && impl && A && B && C && M > 0 && N > 0 && K > 0, "bad argument");
+  Engine& e = *h->e;
+  OSRL_CUDA(cudaSetDevice(e.device));
+  const size_t before = e.allocs.size();
+  float* dA = e.ws((size_t)M * K); float* dB = e.ws((size_t)N * K); float* dC = e.ws((size_t)M * N); float* dS = e.ws(M);
+  OSRL_CUDA(cudaMemcpy(dA, A, (size_t)M * K * sizeof(float), cudaMemcpyHostToDevice));
+  OSRL_CUDA(cudaMemcpy(dB, B, (size_t)N * K * sizeof(float), cudaMemcpyHostToDevice));
+  GemmTask t = blank_task();
+  t.A = dA; t.a_kc = a_kc; t.lda = a_kc ? K : M;
+  t.B = dB; t.b_kc = b_kc; t.ldb = b_kc ? K : N;
+  t.C = dC; t.ldc = N;
+  t.M = M; t.N = N; t.K = K;
+  t.colsum = colsum ? dS : nullptr;
+  Program prog;
+  setenv("OSRL_GEMM", impl, 1);
+  try { emit_gemm(e, prog, {t}); } catch (...) { unsetenv("OSRL_GEMM"); throw; }
+  unsetenv("OSRL_GEMM");
+  for (auto& op : prog.ops) op(e.cap_stream);
+  OSRL_CUDA(cudaStreamSynchronize(e.cap_stream));
+  OSRL_CUDA(cudaGetLastError());
+  OSRL_CUDA(cudaMemcpy(C, dC, (size_t)M * N * sizeof(float), cudaMemcpyDeviceToHost));
+  if (colsum) OSRL_CUDA(cudaMemcpy(colsum, dS, (size_t)M * sizeof(float), cudaMemcpyDeviceToHost));
   while (e.allocs.size() > before) { cudaFree(e.allocs.back()); e.allocs.pop_back(); }
   OSRL_CATCH
 }

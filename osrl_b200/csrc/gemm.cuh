@@ -46,7 +46,30 @@ struct GemmTask {
   int tiles_mn;           // tiles of one k-split (tiles_m * tiles_n)
   int ksplit;             // >1: split-K -- each split atomically adds its partial into a pre-zeroed C / colsum
   int klen;               // k extent of one split (multiple of every BK)
+  int thin;               // ThinKind (gemm_thin.cuh): 0 = tiled kernels, else which thin body runs the task
 };
+
+// Which task owns tile `tile`?  tile0 is increasing over the list, so the owner is the last task with tile0 <= tile.
+// Warp 0 tests 32 tasks per step with one ballot and copies the descriptor word-parallel into shared memory (a
+// single thread walking the list costs one dependent L2 round trip per task -- microseconds for the 8-16 task
+// launches of an ensemble layer, more than a thin tile's whole body).  Ends with a CTA barrier.
+__device__ __forceinline__ void load_task(GemmTask* ts, const GemmTask* __restrict__ tasks, int ntasks, int tile) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    int ti = 0;
+    for (int base = 0; base < ntasks; base += 32) {
+      const int i = base + lane;
+      const bool le = i < ntasks && tasks[i].tile0 <= tile;
+      const unsigned m = __ballot_sync(0xffffffffu, le);
+      if (m) ti = base + 31 - __clz(m);
+      if (m != 0xffffffffu) break;
+    }
+    const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(tasks + ti);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(ts);
+    for (int w = lane; w < (int)(sizeof(GemmTask) / 4); w += 32) dst[w] = src[w];
+  }
+  __syncthreads();
+}
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_RELU) return v > 0.f ? v : 0.f;
@@ -193,13 +216,7 @@ k_gemm_tasks(const GemmTask* __restrict__ tasks, int ntasks) {
   __shared__ GemmTask ts;
 
   const int tid = threadIdx.x;
-  if (tid == 0) {
-    int ti = 0;
-    const int tile = blockIdx.x;
-    while (ti + 1 < ntasks && tasks[ti + 1].tile0 <= tile) ++ti;
-    ts = tasks[ti];
-  }
-  __syncthreads();
+  load_task(&ts, tasks, ntasks, blockIdx.x);
   const GemmTask& t = ts;
   int lt = blockIdx.x - t.tile0, kbeg = 0;
   if constexpr (FULL) { kbeg = (lt / t.tiles_mn) * t.klen; lt %= t.tiles_mn; }

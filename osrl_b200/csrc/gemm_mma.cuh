@@ -233,13 +233,7 @@ k_gemm_mma(const GemmTask* __restrict__ tasks, int ntasks) {
   float* As = smem;
   float* Bs = smem + NSTAGE * Cfg::A_STAGE;
   __shared__ GemmTask ts;
-  if (threadIdx.x == 0) {
-    int ti = 0;
-    const int tile = blockIdx.x;
-    while (ti + 1 < ntasks && tasks[ti + 1].tile0 <= tile) ++ti;
-    ts = tasks[ti];
-  }
-  __syncthreads();
+  load_task(&ts, tasks, ntasks, blockIdx.x);
   const GemmTask& t = ts;
   int lt = blockIdx.x - t.tile0, kbeg = 0;
   if constexpr (FULL) { kbeg = (lt / t.tiles_mn) * t.klen; lt %= t.tiles_mn; }

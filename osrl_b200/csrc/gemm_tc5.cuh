@@ -113,11 +113,20 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gemm_tc5(const GemmTask* __re
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1 KB alignment
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) {
+  if (warp == 1) {   // task lookup + descriptor copy by a whole warp (see load_task); published by the barrier below
     int ti = 0;
-    const int tile = blockIdx.x;
-    while (ti + 1 < ntasks && tasks[ti + 1].tile0 <= tile) ++ti;
-    ts = tasks[ti];
+    for (int base = 0; base < ntasks; base += 32) {
+      const int i = base + lane;
+      const bool le = i < ntasks && tasks[i].tile0 <= (int)blockIdx.x;
+      const unsigned m = __ballot_sync(0xffffffffu, le);
+      if (m) ti = base + 31 - __clz(m);
+      if (m != 0xffffffffu) break;
+    }
+    const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(tasks + ti);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&ts);
+    for (int w = lane; w < (int)(sizeof(GemmTask) / 4); w += 32) dst[w] = src[w];
+  }
+  if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], PRODUCERS / 32); mbar_init(&empty_bar[s], 1); }
     mbar_init(&acc_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

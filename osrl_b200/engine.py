@@ -172,6 +172,20 @@ class Engine:
                                          C.c_void_p(out.data_ptr())))
         return out
 
+    def debug_gemm(self, impl: str, A, B, a_kc: bool = True, b_kc: bool = True, colsum: bool = False):
+        """op(A) @ op(B) in any operand layout of the step (forward 1,1; dgrad 1,0; wgrad 0,0); unit-test hook.
+        A is [M,K] (a_kc) or [K,M]; B is [N,K] (b_kc) or [K,N].  Returns C [M,N] (and sum_k A(i,k) if colsum)."""
+        A = A.detach().float().cpu().contiguous(); B = B.detach().float().cpu().contiguous()
+        M, K = (A.shape if a_kc else A.shape[::-1])
+        N = B.shape[0] if b_kc else B.shape[1]
+        assert (B.shape[1] if b_kc else B.shape[0]) == K
+        out = torch.empty(M, N)
+        cs = torch.empty(M) if colsum else None
+        check(self.lib.osrl_debug_gemm(self.h, impl.encode(), M, N, K, C.c_void_p(A.data_ptr()), int(a_kc),
+                                       C.c_void_p(B.data_ptr()), int(b_kc), C.c_void_p(out.data_ptr()),
+                                       C.c_void_p(cs.data_ptr()) if colsum else None))
+        return (out, cs) if colsum else out
+
     def read_section(self, section: str) -> "OrderedDict[str, torch.Tensor]":
         """Trained-parameter-shaped tensors of another arena section: 'grad', 'adam_m', 'adam_v'."""
         sec = {"param": 0, "target": 1, "grad": 2, "adam_m": 3, "adam_v": 4}[section]

@@ -32,3 +32,46 @@ def test_linear_matches_torch(lib_built, impl):
             print(f"{impl} {M}x{N}x{K} act {act}: err {err:.2e} torch-fp32 {err32:.2e}")
             assert err <= max(tol, 4 * err32), f"{impl} {M}x{N}x{K} act {act}: err {err:.2e} (torch fp32 {err32:.2e})"
     eng.close()
+
+
+# (M, N, K, a_kc, b_kc): the thin shapes of an OSRL MLP (gemm_thin.cuh) next to tiled ones in every operand layout
+LAYOUT_SHAPES = [
+    (2560, 2048, 12, 1, 1),   # stacked first layer of 8 Q networks on 2560 rows (thin K)
+    (256, 400, 10, 1, 1),
+    (2560, 400, 2, 1, 0),     # last-layer dgrad: dH = dY[M,2] W[2,400] (thin K, B n-contiguous)
+    (2560, 1, 256, 1, 1),     # Q head (thin N)
+    (256, 8, 400, 1, 1),      # VAE mean/log-std heads
+    (300, 12, 256, 1, 0),     # first-layer dgrad wrt the action input (thin N, B n-contiguous)
+    (400, 10, 256, 0, 0),     # first-layer weight gradient: dW[H,in] = dH^T X (batch reduction, wide M)
+    (2, 400, 2560, 0, 0),     # last-layer weight gradient: dW[out,H] = dY^T H (batch reduction, wide N)
+    (16, 750, 300, 0, 0),
+    (333, 16, 1000, 0, 0),
+    (256, 256, 256, 1, 0),    # tiled dgrad / wgrad for comparison
+    (400, 400, 256, 0, 0),
+]
+
+
+@pytest.mark.parametrize("impl", ["ffma", "mma", "tc5"])
+def test_gemm_layouts_match_torch(lib_built, impl):
+    from osrl_b200 import Engine
+    eng = Engine("bc", batch_size=8, device=0, state_dim=4, action_dim=2, a_hidden_sizes=[8, 8])
+    g = torch.Generator().manual_seed(1)
+    for (M, N, K, a_kc, b_kc) in LAYOUT_SHAPES:
+        A = torch.randn(M, K, generator=g)
+        B = torch.randn(N, K, generator=g)
+        want = A.double() @ B.double().T
+        wcs = A.double().sum(1)
+        Ain = A if a_kc else A.T.contiguous()
+        Bin = B if b_kc else B.T.contiguous()
+        use_cs = not a_kc and not b_kc
+        got = eng.debug_gemm(impl, Ain, Bin, bool(a_kc), bool(b_kc), colsum=use_cs)
+        if use_cs:
+            got, cs = got
+            errc = float((cs.double() - wcs).abs().max()) / float(A.abs().sum(1).max())
+            assert errc <= 2e-6, f"{impl} {M}x{N}x{K} colsum err {errc:.2e}"
+        err = float((got.double() - want).abs().max()) / float(want.abs().max())
+        err32 = float(((A @ B.T).double() - want).abs().max()) / float(want.abs().max())
+        print(f"{impl} {M}x{N}x{K} a_kc={a_kc} b_kc={b_kc}: err {err:.2e} torch-fp32 {err32:.2e}")
+        tol = 2e-6 * max(1.0, K / 1024) if impl == "ffma" else 2e-6   # ffma: one serial fp32 chain over K
+        assert err <= max(tol, 4 * err32), f"{impl} {M}x{N}x{K} ({a_kc},{b_kc}): err {err:.2e} (torch fp32 {err32:.2e})"
+    eng.close()
