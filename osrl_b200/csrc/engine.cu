@@ -68,14 +68,18 @@ GemmTask task_wgrad(const float* dY, int lddy, const float* X, int ldx, int rows
 #define OSRL_GEMM_CFG1 64, 64, 32, 4, 4, 4
 #define OSRL_GEMM_CFG2 32, 32, 32, 2, 2, 6
 // tensor-core (3xTF32 mma.sync) tile shapes: {BM, BN, BK, WARPS_M, WARPS_N, NSTAGE}
-#define OSRL_MMA_CFG0 128, 64, 16, 4, 2, 4
-#define OSRL_MMA_CFG1 64, 64, 32, 2, 4, 4
-#define OSRL_MMA_CFG2 32, 32, 32, 2, 2, 6
+#define OSRL_MMA_CFG0 128, 64, 16, 4, 2, 4, 1
+#define OSRL_MMA_CFG1 64, 64, 32, 2, 4, 4, 1
+#define OSRL_MMA_CFG2 32, 32, 32, 2, 2, 6, 1
+// k-group variants (gemm_mma.cuh) for the short-K, less-than-a-wave launches, where the per-tile critical path
+// is the kernel time; long K (split-K weight gradients) and multi-wave launches stay on the plain tiles
+#define OSRL_MMA_CFG1K 64, 64, 32, 2, 4, 4, 2
+#define OSRL_MMA_CFG2K 32, 32, 32, 2, 2, 6, 4
 // Every kernel exists in two variants: the basic one (the MLP algorithms: bias/ReLU/Tanh/residual/clamp
 // epilogues) and FULL (adds exact GELU + split-K accumulation, used by the launches of the CDT program that
 // need them).  Keeping the extras out of the basic variant is worth ~20 % on the BCQ-Lag step.
 template <int BM, int BN, int BK, int TM, int TN, int NS, bool FULL>
-static void launch_gemm(const GemmTask* d, int ntasks, int tiles, cudaStream_t s) {
+static void launch_gemm(const TaskPack& d, int ntasks, int tiles, cudaStream_t s) {
   using Cfg = GemmCfg<BM, BN, BK, TM, TN, NS>;
   k_gemm_tasks<BM, BN, BK, TM, TN, NS, FULL><<<tiles, Cfg::NT, Cfg::SMEM_BYTES, s>>>(d, ntasks);
 }
@@ -87,18 +91,18 @@ static void prepare_gemm() {
   OSRL_CUDA(cudaFuncSetAttribute(k_gemm_tasks<BM, BN, BK, TM, TN, NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  Cfg::SMEM_BYTES));
 }
-template <int BM, int BN, int BK, int WM, int WN, int NS, bool FULL>
-static void launch_mma(const GemmTask* d, int ntasks, int tiles, cudaStream_t s) {
-  using Cfg = MmaCfg<BM, BN, BK, WM, WN, NS>;
-  k_gemm_mma<BM, BN, BK, WM, WN, NS, FULL><<<tiles, Cfg::NT, Cfg::SMEM_BYTES, s>>>(d, ntasks);
+template <int BM, int BN, int BK, int WM, int WN, int NS, int KG, bool FULL>
+static void launch_mma(const TaskPack& d, int ntasks, int tiles, cudaStream_t s) {
+  using Cfg = MmaCfg<BM, BN, BK, WM, WN, NS, KG>;
+  k_gemm_mma<BM, BN, BK, WM, WN, NS, KG, FULL><<<tiles, Cfg::NT, Cfg::SMEM_BYTES, s>>>(d, ntasks);
 }
-template <int BM, int BN, int BK, int WM, int WN, int NS>
+template <int BM, int BN, int BK, int WM, int WN, int NS, int KG>
 static void prepare_mma() {
-  using Cfg = MmaCfg<BM, BN, BK, WM, WN, NS>;
-  OSRL_CUDA(cudaFuncSetAttribute(k_gemm_mma<BM, BN, BK, WM, WN, NS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 Cfg::SMEM_BYTES));
-  OSRL_CUDA(cudaFuncSetAttribute(k_gemm_mma<BM, BN, BK, WM, WN, NS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 Cfg::SMEM_BYTES));
+  using Cfg = MmaCfg<BM, BN, BK, WM, WN, NS, KG>;
+  OSRL_CUDA(cudaFuncSetAttribute(k_gemm_mma<BM, BN, BK, WM, WN, NS, KG, false>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  OSRL_CUDA(cudaFuncSetAttribute(k_gemm_mma<BM, BN, BK, WM, WN, NS, KG, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
 }
 // OSRL_GEMM (read when an engine's program is built): "ffma" = CUDA-core kernel (gemm.cuh); "mma" = 3xTF32
 // mma.sync kernel for everything; default = mma.sync + the tcgen05/TMEM kernel (gemm_tc5.cuh) for the large
@@ -108,6 +112,21 @@ static std::string gemm_mode() {
   return e ? std::string(e) : std::string("tc5");
 }
 static bool use_mma() { return gemm_mode() != "ffma"; }
+static TaskPack make_pack(const std::vector<GemmTask>& tasks) {
+  OSRL_REQUIRE(tasks.size() <= (size_t)PACK_MAX, "task pack overflow");
+  TaskPack p;
+  memset(&p, 0, sizeof(p));
+  for (size_t i = 0; i < tasks.size(); ++i) p.t[i] = tasks[i];
+  return p;
+}
+// task lists longer than one parameter pack run as several launches
+template <class F>
+static bool split_packs(const std::vector<GemmTask>& tasks, F&& emit_one) {
+  if (tasks.size() <= (size_t)PACK_MAX) return false;
+  for (size_t i = 0; i < tasks.size(); i += PACK_MAX)
+    emit_one(std::vector<GemmTask>(tasks.begin() + i, tasks.begin() + std::min(tasks.size(), i + PACK_MAX)));
+  return true;
+}
 // problems with an extent <= 16 (first / last MLP layers and their gradients) -> gemm_thin.cuh.  OSRL_THIN=0 keeps
 // them on the tiled kernels (A/B timing, tests).
 static int thin_kind(const GemmTask& t) {
@@ -125,17 +144,19 @@ static int thin_kind(const GemmTask& t) {
   return THIN_NONE;
 }
 static void emit_thin(Engine& e, Program& p, std::vector<GemmTask> tasks) {
+  if (split_packs(tasks, [&](std::vector<GemmTask> part) { emit_thin(e, p, part); })) return;
   int tot = 0;
   double bytes = 0.0, flops = 0.0;
   for (auto& t : tasks) {
     int tn = 1;
+    t.klen = 16;   // THIN_N: rows per CTA (two per warp)
     const int n = thin_tiles(t, t.thin, &tn);
     t.tile0 = tot; t.tiles_n = tn; t.tiles_mn = n; t.ksplit = 1;
     tot += n;
     bytes += 4.0 * ((double)t.M * t.K + (double)t.K * t.N + (double)t.M * t.N);
     flops += 2.0 * (double)t.M * t.N * t.K;
   }
-  GemmTask* d = e.upload(tasks);
+  const TaskPack d = make_pack(tasks);
   const int nt = (int)tasks.size(), tiles = tot;
   Engine* ep = &e;
   p.add("k_gemm_thin", bytes, flops, true, [=](cudaStream_t s) {
@@ -147,6 +168,7 @@ static bool tc5_eligible(const GemmTask& t) {
   return t.a_kc && t.b_kc && t.a_vec && t.b_vec && t.ksplit <= 1 && t.M >= 512 && t.K >= 64 && t.N >= 64;
 }
 static void emit_tc5(Engine& e, Program& p, std::vector<GemmTask> tasks) {
+  if (split_packs(tasks, [&](std::vector<GemmTask> part) { emit_tc5(e, p, part); })) return;
   int tot = 0;
   double bytes = 0.0, flops = 0.0;
   bool full = false;
@@ -160,7 +182,7 @@ static void emit_tc5(Engine& e, Program& p, std::vector<GemmTask> tasks) {
     flops += 2.0 * (double)t.M * t.N * t.K;
     full = full || t.act == ACT_GELU || t.dact == ACT_GELU;
   }
-  GemmTask* d = e.upload(tasks);
+  const TaskPack d = make_pack(tasks);
   const int nt = (int)tasks.size(), tiles = tot;
   Engine* ep = &e;
   p.add(BNsel == 128 ? "k_gemm_tc5<128,128,32>" : "k_gemm_tc5<128,64,32>", bytes, flops, true, [=](cudaStream_t s) {
@@ -183,6 +205,8 @@ void prepare_kernels() {
   prepare_mma<OSRL_MMA_CFG0>();
   prepare_mma<OSRL_MMA_CFG1>();
   prepare_mma<OSRL_MMA_CFG2>();
+  prepare_mma<OSRL_MMA_CFG1K>();
+  prepare_mma<OSRL_MMA_CFG2K>();
   OSRL_CUDA(cudaFuncSetAttribute(tc5::k_gemm_tc5<128, 3, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  tc5::Shape<128, 3>::SMEM_BYTES));
   OSRL_CUDA(cudaFuncSetAttribute(tc5::k_gemm_tc5<128, 3, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -201,6 +225,7 @@ static int count_tiles(std::vector<GemmTask>& ts, int BM, int BN, bool assign) {
   }
   return tot;
 }
+static void emit_tiled(Engine& e, Program& p, std::vector<GemmTask> tasks);
 void emit_gemm(Engine& e, Program& p, const std::vector<GemmTask>& tasks_in) {
   if (tasks_in.empty()) return;
   std::vector<GemmTask> tasks;
@@ -252,13 +277,17 @@ void emit_gemm(Engine& e, Program& p, const std::vector<GemmTask>& tasks_in) {
       tasks = rest;
     }
   }
+  emit_tiled(e, p, tasks);
+}
+static void emit_tiled(Engine& e, Program& p, std::vector<GemmTask> tasks) {
+  if (split_packs(tasks, [&](std::vector<GemmTask> part) { emit_tiled(e, p, part); })) return;
   // largest tile shape that still yields >= ~1 wave-fraction of CTAs (148 SMs)
   int cfg = 2;
   if (count_tiles(tasks, 128, 64, false) >= 120) cfg = 0;
   else if (count_tiles(tasks, 64, 64, false) >= 96) cfg = 1;
   static const int bm[3] = {128, 64, 32}, bn[3] = {64, 64, 32};
   const int tiles = count_tiles(tasks, bm[cfg], bn[cfg], true);
-  GemmTask* d = e.upload(tasks);
+  const TaskPack d = make_pack(tasks);
   const int nt = (int)tasks.size();
   Engine* ep = &e;
   double bytes = 0.0, flops = 0.0;
@@ -271,13 +300,18 @@ void emit_gemm(Engine& e, Program& p, const std::vector<GemmTask>& tasks_in) {
   static const char* mnames[3] = {"k_gemm_mma<128,64,16,4,2,4>", "k_gemm_mma<64,64,32,2,4,4>",
                                   "k_gemm_mma<32,32,32,2,2,6>"};
   const bool mma = use_mma();
+  int kmax = 0;
+  for (auto& t : tasks) kmax = std::max(kmax, t.ksplit > 1 ? t.klen : t.K);
+  const bool kgroups = cfg > 0 && kmax <= 1024 && tiles <= 2 * 148;
   bool full = false;
   for (auto& t : tasks) full = full || t.ksplit > 1 || t.act == ACT_GELU || t.dact == ACT_GELU;
   p.add(mma ? mnames[cfg] : names[cfg], bytes, flops, true, [=](cudaStream_t s) {
 #define OSRL_DISPATCH(FULL_)                                                      \
     if (mma) {                                                                    \
       if (cfg == 0) launch_mma<OSRL_MMA_CFG0, FULL_>(d, nt, tiles, s);            \
+      else if (cfg == 1 && kgroups) launch_mma<OSRL_MMA_CFG1K, FULL_>(d, nt, tiles, s); \
       else if (cfg == 1) launch_mma<OSRL_MMA_CFG1, FULL_>(d, nt, tiles, s);       \
+      else if (kgroups) launch_mma<OSRL_MMA_CFG2K, FULL_>(d, nt, tiles, s);       \
       else launch_mma<OSRL_MMA_CFG2, FULL_>(d, nt, tiles, s);                     \
     } else {                                                                      \
       if (cfg == 0) launch_gemm<OSRL_GEMM_CFG0, FULL_>(d, nt, tiles, s);          \
@@ -1113,6 +1147,21 @@ int osrl_debug_gemm(osrl_engine* h, const char* impl, int M, int N, int K, const
   for (auto& op : prog.ops) op(e.cap_stream);
   OSRL_CUDA(cudaStreamSynchronize(e.cap_stream));
   OSRL_CUDA(cudaGetLastError());
+  if (const char* reps_s = getenv("OSRL_DEBUG_TIME")) {   // kernel tuning aid: mean device time of the launch(es)
+    const int reps = std::max(1, atoi(reps_s));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, e.cap_stream);
+    for (int r = 0; r < reps; ++r)
+      for (auto& op : prog.ops) op(e.cap_stream);
+    cudaEventRecord(e1, e.cap_stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    fprintf(stderr, "[osrl_debug_gemm] %s %dx%dx%d a_kc=%d b_kc=%d: %.2f us/launch (%zu ops, %d back-to-back reps)\n", impl, M,
+            N, K, a_kc, b_kc, ms * 1e3f / reps, prog.ops.size(), reps);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
   OSRL_CUDA(cudaMemcpy(C, dC, (size_t)M * N * sizeof(float), cudaMemcpyDeviceToHost));
   if (colsum) OSRL_CUDA(cudaMemcpy(colsum, dS, (size_t)M * sizeof(float), cudaMemcpyDeviceToHost));
   while (e.allocs.size() > before) { cudaFree(e.allocs.back()); e.allocs.pop_back(); }

@@ -49,26 +49,22 @@ struct GemmTask {
   int thin;               // ThinKind (gemm_thin.cuh): 0 = tiled kernels, else which thin body runs the task
 };
 
-// Which task owns tile `tile`?  tile0 is increasing over the list, so the owner is the last task with tile0 <= tile.
-// Warp 0 tests 32 tasks per step with one ballot and copies the descriptor word-parallel into shared memory (a
-// single thread walking the list costs one dependent L2 round trip per task -- microseconds for the 8-16 task
-// launches of an ensemble layer, more than a thin tile's whole body).  Ends with a CTA barrier.
-__device__ __forceinline__ void load_task(GemmTask* ts, const GemmTask* __restrict__ tasks, int ntasks, int tile) {
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    int ti = 0;
-    for (int base = 0; base < ntasks; base += 32) {
-      const int i = base + lane;
-      const bool le = i < ntasks && tasks[i].tile0 <= tile;
-      const unsigned m = __ballot_sync(0xffffffffu, le);
-      if (m) ti = base + 31 - __clz(m);
-      if (m != 0xffffffffu) break;
-    }
-    const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(tasks + ti);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(ts);
-    for (int w = lane; w < (int)(sizeof(GemmTask) / 4); w += 32) dst[w] = src[w];
-  }
-  __syncthreads();
+// A launch's task list travels as a kernel parameter (constant bank), not through global memory: finding the
+// owner of a tile and reading its fields then costs no L2 round trip and no CTA barrier -- on the thin / small
+// problems of this workload the old lookup (scan tile0 in global memory, copy the descriptor to shared memory)
+// was 1-2 us of a 5-10 us kernel.  Fields are read straight from the parameter (uniform loads the compiler may
+// hoist, since parameter space is read-only).  Longer lists are split over several launches by the host.
+constexpr int PACK_MAX = 16;
+struct TaskPack { GemmTask t[PACK_MAX]; };
+static_assert(sizeof(TaskPack) <= 4000, "task pack must fit the 4 KB kernel parameter space");
+
+// tile0 is increasing over the list: the owner of `tile` is the last task with tile0 <= tile
+__device__ __forceinline__ int find_task(const TaskPack& P, int ntasks, int tile) {
+  int ti = 0;
+#pragma unroll
+  for (int i = 1; i < PACK_MAX; ++i)
+    if (i < ntasks && P.t[i].tile0 <= tile) ti = i;
+  return ti;
 }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -206,18 +202,16 @@ __device__ __forceinline__ void stage_operand(float* __restrict__ s, const float
 
 template <int BM, int BN, int BK, int TM, int TN, int NSTAGE, bool FULL>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
-k_gemm_tasks(const GemmTask* __restrict__ tasks, int ntasks) {
+k_gemm_tasks(const __grid_constant__ TaskPack P, int ntasks) {
   using Cfg = GemmCfg<BM, BN, BK, TM, TN, NSTAGE>;
   constexpr int NT = Cfg::NT;
   constexpr int TXN = BN / TN;  // threads along N
   extern __shared__ __align__(16) float smem[];
   float* As = smem;
   float* Bs = smem + NSTAGE * Cfg::A_STAGE;
-  __shared__ GemmTask ts;
 
   const int tid = threadIdx.x;
-  load_task(&ts, tasks, ntasks, blockIdx.x);
-  const GemmTask& t = ts;
+  const GemmTask& t = P.t[find_task(P, ntasks, blockIdx.x)];
   int lt = blockIdx.x - t.tile0, kbeg = 0;
   if constexpr (FULL) { kbeg = (lt / t.tiles_mn) * t.klen; lt %= t.tiles_mn; }
   const int m0 = (lt / t.tiles_n) * BM;

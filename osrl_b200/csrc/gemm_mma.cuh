@@ -14,10 +14,14 @@
 
 namespace osrl {
 
-template <int BM, int BN, int BK, int WM_, int WN_, int NSTAGE>
+// KG > 1: "k-groups" -- KG copies of the WM x WN warp grid share a tile, group g taking the k8-steps g, g+KG, ...
+// of every slab, and the partial tiles are summed through shared memory in a fixed order at the end.  The small
+// layers of this workload (256 rows) are one 32x32 tile per SM with a 13-slab dependent chain: splitting the
+// chain four ways cuts the kernel's critical path, which is all that matters there.
+template <int BM, int BN, int BK, int WM_, int WN_, int NSTAGE, int KG_ = 1>
 struct MmaCfg {
-  static constexpr int WARPS_M = WM_, WARPS_N = WN_;
-  static constexpr int NT = WARPS_M * WARPS_N * 32;
+  static constexpr int WARPS_M = WM_, WARPS_N = WN_, KG = KG_;
+  static constexpr int NT = WARPS_M * WARPS_N * 32 * KG;
   static constexpr int WTM = BM / WARPS_M, WTN = BN / WARPS_N;  // warp tile
   static constexpr int MT = WTM / 16, NTL = WTN / 8;            // mma tiles per warp
   static constexpr int A_KC = BM * (BK + 4), A_MC = BK * (BM + 8);
@@ -26,6 +30,8 @@ struct MmaCfg {
   static constexpr int B_STAGE = B_KC > B_MC ? B_KC : B_MC;
   static constexpr int SMEM_BYTES = NSTAGE * (A_STAGE + B_STAGE) * (int)sizeof(float);
   static_assert(WTM % 16 == 0 && WTN % 8 == 0 && BK % 8 == 0, "bad mma tiling");
+  static_assert(BK % (8 * KG) == 0, "every k-group needs a k8-step in every slab");
+  static_assert(KG == 1 || (KG * BM * (BN + 1) + KG * BM) * (int)sizeof(float) <= SMEM_BYTES, "reduction scratch");
 };
 
 // stage ROWS x BK elements of one operand (layout fixed at compile time, 16B/4B chosen per task)
@@ -87,7 +93,9 @@ template <class Cfg, int BM, int BN, int BK, int NSTAGE, bool AKC, bool BKC, boo
 __device__ __forceinline__ void gemm_mma_body(const GemmTask& t, float* __restrict__ As, float* __restrict__ Bs,
                                               int m0, int n0, int kbeg) {
   constexpr int NT = Cfg::NT, MT = Cfg::MT, NTL = Cfg::NTL;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int KG = Cfg::KG;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int kgrp = (tid >> 5) / (Cfg::WARPS_M * Cfg::WARPS_N), warp = (tid >> 5) % (Cfg::WARPS_M * Cfg::WARPS_N);
   const int g = lane >> 2, tq = lane & 3;
   const int wm = (warp / Cfg::WARPS_N) * Cfg::WTM;
   const int wn = (warp % Cfg::WARPS_N) * Cfg::WTN;
@@ -142,7 +150,7 @@ __device__ __forceinline__ void gemm_mma_body(const GemmTask& t, float* __restri
 #pragma unroll
         for (int q = 0; q < 4; ++q) part[i][j][q] = 0.f;
 #pragma unroll
-    for (int kk = 0; kk < BK; kk += 8) {
+    for (int kk = 8 * kgrp; kk < BK; kk += 8 * KG) {
       uint32_t ah[MT][4], al[MT][4], bh[NTL][2], bl[NTL][2];
 #pragma unroll
       for (int i = 0; i < MT; ++i) {
@@ -195,6 +203,50 @@ __device__ __forceinline__ void gemm_mma_body(const GemmTask& t, float* __restri
   }
   cp_async_wait<0>();
 
+  if constexpr (KG > 1) {
+    // ---- sum the k-groups' partial tiles through shared memory (the staging ring is idle now), fixed order
+    __syncthreads();
+    float* red = As;                             // [KG][BM][BN+1]
+    float* redcs = As + KG * BM * (BN + 1);      // [KG][BM]
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int j = 0; j < NTL; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r = wm + i * 16 + g + (q >> 1) * 8, c = wn + j * 8 + 2 * tq + (q & 1);
+          red[(kgrp * BM + r) * (BN + 1) + c] = acc[i][j][q];
+        }
+    if (want_colsum) {
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float v = rs[i][h];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          if (tq == 0) redcs[kgrp * BM + wm + i * 16 + g + h * 8] = v;
+        }
+    }
+    __syncthreads();
+    if (t.colsum != nullptr && n0 == 0 && tid < BM && m0 + tid < M) {
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < KG; ++k) v += redcs[k * BM + tid];
+      if (FULL && t.ksplit > 1) atomicAdd(&t.colsum[m0 + tid], v);
+      else t.colsum[m0 + tid] = v;
+    }
+    for (int e = tid; e < BM * BN; e += NT) {    // consecutive threads -> consecutive columns: coalesced epilogue
+      const int r = e / BN, c = e % BN;
+      const int gi = m0 + r, gj = n0 + c;
+      if (gi >= M || gj >= N) continue;
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < KG; ++k) v += red[(k * BM + r) * (BN + 1) + c];
+      epilogue_store<FULL>(t, gi, gj, v);
+    }
+    return;
+  }
   // ---- bias gradient: rows g / g+8 of each m-tile; the 4 lanes of a quad hold different k
   if (want_colsum) {
 #pragma unroll
@@ -225,16 +277,14 @@ __device__ __forceinline__ void gemm_mma_body(const GemmTask& t, float* __restri
       }
 }
 
-template <int BM, int BN, int BK, int WM_, int WN_, int NSTAGE, bool FULL>
-__global__ void __launch_bounds__(WM_* WN_ * 32)
-k_gemm_mma(const GemmTask* __restrict__ tasks, int ntasks) {
-  using Cfg = MmaCfg<BM, BN, BK, WM_, WN_, NSTAGE>;
+template <int BM, int BN, int BK, int WM_, int WN_, int NSTAGE, int KG, bool FULL>
+__global__ void __launch_bounds__(WM_* WN_ * 32 * KG, (WM_ * WN_ * 32 * KG <= 256 ? 2 : 1))   // <= 128 registers: 2 CTAs/SM
+k_gemm_mma(const __grid_constant__ TaskPack P, int ntasks) {
+  using Cfg = MmaCfg<BM, BN, BK, WM_, WN_, NSTAGE, KG>;
   extern __shared__ __align__(16) float smem[];
   float* As = smem;
   float* Bs = smem + NSTAGE * Cfg::A_STAGE;
-  __shared__ GemmTask ts;
-  load_task(&ts, tasks, ntasks, blockIdx.x);
-  const GemmTask& t = ts;
+  const GemmTask& t = P.t[find_task(P, ntasks, blockIdx.x)];
   int lt = blockIdx.x - t.tile0, kbeg = 0;
   if constexpr (FULL) { kbeg = (lt / t.tiles_mn) * t.klen; lt %= t.tiles_mn; }
   const int m0 = (lt / t.tiles_n) * BM;

@@ -100,32 +100,18 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
 }
 
 template <int BN_, int NSTAGE_, int MINB, bool FULL>
-__global__ void __launch_bounds__(THREADS, MINB) k_gemm_tc5(const GemmTask* __restrict__ tasks, int ntasks) {
+__global__ void __launch_bounds__(THREADS, MINB) k_gemm_tc5(const __grid_constant__ TaskPack P, int ntasks) {
   using S = Shape<BN_, NSTAGE_>;
   constexpr int BN = S::BN, NSTAGE = S::NSTAGE, STAGE_BYTES = S::STAGE_BYTES, TMEM_COLS = S::TMEM_COLS;
   constexpr int A_T = A_TILE_BYTES, B_T = S::B_TILE_BYTES;
   constexpr bool PREFETCH = (MINB == 1);
   constexpr int BCH = BN * 8 / PRODUCERS;   // 16-byte chunks of the B tile per producer thread
   extern __shared__ uint8_t smem_raw[];
-  __shared__ GemmTask ts;
   __shared__ __align__(8) uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], acc_bar;
   __shared__ uint32_t tmem_base_s;
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1 KB alignment
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (warp == 1) {   // task lookup + descriptor copy by a whole warp (see load_task); published by the barrier below
-    int ti = 0;
-    for (int base = 0; base < ntasks; base += 32) {
-      const int i = base + lane;
-      const bool le = i < ntasks && tasks[i].tile0 <= (int)blockIdx.x;
-      const unsigned m = __ballot_sync(0xffffffffu, le);
-      if (m) ti = base + 31 - __clz(m);
-      if (m != 0xffffffffu) break;
-    }
-    const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(tasks + ti);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&ts);
-    for (int w = lane; w < (int)(sizeof(GemmTask) / 4); w += 32) dst[w] = src[w];
-  }
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], PRODUCERS / 32); mbar_init(&empty_bar[s], 1); }
     mbar_init(&acc_bar, 1);
@@ -140,7 +126,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gemm_tc5(const GemmTask* __re
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
-  const GemmTask& t = ts;
+  const GemmTask& t = P.t[find_task(P, ntasks, blockIdx.x)];
   const int lt = blockIdx.x - t.tile0;
   const int m0 = (lt / t.tiles_n) * BM, n0 = (lt % t.tiles_n) * BN;
   const int M = t.M, N = t.N, K = t.K;

@@ -22,7 +22,7 @@ namespace osrl {
 enum ThinKind { THIN_NONE = 0, THIN_K = 1, THIN_N = 2, THIN_R_WIDE_M = 3, THIN_R_WIDE_N = 4 };
 constexpr int THIN_THREADS = 256;
 constexpr int THIN_K_ROWS = 16, THIN_K_COLS = THIN_THREADS;   // THIN_K tile
-constexpr int THIN_N_ROWS = 16;                               // THIN_N: one warp per row, two rows per warp
+constexpr int THIN_SMEM_FLOATS = 16 * 17 * 16;                // shared scratch: THIN_R reduction / THIN_N B tile / THIN_K A tile
 constexpr int THIN_R_W = 16, THIN_R_KG = THIN_THREADS / THIN_R_W;   // THIN_R: 16 wide indices x 16 k-groups
 
 // number of CTAs ("tiles") a task needs, by kind; tiles_n is what the kernel divides the local tile index by
@@ -32,7 +32,7 @@ static inline int thin_tiles(const GemmTask& t, int kind, int* tiles_n) {
     return ((t.M + THIN_K_ROWS - 1) / THIN_K_ROWS) * *tiles_n;
   }
   *tiles_n = 1;
-  if (kind == THIN_N) return (t.M + THIN_N_ROWS - 1) / THIN_N_ROWS;
+  if (kind == THIN_N) return (t.M + t.klen - 1) / t.klen;   // klen = rows per CTA (set by the host)
   if (kind == THIN_R_WIDE_M) return (t.M + THIN_R_W - 1) / THIN_R_W;
   return (t.N + THIN_R_W - 1) / THIN_R_W;
 }
@@ -111,6 +111,9 @@ __device__ __forceinline__ void thin_k_body(const GemmTask& t, int lt, float* sm
 }
 
 // ---------------------------------------------------------------- N <= 16, rows of A contiguous
+// One warp per row, lanes stride k; B (N x K, a few KB) is read through L1, where every warp after the first
+// finds it.  (Measured: holding a whole A row in registers, or staging B through shared memory, is slower --
+// the 4-deep unrolled loop below already keeps enough loads in flight and stays under 64 registers.)
 template <int NMAX>
 __device__ __forceinline__ void thin_n_body(const GemmTask& t, int lt) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -118,9 +121,11 @@ __device__ __forceinline__ void thin_n_body(const GemmTask& t, int lt) {
   const bool bkc = t.b_kc != 0;
   const float* __restrict__ A = t.A;
   const float* __restrict__ B = t.B;
+  const int rows_per_tile = t.klen;            // host: 8 (one row per warp), 16 for very long M
+  const int row1 = min(M, (lt + 1) * rows_per_tile);
   const Epi ep = make_epi(t);
   const float bias = (t.bias && lane < N) ? t.bias[lane] : 0.f;   // lane n finishes output column n
-  for (int row = lt * THIN_N_ROWS + warp; row < min(M, (lt + 1) * THIN_N_ROWS); row += THIN_THREADS / 32) {
+  for (int row = lt * rows_per_tile + warp; row < row1; row += THIN_THREADS / 32) {
     const float* __restrict__ a = A + (size_t)row * lda;
     float acc[NMAX];
 #pragma unroll
@@ -173,7 +178,8 @@ __device__ __forceinline__ void thin_r_body(const GemmTask& t, int lt, float* sm
   for (int q = 0; q < (WIDE_M ? 1 : TMAX); ++q) cs[q] = 0.f;
   const bool want_cs = t.colsum != nullptr;
   const Epi ep = make_epi(t);
-#pragma unroll 2
+  constexpr int UNR = TMAX <= 2 ? 8 : (TMAX <= 4 ? 4 : (TMAX <= 8 ? 2 : 1));   // loads in flight per thread
+#pragma unroll UNR
   for (int k = kg; k < K; k += THIN_R_KG) {
     const float xw = ok ? Xw[(size_t)k * ldw + w] : 0.f;
     const float* __restrict__ tp = Xt + (size_t)k * ldt;
@@ -230,11 +236,9 @@ __device__ __forceinline__ void thin_dispatch(const GemmTask& t, int lt, float* 
   else thin_r_body<TMAX, false>(t, lt, smem);
 }
 
-static __global__ void __launch_bounds__(THIN_THREADS, 4) k_gemm_thin(const GemmTask* __restrict__ tasks, int ntasks) {
-  __shared__ float smem[THIN_R_KG * 17 * THIN_R_W];   // 4352 floats: the THIN_R reduction; THIN_K's A tile fits too
-  __shared__ GemmTask ts;
-  load_task(&ts, tasks, ntasks, blockIdx.x);
-  const GemmTask& t = ts;
+static __global__ void __launch_bounds__(THIN_THREADS, 4) k_gemm_thin(const __grid_constant__ TaskPack P, int ntasks) {
+  __shared__ float smem[THIN_SMEM_FLOATS];
+  const GemmTask& t = P.t[find_task(P, ntasks, blockIdx.x)];
   const int lt = blockIdx.x - t.tile0;
   if (t.thin == THIN_K) { thin_k_body(t, lt, smem); return; }
   const int T = t.thin == THIN_R_WIDE_N ? t.M : t.N;

@@ -28,3 +28,6 @@ agg = collections.defaultdict(float)
 for n, m, by, fl in prof: agg[n.split("<")[0]] += m
 tot = sum(agg.values())
 for n, m in sorted(agg.items(), key=lambda x: -x[1])[:8]: print(f"{n:24s} {m*1e3:10.1f} us {100*m/tot:5.1f}%")
+if os.environ.get("OPS"):
+    for i, (n, m, by, fl) in enumerate(prof):
+        print(f"{i:3d} {n:34s} {m*1e3:9.1f} us  {fl/1e9:9.2f} GFLOP  {fl/max(m,1e-9)/1e9:8.1f} TFLOP/s" if fl else f"{i:3d} {n:34s} {m*1e3:9.1f} us")
