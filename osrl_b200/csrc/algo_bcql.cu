@@ -80,9 +80,9 @@ void build_bcql(Engine& e) {
   // target actions on 2R rows: current VAE decode -> actor_old perturbation
   {
     float* th1 = e.ws((size_t)2 * R * V); float* th2 = e.ws((size_t)2 * R * V);
-    emit_vae_decode(e, p, e.P, t_dec_in, 2 * R, th1, th2, t_ain + o, in, 0);
+    emit_vae_decode(e, p, e.P, t_dec_in, 2 * R, th1, th2, t_ain + o, in, 0, true);
     std::vector<float*> ah;
-    GemmTask last = mlp_fwd_hidden(e, p, e.T, act, t_ain, in, 2 * R, ACT_TANH, ah, t_qin + o, in);
+    GemmTask last = mlp_fwd_hidden(e, p, e.T, act, t_ain, in, 2 * R, ACT_TANH, ah, t_qin + o, in, true);
     last.act = ACT_TANH; last.scale = philim;           // net.py:61: phi*act_limit*pi(.)
     last.resid = t_ain + o; last.ldr = in;              // + act
     last.clamp = 1; last.lo = -lim; last.hi = lim;      // net.py:62
@@ -92,8 +92,8 @@ void build_bcql(Engine& e) {
   EnsBuf oq = ens_alloc(e, cr, B), oqc = ens_alloc(e, cc, B);        // online nets on (s, a)
   {
     std::vector<Stage> st(nh + 1);
-    ens_fwd(st, cr, e.T, t_qin, in, R, tq);
-    ens_fwd(st, cc, e.T, t_qin + (size_t)R * in, in, R, tqc);
+    ens_fwd(st, cr, e.T, t_qin, in, R, tq, true);
+    ens_fwd(st, cc, e.T, t_qin + (size_t)R * in, in, R, tqc, true);
     ens_fwd(st, cr, e.P, sa, in, B, oq);
     ens_fwd(st, cc, e.P, sa, in, B, oqc);
     emit_stages(e, p, st);

@@ -79,10 +79,10 @@ void build_cpq(Engine& e) {
   float* ood_h1 = e.ws((size_t)SB * V); float* ood_h2 = e.ws((size_t)SB * V); float* ood_ml = e.ws((size_t)SB * 2 * L);
   {
     std::vector<Stage> st(std::max(nh + 1, 3));
-    ens_fwd(st, cr, e.T, qin1, in, B, tq);
-    ens_fwd(st, cc, e.T, qin1, in, B, tqc1);
-    ens_fwd(st, cc, e.T, qin2, in, B, tqc2);
-    ens_fwd(st, cc, e.T, qin_ood, in, SB, tood);
+    ens_fwd(st, cr, e.T, qin1, in, B, tq, true);
+    ens_fwd(st, cc, e.T, qin1, in, B, tqc1, true);
+    ens_fwd(st, cc, e.T, qin2, in, B, tqc2, true);
+    ens_fwd(st, cc, e.T, qin_ood, in, SB, tood, true);
     ens_fwd(st, cr, e.P, sa, in, B, oq);
     ens_fwd(st, cc, e.P, sa, in, B, oqc);
     // VAE encoder on the OOD samples (cpq.py:178; decoder output is discarded there)
@@ -210,8 +210,8 @@ void build_bearl(Engine& e) {
   EnsBuf oq = ens_alloc(e, cr, B), oqc = ens_alloc(e, cc, B);
   {
     std::vector<Stage> st(nh + 1);
-    ens_fwd(st, cr, e.T, t_qin, in, R, tq);
-    ens_fwd(st, cc, e.T, t_qin + (size_t)R * in, in, R, tqc);
+    ens_fwd(st, cr, e.T, t_qin, in, R, tq, true);
+    ens_fwd(st, cc, e.T, t_qin + (size_t)R * in, in, R, tqc, true);
     ens_fwd(st, cr, e.P, sa, in, B, oq);
     ens_fwd(st, cc, e.P, sa, in, B, oqc);
     emit_stages(e, p, st);

@@ -9,10 +9,12 @@ static void flush(Engine& e, Program& p, std::vector<GemmTask> tasks) { emit_gem
 // VAE.decode trunk (net.py:337-339): dec_in [rows, o+L] -> relu d1 -> relu d2 -> d3.
 // mode 0: out = act_lim * tanh(d3)    mode 1: out = raw d3 (BEAR decode_multiple, net.py:353)
 void emit_vae_decode(Engine& e, Program& p, const float* W, const float* dec_in, int rows, float* h1, float* h2,
-                     float* out, int ldout, int mode) {
+                     float* out, int ldout, int mode, bool nograd) {
   const VaeLay& v = e.plan.vae;
   const int V = v.d1.out, ldin = v.d1.in;
-  flush(e, p, {task_fwd(dec_in, ldin, rows, W, v.d1, h1, V, ACT_RELU)});
+  GemmTask first = task_fwd(dec_in, ldin, rows, W, v.d1, h1, V, ACT_RELU);
+  if (nograd) { first.pk_gcols = V; first.c_dead = 1; }
+  flush(e, p, {first});
   flush(e, p, {task_fwd(h1, V, rows, W, v.d2, h2, V, ACT_RELU)});
   if (mode == 0) flush(e, p, {task_fwd(h2, V, rows, W, v.d3, out, ldout, ACT_TANH, e.plan.cfg.max_action)});
   else flush(e, p, {task_fwd(h2, V, rows, W, v.d3, out, ldout, ACT_NONE)});
@@ -64,14 +66,16 @@ void emit_vae_update(Engine& e, Program& p, const float* sa, float* dec_in, cons
 // returned un-emitted so the caller can attach its epilogue (tanh/scale/resid/clamp/aux) and merge it
 // into a launch.  h[j] = output of layer j (j < n-1).
 GemmTask mlp_fwd_hidden(Engine& e, Program& p, const float* W, const MlpLay& m, const float* X, int ldx, int rows,
-                        int hact, std::vector<float*>& h, float* out, int ldout) {
+                        int hact, std::vector<float*>& h, float* out, int ldout, bool nograd) {
   const int n = (int)m.L.size();
   const float* cur = X;
   int ld = ldx;
   h.clear();
   for (int j = 0; j + 1 < n; ++j) {
     float* y = e.ws((size_t)rows * m.L[j].out);
-    emit_gemm(e, p, {task_fwd(cur, ld, rows, W, m.L[j], y, m.L[j].out, hact)});
+    GemmTask lay = task_fwd(cur, ld, rows, W, m.L[j], y, m.L[j].out, hact);
+    if (nograd && j == 0 && n > 2) { lay.pk_gcols = m.L[j].out; lay.c_dead = 1; }
+    emit_gemm(e, p, {lay});
     h.push_back(y);
     cur = y;
     ld = m.L[j].out;

@@ -143,11 +143,31 @@ static int thin_kind(const GemmTask& t) {
   if (t.N <= 16 && t.a_kc && !t.colsum) return THIN_N;
   return THIN_NONE;
 }
+// does `t` qualify as a packed-image producer (GemmTask::pk_*)?  Large-row thin-K forward layer whose column groups
+// are whole consumers.  OSRL_PACK=0 disables the path (A/B timing, tests).
+static bool pack_producer_ok(const GemmTask& t) {
+  const char* v = getenv("OSRL_PACK");   // read at program build, like OSRL_GEMM
+  const bool on = !(v && v[0] == '0');
+  return on && gemm_mode() == "tc5" && t.thin == THIN_K && t.pk_gcols >= 64 && t.pk_gcols % 4 == 0 && t.M >= 512 &&
+         t.N % t.pk_gcols == 0 && t.C != nullptr;
+}
 static void emit_thin(Engine& e, Program& p, std::vector<GemmTask> tasks) {
   if (split_packs(tasks, [&](std::vector<GemmTask> part) { emit_thin(e, p, part); })) return;
   int tot = 0;
   double bytes = 0.0, flops = 0.0;
   for (auto& t : tasks) {
+    if (t.pk_gcols > 0 && pack_producer_ok(t)) {
+      const int groups = t.N / t.pk_gcols, ks = (t.pk_gcols + 31) / 32, rbs = 2 * ((t.M + 127) / 128);
+      const size_t per_group = (size_t)rbs * ks * 2048;
+      OSRL_REQUIRE(per_group < ((size_t)1 << 31), "packed image too large");
+      t.pk_ks = ks;
+      t.pk_gstride = (int)per_group;
+      t.pk_hi = e.ws(per_group * groups);   // zero-initialised: the row / k padding is never written
+      t.pk_lo = e.ws(per_group * groups);
+      e.pack_regs.push_back({t.C, t.ldc, t.M, t.N, t.pk_gcols, t.pk_gstride, ks, t.c_dead, t.pk_hi, t.pk_lo});
+    } else {
+      t.pk_gcols = 0; t.pk_hi = t.pk_lo = nullptr; t.c_dead = 0;
+    }
     int tn = 1;
     t.klen = 16;   // THIN_N: rows per CTA (two per warp)
     const int n = thin_tiles(t, t.thin, &tn);
@@ -167,13 +187,13 @@ static void emit_thin(Engine& e, Program& p, std::vector<GemmTask> tasks) {
 static bool tc5_eligible(const GemmTask& t) {
   return t.a_kc && t.b_kc && t.a_vec && t.b_vec && t.ksplit <= 1 && t.M >= 512 && t.K >= 64 && t.N >= 64;
 }
-static void emit_tc5(Engine& e, Program& p, std::vector<GemmTask> tasks) {
-  if (split_packs(tasks, [&](std::vector<GemmTask> part) { emit_tc5(e, p, part); })) return;
+static void emit_tc5(Engine& e, Program& p, std::vector<GemmTask> tasks, bool apack) {
+  if (split_packs(tasks, [&](std::vector<GemmTask> part) { emit_tc5(e, p, part, apack); })) return;
   int tot = 0;
   double bytes = 0.0, flops = 0.0;
   bool full = false;
   const char* env = getenv("OSRL_TC5_BN");
-  const int BNsel = (env && std::string(env) == "128") ? 128 : 64;
+  const int BNsel = (env && std::string(env) == "128" && !apack) ? 128 : 64;
   for (auto& t : tasks) {
     const int tm = (t.M + tc5::BM - 1) / tc5::BM, tn = (t.N + BNsel - 1) / BNsel;
     t.tile0 = tot; t.tiles_n = tn; t.tiles_mn = tm * tn;
@@ -185,10 +205,14 @@ static void emit_tc5(Engine& e, Program& p, std::vector<GemmTask> tasks) {
   const TaskPack d = make_pack(tasks);
   const int nt = (int)tasks.size(), tiles = tot;
   Engine* ep = &e;
-  p.add(BNsel == 128 ? "k_gemm_tc5<128,128,32>" : "k_gemm_tc5<128,64,32>", bytes, flops, true, [=](cudaStream_t s) {
+  p.add(apack ? "k_gemm_tc5<128,64,32,apack>" : (BNsel == 128 ? "k_gemm_tc5<128,128,32>" : "k_gemm_tc5<128,64,32>"), bytes,
+        flops, true, [=](cudaStream_t s) {
     using S128 = tc5::Shape<128, 3>;
     using S64 = tc5::Shape<64, 2>;
-    if (BNsel == 128) {
+    if (apack) {
+      if (full) tc5::k_gemm_tc5<64, 2, 2, true, true><<<tiles, tc5::THREADS, S64::SMEM_BYTES, s>>>(d, nt);
+      else tc5::k_gemm_tc5<64, 2, 2, false, true><<<tiles, tc5::THREADS, S64::SMEM_BYTES, s>>>(d, nt);
+    } else if (BNsel == 128) {
       if (full) tc5::k_gemm_tc5<128, 3, 1, true><<<tiles, tc5::THREADS, S128::SMEM_BYTES, s>>>(d, nt);
       else tc5::k_gemm_tc5<128, 3, 1, false><<<tiles, tc5::THREADS, S128::SMEM_BYTES, s>>>(d, nt);
     } else {
@@ -214,6 +238,10 @@ void prepare_kernels() {
   OSRL_CUDA(cudaFuncSetAttribute(tc5::k_gemm_tc5<64, 2, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  tc5::Shape<64, 2>::SMEM_BYTES));
   OSRL_CUDA(cudaFuncSetAttribute(tc5::k_gemm_tc5<64, 2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 tc5::Shape<64, 2>::SMEM_BYTES));
+  OSRL_CUDA(cudaFuncSetAttribute(tc5::k_gemm_tc5<64, 2, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 tc5::Shape<64, 2>::SMEM_BYTES));
+  OSRL_CUDA(cudaFuncSetAttribute(tc5::k_gemm_tc5<64, 2, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  tc5::Shape<64, 2>::SMEM_BYTES));
 }
 static int count_tiles(std::vector<GemmTask>& ts, int BM, int BN, bool assign) {
@@ -269,13 +297,28 @@ void emit_gemm(Engine& e, Program& p, const std::vector<GemmTask>& tasks_in) {
       });
     }
   if (gemm_mode() == "tc5") {   // large forward layers -> tcgen05 kernel, the rest stays on mma.sync
-    std::vector<GemmTask> big, rest;
-    for (auto& t : tasks) (tc5_eligible(t) ? big : rest).push_back(t);
-    if (!big.empty()) {
-      emit_tc5(e, p, big);
-      if (rest.empty()) return;
-      tasks = rest;
+    std::vector<GemmTask> big, packed, rest;
+    for (auto& t : tasks) {
+      const Engine::PackReg* reg = nullptr;   // were these activations announced as packed hi/lo images?
+      for (auto& r : e.pack_regs) {
+        const ptrdiff_t off = t.A - r.C;
+        if (t.a_kc && off >= 0 && off < r.N && t.lda == r.ldc && t.M == r.M) reg = &r;
+      }
+      if (reg && tc5_eligible(t) && t.K == reg->gcols && (t.A - reg->C) % reg->gcols == 0) {
+        const int grp = (int)((t.A - reg->C) / reg->gcols);
+        t.a_hi = reg->hi + (size_t)grp * reg->gstride;
+        t.a_lo = reg->lo + (size_t)grp * reg->gstride;
+        t.pk_ks = reg->ks;
+        packed.push_back(t);
+        continue;
+      }
+      OSRL_REQUIRE(!(reg && reg->dead), "a GEMM reads activations that only exist as packed images");
+      (tc5_eligible(t) ? big : rest).push_back(t);
     }
+    if (!packed.empty()) emit_tc5(e, p, packed, true);
+    if (!big.empty()) emit_tc5(e, p, big, false);
+    if (rest.empty()) return;
+    tasks = rest;
   }
   emit_tiled(e, p, tasks);
 }
@@ -411,10 +454,13 @@ EnsBuf ens_alloc(Engine& e, const EnsLay& l, int rows) {
   b.q = e.ws((size_t)rows * l.n);
   return b;
 }
-void ens_fwd(std::vector<Stage>& st, const EnsLay& l, const float* W, const float* X, int ldx, int rows, EnsBuf& buf) {
+void ens_fwd(std::vector<Stage>& st, const EnsLay& l, const float* W, const float* X, int ldx, int rows, EnsBuf& buf,
+             bool nograd) {
   const int nh = (int)l.h.size();
   OSRL_REQUIRE((int)st.size() >= nh + 1, "ens_fwd: not enough stages");
-  st[0].tasks.push_back(task_fwd(X, ldx, rows, W, l.first, buf.h[0], l.n * l.h[0], ACT_RELU));
+  GemmTask first = task_fwd(X, ldx, rows, W, l.first, buf.h[0], l.n * l.h[0], ACT_RELU);
+  if (nograd && nh > 1) { first.pk_gcols = l.h[0]; first.c_dead = 1; }
+  st[0].tasks.push_back(first);
   for (int k = 1; k < nh; ++k)
     for (int i = 0; i < l.n; ++i)
       st[k].tasks.push_back(task_fwd(buf.h[k - 1] + (size_t)i * l.h[k - 1], l.n * l.h[k - 1], rows, W, l.mid[k - 1][i],

@@ -158,6 +158,10 @@ struct Engine {
   cudaStream_t cap_stream = nullptr;
   float* stats = nullptr;
   std::vector<void*> allocs;
+  // packed tf32 hi/lo activation images announced by producer GEMM tasks (GemmTask::pk_*), looked up by the
+  // consumer that reads the same activations: see emit_gemm
+  struct PackReg { const float* C; int ldc, M, N, gcols, gstride, ks, dead; float* hi; float* lo; };
+  std::vector<PackReg> pack_regs;
   int64_t launches = 0;
   // data parallel
   void* comm = nullptr;
@@ -200,7 +204,10 @@ struct EnsBuf {
 };
 EnsBuf ens_alloc(Engine& e, const EnsLay& l, int rows);
 // forward: appends to stages[0..nh] (nh+1 stages)
-void ens_fwd(std::vector<Stage>& st, const EnsLay& l, const float* W, const float* X, int ldx, int rows, EnsBuf& buf);
+// nograd: nothing but the next layer reads the first layer's activations (target / sampling passes): on large-row
+// passes they are then produced as packed tf32 images for the tcgen05 kernel instead of fp32 (GemmTask::pk_*)
+void ens_fwd(std::vector<Stage>& st, const EnsLay& l, const float* W, const float* X, int ldx, int rows, EnsBuf& buf,
+             bool nograd = false);
 // backward: stages[0] = last layer ... stages[nh] = first layer.  Gsec == nullptr: input-gradient only.
 // dX (optional) receives d loss / d X[:, xcol0 : xcol0+xcols].
 void ens_bwd(std::vector<Stage>& st, const EnsLay& l, const float* W, float* Gsec, const float* X, int ldx, int rows,
@@ -212,11 +219,11 @@ struct MlpBuf {
 };
 // blocks.cu
 void emit_vae_decode(Engine& e, Program& p, const float* W, const float* dec_in, int rows, float* h1, float* h2,
-                     float* out, int ldout, int mode);
+                     float* out, int ldout, int mode, bool nograd = false);
 void emit_vae_update(Engine& e, Program& p, const float* sa, float* dec_in, const float* eps, const float* act,
                      int stat_index);
 GemmTask mlp_fwd_hidden(Engine& e, Program& p, const float* W, const MlpLay& m, const float* X, int ldx, int rows,
-                        int hact, std::vector<float*>& h, float* out, int ldout);
+                        int hact, std::vector<float*>& h, float* out, int ldout, bool nograd = false);
 void mlp_bwd(Engine& e, Program& p, const float* W, float* Gsec, const MlpLay& m, const float* X, int ldx, int rows,
              int hact, const std::vector<float*>& h, const float* dpre);
 void emit_stages(Engine& e, Program& p, std::vector<Stage>& st);

@@ -47,7 +47,22 @@ struct GemmTask {
   int ksplit;             // >1: split-K -- each split atomically adds its partial into a pre-zeroed C / colsum
   int klen;               // k extent of one split (multiple of every BK)
   int thin;               // ThinKind (gemm_thin.cuh): 0 = tiled kernels, else which thin body runs the task
+  // ---- packed tf32 hi/lo operands (gemm_tc5.cuh, "A-packed" path).  A producer task with pk_hi set also writes
+  // its output, split into hi = tf32(x) and lo = tf32(x - hi), as ready-made SWIZZLE_128B shared-memory images:
+  // blocks of 64 rows x 32 k (8 KB), block (rb, ks) at float offset (rb * pk_ks + ks) * 2048, one image set per
+  // group of pk_gcols output columns (= one consumer network of a stacked ensemble layer).  The consumer GEMM then
+  // fetches its A tiles with cp.async.bulk instead of loading, splitting and storing them in every column tile.
+  float* pk_hi; float* pk_lo;
+  const float* a_hi; const float* a_lo;   // consumer side: packed images of A (null: load + split A from t.A)
+  int pk_gcols;           // producer: columns per group (the consumer's K); 0 = no packed output wanted
+  int pk_gstride;         // floats between the image sets of consecutive groups
+  int pk_ks;              // k-slabs (of 32) per row block = ceil(pk_gcols / 32); consumer: same value
+  int c_dead;             // producer hint: nothing reads C except through the packed images -> skip the fp32 store
 };
+__host__ __device__ __forceinline__ size_t pk_offset(int row, int col, int ks_per_rb) {   // float offset in an image set
+  const int rb = row >> 6, r = row & 63, ks = col >> 5, c = col & 31;
+  return ((size_t)rb * ks_per_rb + ks) * 2048 + (size_t)((r >> 3) * 256 + (r & 7) * 32 + ((((c >> 2) ^ (r & 7))) << 2) + (c & 3));
+}
 
 // A launch's task list travels as a kernel parameter (constant bank), not through global memory: finding the
 // owner of a tile and reading its fields then costs no L2 round trip and no CTA barrier -- on the thin / small
@@ -81,39 +96,50 @@ static __device__ __noinline__ float gelu_bwd(float s) {
   return 0.5f * (1.f + erff(s * 0.70710678118654752f)) + s * 0.3989422804014327f * expf(-0.5f * s * s);
 }
 
-// one output element through the fused epilogue.  FULL adds GELU (aux keeps the PRE-activation, the dgrad mask
-// reads it back) and split-K accumulation.
+// The fused epilogue.  A task's fields live in the kernel's parameter space behind a runtime task index, so
+// reading them per output element costs a dozen indexed constant loads and branches per element -- measured at
+// half of the tcgen05 kernel's samples.  Every thread therefore copies what the epilogue needs into registers
+// once (Epi) and loads the bias of its columns once; the per-element path is then a handful of predicated ops.
+// FULL adds GELU (aux keeps the PRE-activation, the dgrad mask reads it back) and split-K accumulation.
+struct Epi {
+  float* C; float* aux; const float* resid; const float* dsrc; const float* bias;
+  int ldc, ldaux, ldr, ldd, act, clamp, dact, ksplit;
+  float scale, lo, hi;
+};
+__device__ __forceinline__ Epi make_epi(const GemmTask& t) {
+  Epi e;
+  e.C = t.C; e.aux = t.aux; e.resid = t.resid; e.dsrc = t.dact_src; e.bias = t.bias;
+  e.ldc = t.ldc; e.ldaux = t.ldaux; e.ldr = t.ldr; e.ldd = t.ld_dact;
+  e.act = t.act; e.clamp = t.clamp; e.dact = t.dact; e.ksplit = t.ksplit;
+  e.scale = t.scale; e.lo = t.lo; e.hi = t.hi;
+  return e;
+}
+__device__ __forceinline__ float epi_bias(const Epi& e, int gj, int N) { return (e.bias && gj < N) ? e.bias[gj] : 0.f; }
+// final value of one output element (stores aux on the way); `bias` = epi_bias of the element's column
 template <bool FULL>
-__device__ __forceinline__ void epilogue_store(const GemmTask& t, int gi, int gj, float v) {
-  if constexpr (FULL) {
-    if (t.ksplit > 1) { atomicAdd(&t.C[(size_t)gi * t.ldc + gj], v); return; }
-  }
-  if (t.bias) v += t.bias[gj];
-  if constexpr (FULL) {
-    if (t.act == ACT_GELU) {
-      if (t.aux) t.aux[(size_t)gi * t.ldaux + gj] = v;
-      v = gelu_fwd(v);
-    } else {
-      v = apply_act(v, t.act);
-      if (t.aux) t.aux[(size_t)gi * t.ldaux + gj] = v;
-    }
+__device__ __forceinline__ float epi_value(const Epi& e, float bias, int gi, int gj, float v) {
+  v += bias;
+  if (FULL && e.act == ACT_GELU) {
+    if (e.aux) e.aux[(size_t)gi * e.ldaux + gj] = v;
+    v = gelu_fwd(v);
   } else {
-    v = apply_act(v, t.act);
-    if (t.aux) t.aux[(size_t)gi * t.ldaux + gj] = v;
+    v = apply_act(v, e.act);
+    if (e.aux) e.aux[(size_t)gi * e.ldaux + gj] = v;
   }
-  v *= t.scale;
-  if (t.resid) v += t.resid[(size_t)gi * t.ldr + gj];
-  if (t.clamp) v = fminf(fmaxf(v, t.lo), t.hi);
-  if (t.dact) {
-    const float s = t.dact_src[(size_t)gi * t.ld_dact + gj];
-    if constexpr (FULL) {
-      if (t.dact == ACT_GELU) v *= gelu_bwd(s);
-      else v = (t.dact == ACT_RELU) ? (s > 0.f ? v : 0.f) : v * (1.f - s * s);
-    } else {
-      v = (t.dact == ACT_RELU) ? (s > 0.f ? v : 0.f) : v * (1.f - s * s);
-    }
+  v *= e.scale;
+  if (e.resid) v += e.resid[(size_t)gi * e.ldr + gj];
+  if (e.clamp) v = fminf(fmaxf(v, e.lo), e.hi);
+  if (e.dact) {
+    const float s = e.dsrc[(size_t)gi * e.ldd + gj];
+    if (FULL && e.dact == ACT_GELU) v *= gelu_bwd(s);
+    else v = (e.dact == ACT_RELU) ? (s > 0.f ? v : 0.f) : v * (1.f - s * s);
   }
-  t.C[(size_t)gi * t.ldc + gj] = v;
+  return v;
+}
+template <bool FULL>
+__device__ __forceinline__ void epi_store(const Epi& e, float bias, int gi, int gj, float v) {
+  if (FULL && e.ksplit > 1) { atomicAdd(&e.C[(size_t)gi * e.ldc + gj], v); return; }
+  e.C[(size_t)gi * e.ldc + gj] = epi_value<FULL>(e, bias, gi, gj, v);
 }
 
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, bool valid) {
@@ -300,6 +326,10 @@ k_gemm_tasks(const __grid_constant__ TaskPack P, int ntasks) {
   cp_async_wait<0>();
 
   // ---- fused epilogue
+  const Epi ep = make_epi(t);
+  float bj[TN];
+#pragma unroll
+  for (int j = 0; j < TN; ++j) bj[j] = epi_bias(ep, n0 + (bkc ? tx + j * TXN : tx * TN + j), N);
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const int gi = m0 + ty * TM + i;
@@ -312,7 +342,7 @@ k_gemm_tasks(const __grid_constant__ TaskPack P, int ntasks) {
     for (int j = 0; j < TN; ++j) {
       const int gj = n0 + (bkc ? tx + j * TXN : tx * TN + j);
       if (gj >= N) continue;
-      epilogue_store<FULL>(t, gi, gj, acc[i][j]);
+      epi_store<FULL>(ep, bj[j], gi, gj, acc[i][j]);
     }
   }
 }

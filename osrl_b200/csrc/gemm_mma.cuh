@@ -236,14 +236,19 @@ __device__ __forceinline__ void gemm_mma_body(const GemmTask& t, float* __restri
       if (FULL && t.ksplit > 1) atomicAdd(&t.colsum[m0 + tid], v);
       else t.colsum[m0 + tid] = v;
     }
-    for (int e = tid; e < BM * BN; e += NT) {    // consecutive threads -> consecutive columns: coalesced epilogue
-      const int r = e / BN, c = e % BN;
-      const int gi = m0 + r, gj = n0 + c;
-      if (gi >= M || gj >= N) continue;
-      float v = 0.f;
+    const Epi ep = make_epi(t);
+    static_assert(NT % BN == 0, "a thread keeps its column across the reduction loop");
+    const int c = tid % BN, gj = n0 + c;         // consecutive threads -> consecutive columns: coalesced epilogue
+    const float bias = epi_bias(ep, gj, N);
+    if (gj < N) {
+      for (int r = tid / BN; r < BM; r += NT / BN) {
+        const int gi = m0 + r;
+        if (gi >= M) break;
+        float v = 0.f;
 #pragma unroll
-      for (int k = 0; k < KG; ++k) v += red[(k * BM + r) * (BN + 1) + c];
-      epilogue_store<FULL>(t, gi, gj, v);
+        for (int k = 0; k < KG; ++k) v += red[(k * BM + r) * (BN + 1) + c];
+        epi_store<FULL>(ep, bias, gi, gj, v);
+      }
     }
     return;
   }
@@ -264,6 +269,13 @@ __device__ __forceinline__ void gemm_mma_body(const GemmTask& t, float* __restri
       }
   }
   // ---- fused epilogue: c0,c1 -> (row g, cols 2t,2t+1); c2,c3 -> (row g+8, same cols)
+  const Epi ep = make_epi(t);
+  float bj[NTL][2];
+#pragma unroll
+  for (int j = 0; j < NTL; ++j) {
+    bj[j][0] = epi_bias(ep, n0 + wn + j * 8 + 2 * tq, N);
+    bj[j][1] = epi_bias(ep, n0 + wn + j * 8 + 2 * tq + 1, N);
+  }
 #pragma unroll
   for (int i = 0; i < MT; ++i)
 #pragma unroll
@@ -273,7 +285,7 @@ __device__ __forceinline__ void gemm_mma_body(const GemmTask& t, float* __restri
         const int gi = m0 + wm + i * 16 + g + (q >> 1) * 8;
         const int gj = n0 + wn + j * 8 + 2 * tq + (q & 1);
         if (gi >= M || gj >= N) continue;
-        epilogue_store<FULL>(t, gi, gj, acc[i][j][q]);
+        epi_store<FULL>(ep, bj[j][q & 1], gi, gj, acc[i][j][q]);
       }
 }
 

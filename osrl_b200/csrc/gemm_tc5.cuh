@@ -99,7 +99,11 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
   lo.x = rna_tf32(v.x - hi.x); lo.y = rna_tf32(v.y - hi.y); lo.z = rna_tf32(v.z - hi.z); lo.w = rna_tf32(v.w - hi.w);
 }
 
-template <int BN_, int NSTAGE_, int MINB, bool FULL>
+// APACK: the A operand arrives as ready-made hi/lo shared-memory images (GemmTask::a_hi / a_lo, written by the
+// producer of the activations): one thread fetches a stage's four 8 KB blocks with cp.async.bulk (completion
+// counted on the stage's full barrier) and the producer warps only load / split / store the 64-row B tile --
+// a third of the shared-memory stores and ALU work of the generic path, which bounds this kernel.
+template <int BN_, int NSTAGE_, int MINB, bool FULL, bool APACK = false>
 __global__ void __launch_bounds__(THREADS, MINB) k_gemm_tc5(const __grid_constant__ TaskPack P, int ntasks) {
   using S = Shape<BN_, NSTAGE_>;
   constexpr int BN = S::BN, NSTAGE = S::NSTAGE, STAGE_BYTES = S::STAGE_BYTES, TMEM_COLS = S::TMEM_COLS;
@@ -113,7 +117,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gemm_tc5(const __grid_constan
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full_bar[s], PRODUCERS / 32); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(&full_bar[s], PRODUCERS / 32 + (APACK ? 1 : 0));   // + the bulk-copy issuer's expect_tx arrival
+      mbar_init(&empty_bar[s], 1);
+    }
     mbar_init(&acc_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -141,12 +148,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gemm_tc5(const __grid_constan
     // so a k-step costs the shared-store time, not a global round trip
     auto load_slab = [&](int kt, float4 (&va)[4], float4 (&vb)[BCH]) {
       const int k0 = kt * BK;
+      if constexpr (!APACK) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {   // 1024 chunks of the A tile, 4 per thread; 8 lanes = one 128-byte row
-        const int c = tid + PRODUCERS * i, r = c >> 3, ck = c & 7;
-        const int gk = k0 + ck * 4;
-        va[i] = (m0 + r < M && gk < K) ? *reinterpret_cast<const float4*>(A + (size_t)(m0 + r) * lda + gk)
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 4; ++i) {   // 1024 chunks of the A tile, 4 per thread; 8 lanes = one 128-byte row
+          const int c = tid + PRODUCERS * i, r = c >> 3, ck = c & 7;
+          const int gk = k0 + ck * 4;
+          va[i] = (m0 + r < M && gk < K) ? *reinterpret_cast<const float4*>(A + (size_t)(m0 + r) * lda + gk)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
 #pragma unroll
       for (int i = 0; i < BCH; ++i) {
@@ -160,14 +169,37 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gemm_tc5(const __grid_constan
       const int s = kt % NSTAGE;
       if (kt >= NSTAGE) mbar_wait(&empty_bar[s], ((kt / NSTAGE) - 1) & 1);
       uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+      if constexpr (APACK) {
+        if (tid == 0) {   // A_hi | A_lo of this stage = two 64-row blocks each, 8 KB apiece, already swizzled
+          const uint32_t bar = smem_u32(&full_bar[s]);
+          asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar),
+                       "r"(2 * A_T)
+                       : "memory");
+          const int rb = m0 >> 6, ksr = t.pk_ks;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c = tid + PRODUCERS * i, r = c >> 3, ck = c & 7;
-        const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((ck ^ (r & 7)) << 4);
-        float4 hi, lo;
-        split4(va[i], hi, lo);
-        *reinterpret_cast<float4*>(st + off) = hi;
-        *reinterpret_cast<float4*>(st + A_T + off) = lo;
+          for (int h = 0; h < 2; ++h) {
+            const float* src = (h ? t.a_lo : t.a_hi);
+#pragma unroll
+            for (int b2 = 0; b2 < 2; ++b2) {
+              const float* g = src + ((size_t)(rb + b2) * ksr + kt) * 2048;
+              asm volatile(
+                  "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                      smem_u32(st + h * A_T + b2 * 8192)),
+                  "l"(g), "r"(8192), "r"(bar)
+                  : "memory");
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = tid + PRODUCERS * i, r = c >> 3, ck = c & 7;
+          const int off = (r >> 3) * 1024 + (r & 7) * 128 + ((ck ^ (r & 7)) << 4);
+          float4 hi, lo;
+          split4(va[i], hi, lo);
+          *reinterpret_cast<float4*>(st + off) = hi;
+          *reinterpret_cast<float4*>(st + A_T + off) = lo;
+        }
       }
 #pragma unroll
       for (int i = 0; i < BCH; ++i) {
@@ -234,13 +266,17 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gemm_tc5(const __grid_constan
     }
     asm volatile("bar.sync 1, %0;" ::"n"(PRODUCERS) : "memory");   // the 8 epilogue warps only
     // phase 2: fused epilogue + coalesced stores (32 lanes = 32 consecutive columns of one row)
+    const Epi ep = make_epi(t);
+    float bj[BN / 32];
+#pragma unroll
+    for (int j = 0; j < BN / 32; ++j) bj[j] = epi_bias(ep, n0 + j * 32 + lane, N);
     for (int r = warp; r < BM; r += PRODUCERS / 32) {
       const int gi = m0 + r;
       if (gi >= M) break;
 #pragma unroll
       for (int j = 0; j < BN / 32; ++j) {
         const int gj = n0 + j * 32 + lane;
-        if (gj < N) epilogue_store<FULL>(t, gi, gj, tile[r * TP + j * 32 + lane]);
+        if (gj < N) epi_store<FULL>(ep, bj[j], gi, gj, tile[r * TP + j * 32 + lane]);
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -37,33 +37,10 @@ static inline int thin_tiles(const GemmTask& t, int kind, int* tiles_n) {
   return (t.N + THIN_R_W - 1) / THIN_R_W;
 }
 
-// the fused epilogue of gemm.cuh (epilogue_store<false>) with the task fields held in registers: the task
-// descriptor lives in shared memory and every global store may alias it as far as the compiler knows, so the
-// generic version re-reads a dozen fields per element -- more work than a thin problem's whole dot product.
-struct Epi {
-  float* C; float* aux; const float* resid; const float* dsrc;
-  int ldc, ldaux, ldr, ldd, act, clamp, dact;
-  float scale, lo, hi;
-};
-__device__ __forceinline__ Epi make_epi(const GemmTask& t) {
-  Epi e;
-  e.C = t.C; e.aux = t.aux; e.resid = t.resid; e.dsrc = t.dact_src;
-  e.ldc = t.ldc; e.ldaux = t.ldaux; e.ldr = t.ldr; e.ldd = t.ld_dact;
-  e.act = t.act; e.clamp = t.clamp; e.dact = t.dact;
-  e.scale = t.scale; e.lo = t.lo; e.hi = t.hi;
-  return e;
-}
-__device__ __forceinline__ void epi_store(const Epi& e, float bias, int gi, int gj, float v) {
-  v = apply_act(v + bias, e.act);
-  if (e.aux) e.aux[(size_t)gi * e.ldaux + gj] = v;
-  v *= e.scale;
-  if (e.resid) v += e.resid[(size_t)gi * e.ldr + gj];
-  if (e.clamp) v = fminf(fmaxf(v, e.lo), e.hi);
-  if (e.dact) {
-    const float s = e.dsrc[(size_t)gi * e.ldd + gj];
-    v = (e.dact == ACT_RELU) ? (s > 0.f ? v : 0.f) : v * (1.f - s * s);
-  }
-  e.C[(size_t)gi * e.ldc + gj] = v;
+__device__ __forceinline__ float thin_rna_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
 }
 
 __device__ __forceinline__ float ld_a(const GemmTask& t, int i, int k) {
@@ -92,20 +69,39 @@ __device__ __forceinline__ void thin_k_body(const GemmTask& t, int lt, float* sm
   const int rows = min(THIN_K_ROWS, t.M - m0);
   __syncthreads();
   if (j >= t.N) return;
+  if (t.pk_hi) {   // packed tf32 hi/lo images for a tcgen05 consumer (see GemmTask), optionally instead of C
+    const int grp = j / t.pk_gcols, col = j - grp * t.pk_gcols, ksr = t.pk_ks;
+    float* __restrict__ phi = t.pk_hi + (size_t)grp * t.pk_gstride;
+    float* __restrict__ plo = t.pk_lo + (size_t)grp * t.pk_gstride;
+    const bool dead = t.c_dead != 0;
+#pragma unroll 4
+    for (int r = 0; r < rows; ++r) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) acc = fmaf(As[r][k], b[k], acc);
+      const float v = epi_value<false>(ep, bias, m0 + r, j, acc);
+      if (!dead) ep.C[(size_t)(m0 + r) * ep.ldc + j] = v;
+      const size_t off = pk_offset(m0 + r, col, ksr);
+      const float hi = thin_rna_tf32(v);
+      phi[off] = hi;
+      plo[off] = thin_rna_tf32(v - hi);
+    }
+    return;
+  }
   if (rows == THIN_K_ROWS) {
 #pragma unroll 4
     for (int r = 0; r < THIN_K_ROWS; ++r) {
       float acc = 0.f;
 #pragma unroll
       for (int k = 0; k < 16; ++k) acc = fmaf(As[r][k], b[k], acc);
-      epi_store(ep, bias, m0 + r, j, acc);
+      epi_store<false>(ep, bias, m0 + r, j, acc);
     }
   } else {
     for (int r = 0; r < rows; ++r) {
       float acc = 0.f;
 #pragma unroll
       for (int k = 0; k < 16; ++k) acc = fmaf(As[r][k], b[k], acc);
-      epi_store(ep, bias, m0 + r, j, acc);
+      epi_store<false>(ep, bias, m0 + r, j, acc);
     }
   }
 }
@@ -156,7 +152,7 @@ __device__ __forceinline__ void thin_n_body(const GemmTask& t, int lt) {
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if (lane == n) mine = v;
     }
-    if (lane < N) epi_store(ep, bias, row, lane, mine);
+    if (lane < N) epi_store<false>(ep, bias, row, lane, mine);
   }
 }
 
@@ -207,8 +203,8 @@ __device__ __forceinline__ void thin_r_body(const GemmTask& t, int lt, float* sm
     if (!ok) continue;
     if (q < TMAX) {
       if (q < T) {   // (weight gradients: no bias)
-        if (WIDE_M) epi_store(ep, 0.f, w, q, v);
-        else epi_store(ep, 0.f, q, w, v);
+        if (WIDE_M) epi_store<false>(ep, 0.f, w, q, v);
+        else epi_store<false>(ep, 0.f, q, w, v);
       }
     } else if (WIDE_M && want_cs) {
       t.colsum[w] = v;

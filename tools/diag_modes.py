@@ -15,7 +15,10 @@ orc = make_oracle(algo, cfg, meta["init_seed"])
 data = synth.make_dataset(cfg["state_dim"], cfg["action_dim"], 300, 200, seed=0)
 engs = []
 for m in modes:
-    os.environ["OSRL_GEMM"] = m
+    if m.startswith("pack"):          # "pack0" / "pack1": tc5 with the packed-image path off / on
+        os.environ["OSRL_GEMM"] = "tc5"; os.environ["OSRL_PACK"] = m[4:]
+    else:
+        os.environ["OSRL_GEMM"] = m
     e = Engine(algo, batch_size=B, device=0, seed=7, **cfg)
     e.load_params(orc.params)
     e.upload_dataset(data, 0.1, 1.0)
