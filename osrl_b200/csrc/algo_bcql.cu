@@ -29,10 +29,17 @@ void build_bc(Engine& e) {
 }
 
 // ====================================================================== BCQ-Lag
-void build_bcql(Engine& e) {
+// phase 0: the whole step into e.body.  Pipelined graphs (engine.cu) build the step a second time in two halves
+// that can run concurrently: phase 1 = the VAE update alone (into e.pa, reading the NEXT minibatch e.nb_*), phase 2 =
+// everything else (into e.pm, reading the current minibatch and the VAE weights from the snapshot e.Psnap).
+void build_bcql(Engine& e, int phase) {
   const osrl_config& c = e.plan.cfg;
   const Plan& pl = e.plan;
-  Program& p = e.body;
+  Program& p = phase == 1 ? e.pa : (phase == 2 ? e.pm : e.body);
+  const bool do_vae = phase != 2, do_rest = phase != 1;
+  const float* bobs = phase == 1 ? e.nb_obs : e.b_obs;
+  const float* bact = phase == 1 ? e.nb_act : e.b_act;
+  const float* Wvae = phase == 2 ? e.Psnap : e.P;
   const int B = e.B, S = c.sample_action_num, R = B * S, o = c.obs_dim, a = c.act_dim, L = 2 * a, V = c.vae_hidden;
   const int in = o + a, din = o + L;
   const float lim = c.max_action, philim = (float)((double)c.phi * (double)c.max_action);
@@ -54,33 +61,36 @@ void build_bcql(Engine& e) {
   float* p_qin = e.ws((size_t)B * in);
   {
     std::vector<CopyTask> ct;
-    ct.push_back(copy_cols(sa, in, 0, e.b_obs, o, 0, B, o));
-    ct.push_back(copy_cols(sa, in, o, e.b_act, a, 0, B, a));
-    ct.push_back(copy_cols(v_dec_in, din, 0, e.b_obs, o, 0, B, o));
-    ct.push_back(copy_cols(t_dec_in, din, 0, e.b_nobs, o, 0, 2 * R, o, S, B));   // repeat_interleave (bcql.py:138)
-    ct.push_back(copy_cols(t_ain, in, 0, e.b_nobs, o, 0, 2 * R, o, S, B));
-    ct.push_back(copy_cols(t_qin, in, 0, e.b_nobs, o, 0, 2 * R, o, S, B));
-    CopyTask z1 = copy_cols(t_dec_in, din, o, n_zc, L, 0, R, L);                 // z.clamp(-0.5, 0.5) (net.py:334)
-    z1.clamp = 1; z1.lo = -0.5f; z1.hi = 0.5f;
-    CopyTask z2 = copy_cols(t_dec_in + (size_t)R * din, din, o, n_zcc, L, 0, R, L);
-    z2.clamp = 1; z2.lo = -0.5f; z2.hi = 0.5f;
-    CopyTask z3 = copy_cols(p_dec_in, din, o, n_za, L, 0, B, L);
-    z3.clamp = 1; z3.lo = -0.5f; z3.hi = 0.5f;
-    ct.push_back(z1); ct.push_back(z2); ct.push_back(z3);
-    ct.push_back(copy_cols(p_dec_in, din, 0, e.b_obs, o, 0, B, o));
-    ct.push_back(copy_cols(p_ain, in, 0, e.b_obs, o, 0, B, o));
-    ct.push_back(copy_cols(p_qin, in, 0, e.b_obs, o, 0, B, o));
+    ct.push_back(copy_cols(sa, in, 0, bobs, o, 0, B, o));     // (both halves use [obs | act]: VAE loss, online critics)
+    ct.push_back(copy_cols(sa, in, o, bact, a, 0, B, a));
+    if (do_vae) ct.push_back(copy_cols(v_dec_in, din, 0, bobs, o, 0, B, o));
+    if (do_rest) {
+      ct.push_back(copy_cols(t_dec_in, din, 0, e.b_nobs, o, 0, 2 * R, o, S, B));   // repeat_interleave (bcql.py:138)
+      ct.push_back(copy_cols(t_ain, in, 0, e.b_nobs, o, 0, 2 * R, o, S, B));
+      ct.push_back(copy_cols(t_qin, in, 0, e.b_nobs, o, 0, 2 * R, o, S, B));
+      CopyTask z1 = copy_cols(t_dec_in, din, o, n_zc, L, 0, R, L);                 // z.clamp(-0.5, 0.5) (net.py:334)
+      z1.clamp = 1; z1.lo = -0.5f; z1.hi = 0.5f;
+      CopyTask z2 = copy_cols(t_dec_in + (size_t)R * din, din, o, n_zcc, L, 0, R, L);
+      z2.clamp = 1; z2.lo = -0.5f; z2.hi = 0.5f;
+      CopyTask z3 = copy_cols(p_dec_in, din, o, n_za, L, 0, B, L);
+      z3.clamp = 1; z3.lo = -0.5f; z3.hi = 0.5f;
+      ct.push_back(z1); ct.push_back(z2); ct.push_back(z3);
+      ct.push_back(copy_cols(p_dec_in, din, 0, e.b_obs, o, 0, B, o));
+      ct.push_back(copy_cols(p_ain, in, 0, e.b_obs, o, 0, B, o));
+      ct.push_back(copy_cols(p_qin, in, 0, e.b_obs, o, 0, B, o));
+    }
     emit_copy(e, p, ct);
   }
 
   // ---------------- 1. VAE update (bcql.py:122-132)
-  emit_vae_update(e, p, sa, v_dec_in, n_vae, e.b_act, 0);
+  if (do_vae) emit_vae_update(e, p, sa, v_dec_in, n_vae, bact, 0);
+  if (!do_rest) return;
 
   // ---------------- 2+3. critic and cost-critic updates (bcql.py:134-179), merged launch-by-launch
   // target actions on 2R rows: current VAE decode -> actor_old perturbation
   {
     float* th1 = e.ws((size_t)2 * R * V); float* th2 = e.ws((size_t)2 * R * V);
-    emit_vae_decode(e, p, e.P, t_dec_in, 2 * R, th1, th2, t_ain + o, in, 0, true);
+    emit_vae_decode(e, p, Wvae, t_dec_in, 2 * R, th1, th2, t_ain + o, in, 0, true);
     std::vector<float*> ah;
     GemmTask last = mlp_fwd_hidden(e, p, e.T, act, t_ain, in, 2 * R, ACT_TANH, ah, t_qin + o, in, true);
     last.act = ACT_TANH; last.scale = philim;           // net.py:61: phi*act_limit*pi(.)
@@ -132,7 +142,7 @@ void build_bcql(Engine& e) {
   std::vector<float*> pah;
   {
     float* ph1 = e.ws((size_t)B * V); float* ph2 = e.ws((size_t)B * V);
-    emit_vae_decode(e, p, e.P, p_dec_in, B, ph1, ph2, p_ain + o, in, 0);
+    emit_vae_decode(e, p, Wvae, p_dec_in, B, ph1, ph2, p_ain + o, in, 0);
     GemmTask last = mlp_fwd_hidden(e, p, e.P, act, p_ain, in, B, ACT_TANH, pah, p_qin + o, in);
     last.act = ACT_TANH; last.scale = philim;
     last.aux = pt; last.ldaux = a;

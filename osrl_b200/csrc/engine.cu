@@ -507,18 +507,56 @@ void ens_bwd(std::vector<Stage>& st, const EnsLay& l, const float* W, float* Gse
 }
 
 // ------------------------------------------------------------------ engine life cycle
+static void drop_sampled_graphs(Engine& e) {   // they bake the dataset pointers
+  for (cudaGraphExec_t* g : {&e.g_sampled, &e.g_pro, &e.g_mid, &e.g_last})
+    if (*g) { cudaGraphExecDestroy(*g); *g = nullptr; }
+}
 static void free_all(Engine* e) {
   if (e->g_body) cudaGraphExecDestroy(e->g_body);
-  if (e->g_sampled) cudaGraphExecDestroy(e->g_sampled);
+  drop_sampled_graphs(*e);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
+  if (e->side_stream) cudaStreamDestroy(e->side_stream);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   for (void* p : e->allocs) cudaFree(p);
   if (e->comm && nccl::CommDestroy) nccl::CommDestroy(e->comm);
 }
 
+// Second build of the step as two concurrent halves (see Engine::pa / pm).  Only single-GPU for now: the halves'
+// gradient all-reduces would need two communicators to overlap.  OSRL_PIPELINE=0 keeps osrl_steps() sequential.
+static void build_pipelined(Engine& e, const std::vector<int>& vae_slots) {
+  const char* v = getenv("OSRL_PIPELINE");
+  if ((v && v[0] == '0') || e.world > 1) return;
+  const osrl_config& c = e.plan.cfg;
+  const int o = c.obs_dim, a = c.act_dim, B = e.B;
+  e.nb_obs = e.ws((size_t)B * o); e.nb_nobs = e.ws((size_t)B * o); e.nb_act = e.ws((size_t)B * a);
+  e.nb_rew = e.ws(B); e.nb_cost = e.ws(B); e.nb_done = e.ws(B);
+  e.nb_idx = (int64_t*)e.ws((size_t)B * 2);
+  e.Psnap = e.ws((size_t)e.plan.nP);
+  std::vector<NoiseSlot> sv, sr;
+  for (int i = 0; i < (int)e.noise_buf.size(); ++i) {
+    const bool is_vae = std::find(vae_slots.begin(), vae_slots.end(), i) != vae_slots.end();
+    NoiseSlot s{e.noise_buf[i], (long long)e.plan.noise[i].second, i, 1};
+    NoiseSlot off = s;
+    off.enabled = 0;
+    sv.push_back(is_vae ? s : off);
+    sr.push_back(is_vae ? off : s);
+  }
+  e.d_slots_vae = e.upload(sv);
+  e.d_slots_rest = e.upload(sr);
+  OSRL_CUDA(cudaStreamCreateWithFlags(&e.side_stream, cudaStreamNonBlocking));
+  OSRL_CUDA(cudaEventCreateWithFlags(&e.ev_fork, cudaEventDisableTiming));
+  OSRL_CUDA(cudaEventCreateWithFlags(&e.ev_join, cudaEventDisableTiming));
+  switch (c.algo) {
+    case OSRL_ALGO_BCQL: build_bcql(e, 1); build_bcql(e, 2); break;
+    default: return;
+  }
+  e.pipelined = true;
+}
 static void build_program(Engine& e) {
   switch (e.plan.cfg.algo) {
     case OSRL_ALGO_BC: build_bc(e); break;
-    case OSRL_ALGO_BCQL: build_bcql(e); break;
+    case OSRL_ALGO_BCQL: build_bcql(e); build_pipelined(e, {0}); break;
     case OSRL_ALGO_CPQ: build_cpq(e); break;
     case OSRL_ALGO_BEARL: build_bearl(e); break;
     case OSRL_ALGO_CDT: build_cdt(e); break;
@@ -595,12 +633,12 @@ static Engine* create(const osrl_config& cfg, int device) {
 static void run_ops(Engine& e, const Program& p, cudaStream_t s) {
   for (auto& op : p.ops) op(s);
 }
-static void prologue(Engine& e, cudaStream_t s) {
-  k_prologue<<<1, 32, 0, s>>>(e.ds, e.d_groups, (int)e.plan.groups.size());
+static void prologue(Engine& e, cudaStream_t s, unsigned mask = 0xffffffffu) {
+  k_prologue<<<1, 32, 0, s>>>(e.ds, e.d_groups, (int)e.plan.groups.size(), mask);
   e.launches++;
 }
-static void epilogue(Engine& e, cudaStream_t s) {
-  k_epilogue<<<1, 32, 0, s>>>(e.ds);
+static void epilogue(Engine& e, cudaStream_t s, int mode = 0) {
+  k_epilogue<<<1, 32, 0, s>>>(e.ds, mode);
   e.launches++;
 }
 static void launch_seq_gather(Engine& e, cudaStream_t s, const int* traj_in, const int* start_in, int rows,
@@ -623,12 +661,12 @@ static void sample_front(Engine& e, cudaStream_t s) {
   }
   const int warps_per_block = 8;
   k_sample_gather<<<(e.B + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, s>>>(
-      e.ds_rows, e.ds_n, e.ds_stride, c.obs_dim, c.act_dim, nullptr, c.seed, e.ds, (uint32_t)e.rank, e.B, e.b_obs,
+      e.ds_rows, e.ds_n, e.ds_stride, c.obs_dim, c.act_dim, nullptr, c.seed, &e.ds->step, (uint32_t)e.rank, e.B, e.b_obs,
       e.b_nobs, e.b_act, e.b_rew, e.b_cost, e.b_done, e.b_idx);
   e.launches++;
   if (!e.noise_buf.empty()) {
     k_noise_fill<<<dim3(64, (unsigned)e.noise_buf.size()), 256, 0, s>>>(e.d_slots_all, (int)e.noise_buf.size(), c.seed,
-                                                                         e.ds, (uint32_t)e.rank);
+                                                                         &e.ds->step, (uint32_t)e.rank);
     e.launches++;
   }
 }
@@ -651,6 +689,71 @@ static cudaGraphExec_t capture(Engine& e, bool sampled) {
   }
   OSRL_CUDA(cudaStreamEndCapture(s, &g));
   e.launches = before;  // capture does not execute
+  cudaGraphExec_t x = nullptr;
+  cudaError_t ce = cudaGraphInstantiate(&x, g, 0);
+  cudaGraphDestroy(g);
+  if (ce != cudaSuccess) throw Err(OSRL_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+  return x;
+}
+// ---- pipelined graphs.  side = VAE update of the step whose index is ds->vae_step, on the NEXT minibatch;
+// main = the rest of step ds->step on the current minibatch, VAE weights from the snapshot taken before the fork.
+static void side_ops(Engine& e, cudaStream_t s) {
+  const osrl_config& c = e.plan.cfg;
+  k_sample_gather<<<(e.B + 7) / 8, 256, 0, s>>>(e.ds_rows, e.ds_n, e.ds_stride, c.obs_dim, c.act_dim, nullptr, c.seed,
+                                               &e.ds->vae_step, (uint32_t)e.rank, e.B, e.nb_obs, e.nb_nobs, e.nb_act,
+                                               e.nb_rew, e.nb_cost, e.nb_done, e.nb_idx);
+  k_noise_fill<<<dim3(64, (unsigned)e.noise_buf.size()), 256, 0, s>>>(e.d_slots_vae, (int)e.noise_buf.size(), c.seed,
+                                                                       &e.ds->vae_step, (uint32_t)e.rank);
+  e.launches += 2;
+  prologue(e, s, 1u << e.plan.g_vae);
+  run_ops(e, e.pa, s);
+  epilogue(e, s, 2);
+}
+static void main_ops(Engine& e, cudaStream_t s) {
+  const osrl_config& c = e.plan.cfg;
+  k_sample_gather<<<(e.B + 7) / 8, 256, 0, s>>>(e.ds_rows, e.ds_n, e.ds_stride, c.obs_dim, c.act_dim, nullptr, c.seed,
+                                               &e.ds->step, (uint32_t)e.rank, e.B, e.b_obs, e.b_nobs, e.b_act, e.b_rew,
+                                               e.b_cost, e.b_done, e.b_idx);
+  k_noise_fill<<<dim3(64, (unsigned)e.noise_buf.size()), 256, 0, s>>>(e.d_slots_rest, (int)e.noise_buf.size(), c.seed,
+                                                                       &e.ds->step, (uint32_t)e.rank);
+  e.launches += 2;
+  prologue(e, s, ~(1u << e.plan.g_vae));
+  run_ops(e, e.pm, s);
+  epilogue(e, s, 1);
+}
+static void snapshot_vae(Engine& e, cudaStream_t s) {
+  const Group& g = e.plan.groups[e.plan.g_vae];
+  OSRL_CUDA(cudaMemcpyAsync(e.Psnap + g.begin, e.P + g.begin, (size_t)(g.end - g.begin) * sizeof(float),
+                            cudaMemcpyDeviceToDevice, s));
+}
+// which: 0 = first VAE update alone, 1 = steady state (fork / join), 2 = last step's remainder alone
+static cudaGraphExec_t capture_pipelined(Engine& e, int which) {
+  cudaStream_t s = e.cap_stream, s2 = e.side_stream;
+  const int64_t before = e.launches;
+  OSRL_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  cudaGraph_t g = nullptr;
+  try {
+    if (which == 0) {
+      side_ops(e, s);
+    } else {
+      snapshot_vae(e, s);
+      if (which == 1) {
+        OSRL_CUDA(cudaEventRecord(e.ev_fork, s));
+        OSRL_CUDA(cudaStreamWaitEvent(s2, e.ev_fork, 0));
+        side_ops(e, s2);
+        OSRL_CUDA(cudaEventRecord(e.ev_join, s2));
+      }
+      main_ops(e, s);
+      if (which == 1) OSRL_CUDA(cudaStreamWaitEvent(s, e.ev_join, 0));
+    }
+  } catch (...) {
+    cudaStreamEndCapture(s, &g);
+    if (g) cudaGraphDestroy(g);
+    e.launches = before;
+    throw;
+  }
+  OSRL_CUDA(cudaStreamEndCapture(s, &g));
+  e.launches = before;
   cudaGraphExec_t x = nullptr;
   cudaError_t ce = cudaGraphInstantiate(&x, g, 0);
   cudaGraphDestroy(g);
@@ -824,7 +927,7 @@ int osrl_buffer_upload(osrl_engine* h, const osrl_dataset_view* v) {
   e.ds_rows = (float*)d;
   e.ds_n = v->n;
   e.ds_stride = stride;
-  if (e.g_sampled) { cudaGraphExecDestroy(e.g_sampled); e.g_sampled = nullptr; }
+  drop_sampled_graphs(e);
   OSRL_CATCH
 }
 
@@ -868,7 +971,7 @@ int osrl_seq_buffer_upload(osrl_engine* h, const osrl_seq_dataset_view* v) {
   e.sq_ntraj = (int)v->n_traj;
   e.sq_stride = stride;
   e.ds_rows = e.sq_rows;  // marks "a resident dataset exists" for osrl_steps
-  if (e.g_sampled) { cudaGraphExecDestroy(e.g_sampled); e.g_sampled = nullptr; }
+  drop_sampled_graphs(e);
   OSRL_CATCH
 }
 
@@ -946,7 +1049,7 @@ int osrl_gather(osrl_engine* h, const int64_t* idx, int n, int idx_on_host, osrl
     if (out->on_host) { OSRL_CUDA(cudaMalloc(&tmp[k], cnt[k] * sizeof(float))); dev[k] = (float*)tmp[k]; }
     else dev[k] = dst[k];
   }
-  k_sample_gather<<<(n + 7) / 8, 256, 0, s>>>(e.ds_rows, e.ds_n, e.ds_stride, o, a, didx, 0, e.ds, 0, n, dev[0], dev[1],
+  k_sample_gather<<<(n + 7) / 8, 256, 0, s>>>(e.ds_rows, e.ds_n, e.ds_stride, o, a, didx, 0, &e.ds->step, 0, n, dev[0], dev[1],
                                               dev[2], dev[3], dev[4], dev[5], nullptr);
   e.launches++;
   OSRL_CUDA(cudaGetLastError());
@@ -1001,7 +1104,7 @@ int osrl_step(osrl_engine* h, const osrl_batch* b, const osrl_noise* nz, void* s
         OSRL_CUDA(cudaStreamSynchronize(s));
         slots = e.d_slots_dyn;
       }
-      k_noise_fill<<<dim3(64, (unsigned)ns), 256, 0, s>>>(slots, ns, e.plan.cfg.seed, e.ds, (uint32_t)e.rank);
+      k_noise_fill<<<dim3(64, (unsigned)ns), 256, 0, s>>>(slots, ns, e.plan.cfg.seed, &e.ds->step, (uint32_t)e.rank);
       e.launches++;
     }
   }
@@ -1045,9 +1148,21 @@ int osrl_steps(osrl_engine* h, int k, void* stream) {
   if (e.plan.cfg.algo == OSRL_ALGO_CDT) OSRL_REQUIRE(e.sq_rows, "CDT needs osrl_seq_buffer_upload");
   OSRL_CUDA(cudaSetDevice(e.device));
   cudaStream_t s = (cudaStream_t)stream;
-  if (!e.g_sampled) e.g_sampled = capture(e, true);
-  for (int i = 0; i < k; ++i) OSRL_CUDA(cudaGraphLaunch(e.g_sampled, s));
-  e.launches += (int64_t)k * kernels_per_step(e, true);
+  if (e.pipelined && k >= 2) {
+    // VAE update of step s+1 overlapped with the rest of step s; same kernels on the same data in the same
+    // per-parameter order as the sequential graph, so the state after k steps is bit-identical to k x osrl_steps(1)
+    if (!e.g_pro) e.g_pro = capture_pipelined(e, 0);
+    if (!e.g_mid) e.g_mid = capture_pipelined(e, 1);
+    if (!e.g_last) e.g_last = capture_pipelined(e, 2);
+    OSRL_CUDA(cudaGraphLaunch(e.g_pro, s));
+    for (int i = 0; i + 1 < k; ++i) OSRL_CUDA(cudaGraphLaunch(e.g_mid, s));
+    OSRL_CUDA(cudaGraphLaunch(e.g_last, s));
+    e.launches += (int64_t)k * (e.pa.kernels + e.pm.kernels + 8);
+  } else {
+    if (!e.g_sampled) e.g_sampled = capture(e, true);
+    for (int i = 0; i < k; ++i) OSRL_CUDA(cudaGraphLaunch(e.g_sampled, s));
+    e.launches += (int64_t)k * kernels_per_step(e, true);
+  }
   OSRL_CATCH
 }
 
@@ -1104,7 +1219,7 @@ int osrl_scalars_set(osrl_engine* h, const double* in, int n) {
   OSRL_CUDA(cudaDeviceSynchronize());
   DevState d;
   OSRL_CUDA(cudaMemcpy(&d, e.ds, sizeof(d), cudaMemcpyDeviceToHost));
-  d.step = (unsigned long long)in[0]; d.pid_e_old = (float)in[1]; d.pid_e_int = (float)in[2];
+  d.step = d.vae_step = (unsigned long long)in[0]; d.pid_e_old = (float)in[1]; d.pid_e_int = (float)in[2];
   d.log_alpha = (float)in[3]; d.n_train_steps = (int)in[4]; d.log_temperature = in[5];
   for (int i = 0; i < 4; ++i) d.adam_t[i] = (int)in[6 + i];
   OSRL_CUDA(cudaMemcpy(e.ds, &d, sizeof(d), cudaMemcpyHostToDevice));

@@ -155,6 +155,17 @@ struct Engine {
   // program + graphs
   Program body;
   cudaGraphExec_t g_body = nullptr, g_sampled = nullptr;
+  // pipelined osrl_steps(k >= 2): the VAE update of step s+1 (program pa, minibatch nb_*, counter vae_step) runs
+  // concurrently with the critic / actor updates of step s (program pm, VAE weights read from the snapshot Psnap)
+  Program pa, pm;
+  bool pipelined = false;
+  float *nb_obs = nullptr, *nb_nobs = nullptr, *nb_act = nullptr, *nb_rew = nullptr, *nb_cost = nullptr, *nb_done = nullptr;
+  int64_t* nb_idx = nullptr;
+  float* Psnap = nullptr;
+  NoiseSlot *d_slots_vae = nullptr, *d_slots_rest = nullptr;
+  cudaGraphExec_t g_pro = nullptr, g_mid = nullptr, g_last = nullptr;
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaStream_t cap_stream = nullptr;
   float* stats = nullptr;
   std::vector<void*> allocs;
@@ -229,7 +240,7 @@ void mlp_bwd(Engine& e, Program& p, const float* W, float* Gsec, const MlpLay& m
 void emit_stages(Engine& e, Program& p, std::vector<Stage>& st);
 
 void build_bc(Engine& e);
-void build_bcql(Engine& e);
+void build_bcql(Engine& e, int phase = 0);
 void build_cpq(Engine& e);
 void build_bearl(Engine& e);
 void build_cdt(Engine& e);

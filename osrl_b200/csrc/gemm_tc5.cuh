@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_gemm_tc5(const __grid_constan
   using S = Shape<BN_, NSTAGE_>;
   constexpr int BN = S::BN, NSTAGE = S::NSTAGE, STAGE_BYTES = S::STAGE_BYTES, TMEM_COLS = S::TMEM_COLS;
   constexpr int A_T = A_TILE_BYTES, B_T = S::B_TILE_BYTES;
-  constexpr bool PREFETCH = (MINB == 1);
+  constexpr bool PREFETCH = (MINB == 1) || APACK;   // APACK: only the small B tile passes through registers
   constexpr int BCH = BN * 8 / PRODUCERS;   // 16-byte chunks of the B tile per producer thread
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], acc_bar;

@@ -10,6 +10,9 @@ namespace osrl {
 #define OSRL_MAX_GROUPS 8
 struct DevState {
   unsigned long long step;            // completed steps (Philox counter word)
+  unsigned long long vae_step;        // completed VAE updates: equals `step` between osrl_steps() calls; inside a
+                                      // pipelined run the VAE update of step s+1 overlaps the rest of step s and
+                                      // draws its batch / noise with this counter (engine.cu, pipelined graphs)
   int adam_t[OSRL_MAX_GROUPS];        // per-group Adam step count
   float adam_lr[OSRL_MAX_GROUPS];     // lr used for the current step (after schedule)
   float adam_step_size[OSRL_MAX_GROUPS];  // lr / (1 - beta1^t)
@@ -75,9 +78,10 @@ struct AdamGroupCfg {
   double lr, beta1, beta2;
   int warmup;  // >0: lr * min((t)/warmup, 1) with t = step count after increment (LambdaLR, cdt.py:327-330)
 };
-static __global__ void k_prologue(DevState* ds, const AdamGroupCfg* g, int ngroups) {
+static __global__ void k_prologue(DevState* ds, const AdamGroupCfg* g, int ngroups, unsigned mask) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   for (int i = 0; i < ngroups; ++i) {
+    if (!((mask >> i) & 1u)) continue;   // pipelined graphs advance the VAE group and the others separately
     const int t = ds->adam_t[i] + 1;
     ds->adam_t[i] = t;
     double lr = (double)g[i].lr;
@@ -92,8 +96,12 @@ static __global__ void k_prologue(DevState* ds, const AdamGroupCfg* g, int ngrou
     ds->adam_bc2_sqrt[i] = (float)sqrt(bc2);
   }
 }
-static __global__ void k_epilogue(DevState* ds) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) ds->step += 1ull;
+// mode 0: a whole step finished (both counters); 1: everything but the VAE update; 2: the VAE update only
+static __global__ void k_epilogue(DevState* ds, int mode) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (mode == 0) { ds->step += 1ull; ds->vae_step = ds->step; }
+  else if (mode == 1) ds->step += 1ull;
+  else ds->vae_step += 1ull;
 }
 
 // ------------------------------------------------------------------ Adam (+ Polyak target) over a flat range
@@ -163,10 +171,11 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, fl
   z1 = r * s;
 }
 struct NoiseSlot { float* dst; long long count; int stream; int enabled; };
-static __global__ void k_noise_fill(const NoiseSlot* slots, int nslots, uint64_t seed, const DevState* ds, uint32_t rank) {
+static __global__ void k_noise_fill(const NoiseSlot* slots, int nslots, uint64_t seed,
+                                    const unsigned long long* __restrict__ step_ctr, uint32_t rank) {
   const NoiseSlot s = slots[blockIdx.y];
   if (!s.enabled) return;
-  const uint64_t step = ds->step;
+  const uint64_t step = *step_ctr;
   const long long n4 = (s.count + 3) / 4;
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {
     uint32_t c[4] = {(uint32_t)q, (uint32_t)step,
@@ -186,7 +195,8 @@ static __global__ void k_noise_fill(const NoiseSlot* slots, int nslots, uint64_t
 // Replaces TransitionDataset.__iter__/__prepare_sample + collate + .to(device)
 // (dataset.py:832-847, train_bcql.py:143-146).  One warp per sampled row.
 static __global__ void k_sample_gather(const float* __restrict__ ds_rows, int64_t n, int stride, int o, int a,
-                                const int64_t* __restrict__ idx_in, uint64_t seed, const DevState* st, uint32_t rank,
+                                const int64_t* __restrict__ idx_in, uint64_t seed,
+                                const unsigned long long* __restrict__ step_ctr, uint32_t rank,
                                 int rows, float* obs, float* nobs, float* act, float* rew, float* cost, float* done,
                                 int64_t* idx_out) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -194,7 +204,7 @@ static __global__ void k_sample_gather(const float* __restrict__ ds_rows, int64_
   if (w >= rows) return;
   int64_t idx;
   if (idx_in) idx = idx_in[w];
-  else idx = draw_index(seed, st->step, rank, (uint32_t)w, n);
+  else idx = draw_index(seed, *step_ctr, rank, (uint32_t)w, n);
   if (idx_out && lane == 0) idx_out[w] = idx;
   const float* __restrict__ row = ds_rows + idx * (int64_t)stride;
   for (int c = lane; c < o; c += 32) {

@@ -236,3 +236,35 @@ def test_sampled_steps_match_oracle_on_dumped_batch(lib_built):
         s32, s64, g32, g64, before, p64 = probe_step(orc, "bcql", b, noise=nz)
         _compare_step(f"sampled step {s}", eng, s32, s64, g32, g64, before, p64, "tc5")
     eng.close()
+
+
+@pytest.mark.parametrize("algo", ["bcql"])
+def test_pipelined_steps_equal_sequential(lib_built, algo):
+    """osrl_steps(k >= 2) overlaps the VAE update of step s+1 with the critic / actor updates of step s (two graph
+    branches, VAE weights snapshotted for the readers).  Same kernels on the same data in the same per-parameter order:
+    the state after k steps must be BIT-identical to k single-step (sequential graph) calls."""
+    z, meta = load_golden(f"{algo}_full")
+    cfg, B = meta["cfg"], meta["B"]
+    data = synth.make_dataset(cfg["state_dim"], cfg["action_dim"], 300, 60, seed=0)
+    orc = make_oracle(algo, cfg, 0)
+    engs = []
+    for _ in range(2):
+        eng = _engine(meta, B)
+        eng.load_params(orc.params)
+        eng.upload_dataset(data, reward_scale=0.1, cost_scale=1.0)
+        engs.append(eng)
+    seq, pipe = engs
+    for _ in range(7):
+        seq.steps(1)
+    pipe.steps(4)          # prologue + 3 x steady state + last
+    pipe.steps(1)          # sequential graph in between: the counters must stay consistent
+    pipe.steps(2)
+    for sec in ("param", "target", "grad", "adam_m", "adam_v"):
+        a, b = seq.read_section(sec), pipe.read_section(sec)
+        for k in a:
+            assert torch.equal(a[k], b[k]), f"{sec} {k}: pipelined run differs (max |d| {float((a[k] - b[k]).abs().max()):.3e})"
+    assert seq.scalars() == pipe.scalars()
+    assert seq.stats() == pipe.stats()
+    assert np.array_equal(seq.last_indices(), pipe.last_indices())
+    for eng in engs:
+        eng.close()
