@@ -27,10 +27,16 @@ static MlpLay sq_as_mlp(const SqActorLay& s) {
 }
 
 // ====================================================================== CPQ
-void build_cpq(Engine& e) {
+// phase: see build_bcql (0 = whole step, 1 = VAE update alone on the NEXT minibatch, 2 = the rest, VAE weights
+// read from the snapshot)
+void build_cpq(Engine& e, int phase) {
   const osrl_config& c = e.plan.cfg;
   const Plan& pl = e.plan;
-  Program& p = e.body;
+  Program& p = phase == 1 ? e.pa : (phase == 2 ? e.pm : e.body);
+  const bool do_vae = phase != 2, do_rest = phase != 1;
+  const float* bobs = phase == 1 ? e.nb_obs : e.b_obs;
+  const float* bact = phase == 1 ? e.nb_act : e.b_act;
+  const float* Wvae = phase == 2 ? e.Psnap : e.P;
   const int B = e.B, S = c.sample_action_num, SB = S * B, o = c.obs_dim, a = c.act_dim, L = 2 * a, V = c.vae_hidden;
   const int in = o + a, din = o + L;
   const float lim = c.max_action, iw = e.inv_world();
@@ -50,19 +56,22 @@ void build_cpq(Engine& e) {
   float* p_qin = e.ws((size_t)B * in);          // actor step
   {
     std::vector<CopyTask> ct;
-    ct.push_back(copy_cols(sa, in, 0, e.b_obs, o, 0, B, o));
-    ct.push_back(copy_cols(sa, in, o, e.b_act, a, 0, B, a));
-    ct.push_back(copy_cols(v_dec_in, din, 0, e.b_obs, o, 0, B, o));
-    ct.push_back(copy_cols(obs2, o, 0, e.b_nobs, o, 0, B, o));
-    ct.push_back(copy_cols(obs2 + (size_t)B * o, o, 0, e.b_obs, o, 0, B, o));
-    ct.push_back(copy_cols(qin1, in, 0, e.b_nobs, o, 0, B, o));
-    ct.push_back(copy_cols(qin2, in, 0, e.b_nobs, o, 0, B, o));
-    ct.push_back(copy_cols(qin_ood, in, 0, e.b_obs, o, 0, SB, o, 1, B));  // torch.tile (cpq.py:169-173)
-    ct.push_back(copy_cols(p_qin, in, 0, e.b_obs, o, 0, B, o));
+    ct.push_back(copy_cols(sa, in, 0, bobs, o, 0, B, o));
+    ct.push_back(copy_cols(sa, in, o, bact, a, 0, B, a));
+    if (do_vae) ct.push_back(copy_cols(v_dec_in, din, 0, bobs, o, 0, B, o));
+    if (do_rest) {
+      ct.push_back(copy_cols(obs2, o, 0, e.b_nobs, o, 0, B, o));
+      ct.push_back(copy_cols(obs2 + (size_t)B * o, o, 0, e.b_obs, o, 0, B, o));
+      ct.push_back(copy_cols(qin1, in, 0, e.b_nobs, o, 0, B, o));
+      ct.push_back(copy_cols(qin2, in, 0, e.b_nobs, o, 0, B, o));
+      ct.push_back(copy_cols(qin_ood, in, 0, e.b_obs, o, 0, SB, o, 1, B));  // torch.tile (cpq.py:169-173)
+      ct.push_back(copy_cols(p_qin, in, 0, e.b_obs, o, 0, B, o));
+    }
     emit_copy(e, p, ct);
   }
   // ---- 1. VAE
-  emit_vae_update(e, p, sa, v_dec_in, n_vae, e.b_act, 0);
+  if (do_vae) emit_vae_update(e, p, sa, v_dec_in, n_vae, bact, 0);
+  if (!do_rest) return;
 
   // ---- 2+3. critic and cost critic
   float* mh2 = e.ws((size_t)2 * B * 2 * a);  // actor (mu|log_std) on [next_obs ; obs]
@@ -86,9 +95,9 @@ void build_cpq(Engine& e) {
     ens_fwd(st, cr, e.P, sa, in, B, oq);
     ens_fwd(st, cc, e.P, sa, in, B, oqc);
     // VAE encoder on the OOD samples (cpq.py:178; decoder output is discarded there)
-    st[0].tasks.push_back(task_fwd(qin_ood, in, SB, e.P, pl.vae.e1, ood_h1, V, ACT_RELU));
-    st[1].tasks.push_back(task_fwd(ood_h1, V, SB, e.P, pl.vae.e2, ood_h2, V, ACT_RELU));
-    st[2].tasks.push_back(task_fwd(ood_h2, V, SB, e.P, pl.vae.heads, ood_ml, 2 * L, ACT_NONE));
+    st[0].tasks.push_back(task_fwd(qin_ood, in, SB, Wvae, pl.vae.e1, ood_h1, V, ACT_RELU));
+    st[1].tasks.push_back(task_fwd(ood_h1, V, SB, Wvae, pl.vae.e2, ood_h2, V, ACT_RELU));
+    st[2].tasks.push_back(task_fwd(ood_h2, V, SB, Wvae, pl.vae.heads, ood_ml, 2 * L, ACT_NONE));
     emit_stages(e, p, st);
   }
   float* yq = e.ws(B); float* yc = e.ws(B);
@@ -160,10 +169,14 @@ void build_cpq(Engine& e) {
 }
 
 // ====================================================================== BEAR-Lag
-void build_bearl(Engine& e) {
+void build_bearl(Engine& e, int phase) {
   const osrl_config& c = e.plan.cfg;
   const Plan& pl = e.plan;
-  Program& p = e.body;
+  Program& p = phase == 1 ? e.pa : (phase == 2 ? e.pm : e.body);
+  const bool do_vae = phase != 2, do_rest = phase != 1;
+  const float* bobs = phase == 1 ? e.nb_obs : e.b_obs;
+  const float* bact = phase == 1 ? e.nb_act : e.b_act;
+  const float* Wvae = phase == 2 ? e.Psnap : e.P;
   const int B = e.B, S = c.sample_action_num, R = B * S, N = c.num_samples_mmd_match, BN = B * N;
   const int o = c.obs_dim, a = c.act_dim, L = 2 * a, V = c.vae_hidden;
   const int in = o + a, din = o + L;
@@ -183,19 +196,22 @@ void build_bearl(Engine& e) {
   float* p_qin = e.ws((size_t)B * in);
   {
     std::vector<CopyTask> ct;
-    ct.push_back(copy_cols(sa, in, 0, e.b_obs, o, 0, B, o));
-    ct.push_back(copy_cols(sa, in, o, e.b_act, a, 0, B, a));
-    ct.push_back(copy_cols(v_dec_in, din, 0, e.b_obs, o, 0, B, o));
-    ct.push_back(copy_cols(t_qin, in, 0, e.b_nobs, o, 0, 2 * R, o, S, B));   // repeat_interleave (bearl.py:160)
-    ct.push_back(copy_cols(m_dec_in, din, 0, e.b_obs, o, 0, BN, o, N, B));   // net.py:348-351
-    CopyTask z = copy_cols(m_dec_in, din, o, n_z, L, 0, BN, L);
-    z.clamp = 1; z.lo = -0.5f; z.hi = 0.5f;
-    ct.push_back(z);
-    ct.push_back(copy_cols(p_qin, in, 0, e.b_obs, o, 0, B, o));
+    ct.push_back(copy_cols(sa, in, 0, bobs, o, 0, B, o));
+    ct.push_back(copy_cols(sa, in, o, bact, a, 0, B, a));
+    if (do_vae) ct.push_back(copy_cols(v_dec_in, din, 0, bobs, o, 0, B, o));
+    if (do_rest) {
+      ct.push_back(copy_cols(t_qin, in, 0, e.b_nobs, o, 0, 2 * R, o, S, B));   // repeat_interleave (bearl.py:160)
+      ct.push_back(copy_cols(m_dec_in, din, 0, e.b_obs, o, 0, BN, o, N, B));   // net.py:348-351
+      CopyTask z = copy_cols(m_dec_in, din, o, n_z, L, 0, BN, L);
+      z.clamp = 1; z.lo = -0.5f; z.hi = 0.5f;
+      ct.push_back(z);
+      ct.push_back(copy_cols(p_qin, in, 0, e.b_obs, o, 0, B, o));
+    }
     emit_copy(e, p, ct);
   }
   // ---- 1. VAE
-  emit_vae_update(e, p, sa, v_dec_in, n_vae, e.b_act, 0);
+  if (do_vae) emit_vae_update(e, p, sa, v_dec_in, n_vae, bact, 0);
+  if (!do_rest) return;
 
   // ---- 2+3. critics: actor_old's (mu, std) depend on next_obs only -> one B-row pass, S samples each
   float* mht = e.ws((size_t)B * 2 * a);
@@ -246,7 +262,7 @@ void build_bearl(Engine& e) {
   float* raw_vae = e.ws((size_t)BN * a);  // decode_multiple pre-tanh output (net.py:353)
   {
     float* h1 = e.ws((size_t)BN * V); float* h2 = e.ws((size_t)BN * V);
-    emit_vae_decode(e, p, e.P, m_dec_in, BN, h1, h2, raw_vae, a, 1);
+    emit_vae_decode(e, p, Wvae, m_dec_in, BN, h1, h2, raw_vae, a, 1);
   }
   float* mh = e.ws((size_t)B * 2 * a);
   float* samp = e.ws((size_t)BN * a);   // tanh(u)

@@ -549,6 +549,8 @@ static void build_pipelined(Engine& e, const std::vector<int>& vae_slots) {
   OSRL_CUDA(cudaEventCreateWithFlags(&e.ev_join, cudaEventDisableTiming));
   switch (c.algo) {
     case OSRL_ALGO_BCQL: build_bcql(e, 1); build_bcql(e, 2); break;
+    case OSRL_ALGO_CPQ: build_cpq(e, 1); build_cpq(e, 2); break;
+    case OSRL_ALGO_BEARL: build_bearl(e, 1); build_bearl(e, 2); break;
     default: return;
   }
   e.pipelined = true;
@@ -557,8 +559,8 @@ static void build_program(Engine& e) {
   switch (e.plan.cfg.algo) {
     case OSRL_ALGO_BC: build_bc(e); break;
     case OSRL_ALGO_BCQL: build_bcql(e); build_pipelined(e, {0}); break;
-    case OSRL_ALGO_CPQ: build_cpq(e); break;
-    case OSRL_ALGO_BEARL: build_bearl(e); break;
+    case OSRL_ALGO_CPQ: build_cpq(e); build_pipelined(e, {0}); break;
+    case OSRL_ALGO_BEARL: build_bearl(e); build_pipelined(e, {0}); break;
     case OSRL_ALGO_CDT: build_cdt(e); break;
     default: throw Err(OSRL_ERR_UNSUPPORTED, "algorithm not supported");
   }

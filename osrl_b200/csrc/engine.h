@@ -241,8 +241,8 @@ void emit_stages(Engine& e, Program& p, std::vector<Stage>& st);
 
 void build_bc(Engine& e);
 void build_bcql(Engine& e, int phase = 0);
-void build_cpq(Engine& e);
-void build_bearl(Engine& e);
+void build_cpq(Engine& e, int phase = 0);
+void build_bearl(Engine& e, int phase = 0);
 void build_cdt(Engine& e);
 
 }  // namespace osrl

@@ -238,7 +238,7 @@ def test_sampled_steps_match_oracle_on_dumped_batch(lib_built):
     eng.close()
 
 
-@pytest.mark.parametrize("algo", ["bcql"])
+@pytest.mark.parametrize("algo", ["bcql", "cpq", "bearl"])
 def test_pipelined_steps_equal_sequential(lib_built, algo):
     """osrl_steps(k >= 2) overlaps the VAE update of step s+1 with the critic / actor updates of step s (two graph
     branches, VAE weights snapshotted for the readers).  Same kernels on the same data in the same per-parameter order:

@@ -1,2 +1,3 @@
-timeout 300 python -m pytest tests/test_gpu_parity.py -q -x -k "pipelined or sampled" 2>&1 | tail -12
-for pl in 1 0; do echo "== PIPELINE=$pl"; OSRL_PIPELINE=$pl timeout 200 python tools/quick_bench.py bcql 256 1000 2>&1 | cut -c1-120; done
+timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -k "pipelined" 2>&1 | tail -12
+for algo in cpq bearl; do for pl in 1 0; do echo "== $algo PIPELINE=$pl"; OSRL_PIPELINE=$pl timeout 200 python tools/quick_bench.py $algo 256 500 2>&1 | cut -c1-100; done; done
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -4
