@@ -420,6 +420,7 @@ static int (*CommInitRank)(void**, int, Uid, int) = nullptr;
 static AllReduce_t AllReduce = nullptr;
 static CommDestroy_t CommDestroy = nullptr;
 static GetErrorString_t GetErrorString = nullptr;
+static int (*CommSplit)(void*, int, int, void**, void*) = nullptr;   // optional (NCCL >= 2.18)
 static void load() {
   if (lib) return;
   const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
@@ -430,6 +431,7 @@ static void load() {
   AllReduce = (AllReduce_t)dlsym(lib, "ncclAllReduce");
   CommDestroy = (CommDestroy_t)dlsym(lib, "ncclCommDestroy");
   GetErrorString = (GetErrorString_t)dlsym(lib, "ncclGetErrorString");
+  CommSplit = (int (*)(void*, int, int, void**, void*))dlsym(lib, "ncclCommSplit");
   if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) throw Err(OSRL_ERR_NCCL, "libnccl lacks required symbols");
 }
 static void check(int r, const char* what) {
@@ -440,9 +442,12 @@ static void check(int r, const char* what) {
 void emit_allreduce(Engine& e, Program& p, float* buf, int64_t count) {
   if (e.world <= 1) return;
   Engine* ep = &e;
+  const bool side = (&p == &e.pa);   // the pipelined VAE branch reduces on its own communicator: the two branches'
+                                     // collectives may then be in flight at the same time
   p.add("ncclAllReduce", 4.0 * (double)count, 0.0, false, [=](cudaStream_t s) {
-    if (!ep->comm) throw Err(OSRL_ERR_STATE, "world_size > 1 but osrl_comm_init was not called");
-    nccl::check(nccl::AllReduce(buf, buf, (size_t)count, /*ncclFloat32*/ 7, /*ncclSum*/ 0, ep->comm, s), "ncclAllReduce");
+    void* comm = side ? ep->comm2 : ep->comm;
+    if (!comm) throw Err(OSRL_ERR_STATE, "world_size > 1 but osrl_comm_init was not called");
+    nccl::check(nccl::AllReduce(buf, buf, (size_t)count, /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm, s), "ncclAllReduce");
   });
 }
 
@@ -519,14 +524,15 @@ static void free_all(Engine* e) {
   if (e->side_stream) cudaStreamDestroy(e->side_stream);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   for (void* p : e->allocs) cudaFree(p);
+  if (e->comm2 && nccl::CommDestroy) nccl::CommDestroy(e->comm2);
   if (e->comm && nccl::CommDestroy) nccl::CommDestroy(e->comm);
 }
 
-// Second build of the step as two concurrent halves (see Engine::pa / pm).  Only single-GPU for now: the halves'
-// gradient all-reduces would need two communicators to overlap.  OSRL_PIPELINE=0 keeps osrl_steps() sequential.
+// Second build of the step as two concurrent halves (see Engine::pa / pm).  Data parallel: the VAE branch all-reduces
+// on a second communicator (ncclCommSplit of the first, osrl_comm_init).  OSRL_PIPELINE=0 keeps osrl_steps() sequential.
 static void build_pipelined(Engine& e, const std::vector<int>& vae_slots) {
   const char* v = getenv("OSRL_PIPELINE");
-  if ((v && v[0] == '0') || e.world > 1) return;
+  if (v && v[0] == '0') return;
   const osrl_config& c = e.plan.cfg;
   const int o = c.obs_dim, a = c.act_dim, B = e.B;
   e.nb_obs = e.ws((size_t)B * o); e.nb_nobs = e.ws((size_t)B * o); e.nb_act = e.ws((size_t)B * a);
@@ -1150,7 +1156,7 @@ int osrl_steps(osrl_engine* h, int k, void* stream) {
   if (e.plan.cfg.algo == OSRL_ALGO_CDT) OSRL_REQUIRE(e.sq_rows, "CDT needs osrl_seq_buffer_upload");
   OSRL_CUDA(cudaSetDevice(e.device));
   cudaStream_t s = (cudaStream_t)stream;
-  if (e.pipelined && k >= 2) {
+  if (e.pipelined && k >= 2 && (e.world == 1 || e.comm2)) {
     // VAE update of step s+1 overlapped with the rest of step s; same kernels on the same data in the same
     // per-parameter order as the sequential graph, so the state after k steps is bit-identical to k x osrl_steps(1)
     if (!e.g_pro) e.g_pro = capture_pipelined(e, 0);
@@ -1405,6 +1411,8 @@ int osrl_comm_init(osrl_engine* h, const char id[128], int world_size, int rank)
   nccl::Uid u;
   memcpy(u.internal, id, 128);
   nccl::check(nccl::CommInitRank(&e.comm, world_size, u, rank), "ncclCommInitRank");
+  if (e.pipelined && nccl::CommSplit)   // communicator of the pipelined VAE branch (absent: osrl_steps stays sequential)
+    nccl::check(nccl::CommSplit(e.comm, 0, rank, &e.comm2, nullptr), "ncclCommSplit");
   OSRL_CATCH
 }
 

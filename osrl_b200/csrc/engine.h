@@ -176,6 +176,7 @@ struct Engine {
   int64_t launches = 0;
   // data parallel
   void* comm = nullptr;
+  void* comm2 = nullptr;   // pipelined VAE branch
   int world = 1, rank = 0;
 
   float* ws(size_t n);  // zero-initialised device workspace

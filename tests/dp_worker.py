@@ -89,6 +89,42 @@ def run(algo: str, backend: str, steps: int = 3, Bg: int = 32):
     return bool(ok.item())
 
 
+def run_pipelined(algo: str, steps: int = 5, Bg: int = 32):
+    """osrl_steps(k) on a resident dataset shard under data parallelism: the pipelined graphs (VAE branch on its own
+    communicator) must leave every rank in exactly the state k sequential single-step graphs do."""
+    from osrl_b200 import Engine, comm_unique_id
+    rank, world = dist.get_rank(), dist.get_world_size()
+    cfg = CFGS[algo]
+    dev = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(dev)
+    init = make_oracle(algo, cfg, 0).params
+    data = synth.make_dataset(cfg["state_dim"], cfg["action_dim"], 50, 20, seed=100 + rank)   # this rank's shard
+    engs = []
+    for _ in range(2):
+        eng = Engine(algo, batch_size=Bg // world, device=dev, seed=1, world_size=world, rank=rank, **cfg)
+        eng.load_params(init)
+        ids = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        eng.init_comm(ids[0])
+        eng.upload_dataset(data, 0.1, 1.0)
+        engs.append(eng)
+    for _ in range(steps):
+        engs[0].steps(1)
+    engs[1].steps(steps)
+    torch.cuda.synchronize()
+    same = True
+    for sec in ("param", "target", "adam_m", "adam_v"):
+        a, b = engs[0].read_section(sec), engs[1].read_section(sec)
+        same = same and all(torch.equal(a[k], b[k]) for k in a)
+    ok = torch.tensor([1.0 if same else 0.0]).cuda()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(json.dumps({"algo": algo, "mode": "pipelined-vs-sequential", "world": world, "ok": bool(ok.item())}))
+    for eng in engs:
+        eng.close()
+    return bool(ok.item())
+
+
 def _mp_entry(rank, world, algo, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -102,6 +138,6 @@ def _mp_entry(rank, world, algo, port, q):
 if __name__ == "__main__":   # torchrun entry (GPU): python -m torch.distributed.run ... tests/dp_worker.py bcql
     algo_list = sys.argv[1:] or ["bcql"]
     dist.init_process_group("nccl")
-    good = all(run(a, "nccl") for a in algo_list)
+    good = all(run_pipelined(a[5:]) if a.startswith("pipe:") else run(a, "nccl") for a in algo_list)
     dist.destroy_process_group()
     sys.exit(0 if good else 1)
