@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define OSRL_ABI_VERSION 1
+#define OSRL_ABI_VERSION 2
 
 enum { OSRL_OK = 0, OSRL_ERR_ARG = -1, OSRL_ERR_CUDA = -2, OSRL_ERR_STATE = -3, OSRL_ERR_NCCL = -4,
        OSRL_ERR_UNSUPPORTED = -5 };
@@ -112,8 +112,11 @@ typedef struct osrl_batch {
 
 /* Noise replay: raw standard-normal draws in the order the reference consumes them
  * (SURVEY.md Appendix B).  Slot names/sizes come from osrl_noise_layout.  NULL slots (or a
- * NULL osrl_noise) are generated on the device with Philox4x32-10. */
-#define OSRL_MAX_NOISE 8
+ * NULL osrl_noise) are generated on the device with Philox4x32-10.
+ * CDT dropout (net.py:404-414, cdt.py:87,222): slots named "drop_*" hold the dropout multipliers themselves,
+ * 0 or 1/(1-p) per element -- "drop_emb" [B,4T,E], per block i "drop_attn<i>" [B,H,4T,4T] (attention weights),
+ * "drop_res<i>a" [B,4T,E] (after the attention projection), "drop_res<i>b" [B,4T,E] (after the MLP). */
+#define OSRL_MAX_NOISE 32
 typedef struct osrl_noise {
   int32_t on_host;
   const float* slot[OSRL_MAX_NOISE];
@@ -194,7 +197,7 @@ int osrl_last_sequences(osrl_engine* e, int32_t* traj_out, int32_t* start_out, i
 int osrl_step(osrl_engine* e, const osrl_batch* batch, const osrl_noise* noise, void* stream);
 /* Replaces CDTTrainer.train_one_step (cdt.py:343-418): forward, losses, backward, clip_grad_norm_, AdamW with
  * LR warm-up, temperature Adam -- one sequence minibatch, no host sync. */
-int osrl_step_seq(osrl_engine* e, const osrl_seq_batch* batch, void* stream);
+int osrl_step_seq(osrl_engine* e, const osrl_seq_batch* batch, const osrl_noise* noise_or_null, void* stream);
 /* k steps with minibatches drawn on the device from the resident dataset (replaces the loop
  * body train_bcql.py:142-148 including DataLoader draw and .to(device)). */
 int osrl_steps(osrl_engine* e, int k, void* stream);

@@ -54,8 +54,8 @@ class CDTOracle:
     343-418; TransformerBlock net.py:391-441; DiagGaussianActor net.py:509-533."""
 
     def __init__(self, cfg: CDTConfig):
-        assert cfg.attention_dropout == cfg.residual_dropout == cfg.embedding_dropout == 0.0, \
-            "the oracle compares at dropout 0 (SURVEY.md 7.5-1)"
+        # dropout: the multipliers (0 or 1/(1-p)) are explicit inputs ("noise"), drawn here when not provided, so a
+        # step can be replayed elsewhere on the same draws (SURVEY.md 7.5-1)
         self.cfg = cfg
         E, o, a, T = cfg.embedding_dim, cfg.state_dim, cfg.action_dim, cfg.seq_len
         self.H, self.d, self.Lq = cfg.num_heads, E // cfg.num_heads, 4 * T
@@ -132,9 +132,30 @@ class CDTOracle:
         self.steps = 0
         self.last_noise: Dict[str, torch.Tensor] = {}
 
+    # ---- dropout multipliers, one tensor per site, in the reference's call order (cdt.py:222; net.py:428-440:
+    # attention weights inside nn.MultiheadAttention, self.drop(attention_out), the mlp's trailing nn.Dropout)
+    def mask_shapes(self, B: int):
+        cfg = self.cfg
+        L, E, H = 4 * cfg.seq_len, cfg.embedding_dim, cfg.num_heads
+        out = OrderedDict()
+        if cfg.embedding_dropout > 0:
+            out["drop_emb"] = ((B, L, E), cfg.embedding_dropout)
+        for i in range(cfg.num_layers):
+            if cfg.attention_dropout > 0:
+                out[f"drop_attn{i}"] = ((B, H, L, L), cfg.attention_dropout)
+            if cfg.residual_dropout > 0:
+                out[f"drop_res{i}a"] = ((B, L, E), cfg.residual_dropout)
+                out[f"drop_res{i}b"] = ((B, L, E), cfg.residual_dropout)
+        return out
+
+    def draw_masks(self, B: int, generator=None):
+        return OrderedDict((k, (torch.rand(shape, generator=generator) >= pr).float() / (1.0 - pr))
+                           for k, (shape, pr) in self.mask_shapes(B).items())
+
     # ---- model
-    def forward(self, states, actions, returns, costs_return, time_steps, mask):
+    def forward(self, states, actions, returns, costs_return, time_steps, mask, drop=None):
         p, cfg = self.params, self.cfg
+        drop = drop or {}
         B, T = states.shape[:2]
         E, H, d = cfg.embedding_dim, self.H, self.d
         te = p["timestep_emb.weight"][time_steps]                                   # cdt.py:180
@@ -145,6 +166,8 @@ class CDTOracle:
         x = torch.stack([r, c, s, a_], dim=1).permute(0, 2, 1, 3).reshape(B, 4 * T, E)                  # :198-200
         pad = torch.stack([~mask.bool()] * 4, dim=1).permute(0, 2, 1).reshape(B, -1)                     # :203-205
         x = F.layer_norm(x, (E,), p["emb_norm.weight"], p["emb_norm.bias"])
+        if "drop_emb" in drop:
+            x = x * drop["drop_emb"]                                                                       # cdt.py:222
         L = 4 * T
         causal = ~torch.tril(torch.ones(L, L)).bool()                                                    # net.py:417-418
         for i in range(cfg.num_layers):
@@ -154,11 +177,20 @@ class CDTOracle:
             q, k, v = (t.reshape(B, L, H, d).transpose(1, 2) for t in qkv.chunk(3, dim=-1))
             sc = (q @ k.transpose(-1, -2)) / math.sqrt(d)
             sc = sc.masked_fill(causal[None, None] | pad[:, None, None, :], float("-inf"))
-            o_ = (torch.softmax(sc, dim=-1) @ v).transpose(1, 2).reshape(B, L, E)
-            x = x + F.linear(o_, p[pre + "attention.out_proj.weight"], p[pre + "attention.out_proj.bias"])
+            pw = torch.softmax(sc, dim=-1)
+            if f"drop_attn{i}" in drop:
+                pw = pw * drop[f"drop_attn{i}"]
+            o_ = (pw @ v).transpose(1, 2).reshape(B, L, E)
+            ao = F.linear(o_, p[pre + "attention.out_proj.weight"], p[pre + "attention.out_proj.bias"])
+            if f"drop_res{i}a" in drop:
+                ao = ao * drop[f"drop_res{i}a"]
+            x = x + ao
             h2 = F.layer_norm(x, (E,), p[pre + "norm2.weight"], p[pre + "norm2.bias"])
             m = F.gelu(F.linear(h2, p[pre + "mlp.0.weight"], p[pre + "mlp.0.bias"]))
-            x = x + F.linear(m, p[pre + "mlp.2.weight"], p[pre + "mlp.2.bias"])
+            mo = F.linear(m, p[pre + "mlp.2.weight"], p[pre + "mlp.2.bias"])
+            if f"drop_res{i}b" in drop:
+                mo = mo * drop[f"drop_res{i}b"]
+            x = x + mo
         out = F.layer_norm(x, (E,), p["out_norm.weight"], p["out_norm.bias"]).reshape(B, T, 4, E)
         state_feat, action_feat = out[:, :, 2], out[:, :, 3]                                             # :239-240
         mu = F.linear(state_feat, p["action_head.mu.weight"], p["action_head.mu.bias"])
@@ -170,7 +202,16 @@ class CDTOracle:
     def step(self, states, actions, returns, costs_return, time_steps, mask, episode_cost, costs, noise=None):
         p, cfg = self.params, self.cfg
         C.require_grad(p, self.names)
-        mu, log_std, cost_preds, state_preds = self.forward(states, actions, returns, costs_return, time_steps, mask)
+        drop = OrderedDict()
+        shapes = self.mask_shapes(states.shape[0])
+        if shapes:
+            given = noise or {}
+            fresh = self.draw_masks(states.shape[0])
+            for k, (shape, _) in shapes.items():
+                drop[k] = torch.as_tensor(given[k]).reshape(shape).float() if k in given else fresh[k]
+        self.last_noise = dict(drop)
+        mu, log_std, cost_preds, state_preds = self.forward(states, actions, returns, costs_return, time_steps, mask,
+                                                            drop)
         std = log_std.exp()
         valid = mask > 0
         logp = -((actions - mu) ** 2) / (2 * std ** 2) - log_std - math.log(math.sqrt(2 * math.pi))

@@ -196,13 +196,54 @@ def make_seq_batch(rng, B, T, o, a):
 CDT_KEYS = ("states", "actions", "returns", "costs_return", "time_steps", "mask", "episode_cost", "costs")
 
 
+class DropReplay:
+    """Run the UNMODIFIED reference modules on prescribed dropout multipliers: torch.nn.functional.dropout (what
+    nn.Dropout calls) and torch.nn.functional.scaled_dot_product_attention (what nn.MultiheadAttention's training path
+    calls with dropout_p) are swapped for versions that multiply by the next tensor of the queue.  The reference's
+    call order per step is emb_drop (cdt.py:222), then per block: attention weights, self.drop(attention_out),
+    the mlp's trailing nn.Dropout (net.py:428-440)."""
+
+    def __init__(self, masks):
+        self.q = list(masks)
+
+    def __enter__(self):
+        import math
+        import torch.nn.functional as F
+        self.F, self.old = F, (F.dropout, F.scaled_dot_product_attention)
+        q = self.q
+
+        def dropout(input, p=0.5, training=True, inplace=False):
+            if not training or p == 0.0:
+                return input
+            m = q.pop(0)
+            assert m.shape == input.shape, (m.shape, input.shape)
+            return input * m
+
+        def sdpa(query, key, value, attn_mask=None, dropout_p=0.0, is_causal=False, scale=None, **kw):
+            sc = (query @ key.transpose(-1, -2)) * (scale if scale is not None else 1.0 / math.sqrt(query.shape[-1]))
+            if attn_mask is not None:
+                sc = sc.masked_fill(~attn_mask, float("-inf")) if attn_mask.dtype == torch.bool else sc + attn_mask
+            pw = torch.softmax(sc, dim=-1)
+            if dropout_p > 0.0:
+                pw = pw * q.pop(0).reshape(pw.shape)
+            return pw @ value
+
+        F.dropout, F.scaled_dot_product_attention = dropout, sdpa
+        return self
+
+    def __exit__(self, *a):
+        self.F.dropout, self.F.scaled_dot_product_attention = self.old
+        assert not self.q, f"{len(self.q)} dropout tensors were not consumed by the reference"
+
+
 def run_cdt_case(osrl, name, cfg, B, steps, full):
     from oracle import cdt as ocdt
     torch.manual_seed(0)
     ref = osrl.algorithms.CDT(state_dim=cfg.state_dim, action_dim=cfg.action_dim, max_action=cfg.max_action,
                               seq_len=cfg.seq_len, episode_len=cfg.episode_len, embedding_dim=cfg.embedding_dim,
-                              num_layers=cfg.num_layers, num_heads=cfg.num_heads, attention_dropout=0.0,
-                              residual_dropout=0.0, embedding_dropout=0.0, time_emb=True, use_rew=True, use_cost=True,
+                              num_layers=cfg.num_layers, num_heads=cfg.num_heads,
+                              attention_dropout=cfg.attention_dropout, residual_dropout=cfg.residual_dropout,
+                              embedding_dropout=cfg.embedding_dropout, time_emb=True, use_rew=True, use_cost=True,
                               cost_transform=True, stochastic=True, init_temperature=cfg.init_temperature,
                               target_entropy=-cfg.action_dim)
     trainer = osrl.algorithms.CDTTrainer(ref, None, logger=ref_shim.NullLogger(), learning_rate=cfg.learning_rate,
@@ -218,15 +259,20 @@ def run_cdt_case(osrl, name, cfg, B, steps, full):
     init = {k: v.clone() for k, v in orc.params.items()}
     rng = np.random.default_rng(77)
     batches = [make_seq_batch(rng, B, cfg.seq_len, cfg.state_dim, cfg.action_dim) for _ in range(steps)]
-    ref_stats, orc_stats = [], []
+    ref_stats, orc_stats, all_masks = [], [], []
+    mgen = torch.Generator().manual_seed(4242)
+    ref.train()
     for b in batches:
+        masks = orc.draw_masks(B, generator=mgen)       # empty when every dropout is 0
+        all_masks.append(masks)
         n0 = len(trainer.logger.rows)
-        trainer.train_one_step(*[torch.from_numpy(b[k]) for k in CDT_KEYS])
+        with DropReplay(masks.values()):
+            trainer.train_one_step(*[torch.from_numpy(b[k]) for k in CDT_KEYS])
         row = {}
         for r in trainer.logger.rows[n0:]:
             row.update(r)
         ref_stats.append(row)
-        orc_stats.append(orc.step(*[torch.from_numpy(b[k]) for k in CDT_KEYS]))
+        orc_stats.append(orc.step(*[torch.from_numpy(b[k]) for k in CDT_KEYS], noise=masks))
     worst = 0.0
     for s, (r, o) in enumerate(zip(ref_stats, orc_stats)):
         assert set(r) == set(o), set(r) ^ set(o)
@@ -257,6 +303,8 @@ def run_cdt_case(osrl, name, cfg, B, steps, full):
         for s, b in enumerate(batches):
             for k, v in b.items():
                 out[f"batch{s}/{k}"] = v
+            for k, v in all_masks[s].items():          # keep bits; the multiplier is bit / (1 - p)
+                out[f"drop{s}/{k}"] = np.packbits((v.numpy() > 0).reshape(-1))
         out["log_temperature"] = np.array(float(ref.log_temperature))
     else:
         out["init_checksum"] = np.array([checksum(v) for v in init.values()])
@@ -271,6 +319,11 @@ def main_cdt():
                                                    num_layers=2, num_heads=4, learning_rate=1e-3, lr_warmup_steps=4), 8, 3, True)
     run_cdt_case(osrl, "cdt_full", ocdt.CDTConfig(17, 6, 1.0, seq_len=10, episode_len=1000, embedding_dim=128,
                                                   num_layers=3, num_heads=8), 64, 2, False)
+    # the reference's configured dropouts (cdt_configs.py: 0.1 at all three sites), replayed multipliers
+    run_cdt_case(osrl, "cdt_drop_small", ocdt.CDTConfig(5, 3, 1.0, seq_len=10, episode_len=1000, embedding_dim=32,
+                                                        num_layers=2, num_heads=4, learning_rate=1e-3, lr_warmup_steps=4,
+                                                        attention_dropout=0.1, residual_dropout=0.1,
+                                                        embedding_dropout=0.1), 8, 3, True)
 
 
 if __name__ == "__main__" and "cdt" in sys.argv[1:]:

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, os.environ.get("OSRL_B200_LIBNAME", "libosrl_b200.so"))
 
 OSRL_MAX_HIDDEN = 4
-OSRL_MAX_NOISE = 8
+OSRL_MAX_NOISE = 32
 ALGO = {"bc": 0, "bcql": 1, "cpq": 2, "bearl": 3, "cdt": 4}
 
 
@@ -89,7 +89,7 @@ SYMBOLS = [
     ("osrl_buffer_upload", C.c_int, [C.c_void_p, C.POINTER(DatasetView)]),
     ("osrl_gather", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(Batch), C.c_void_p]),
     ("osrl_step", C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Noise), C.c_void_p]),
-    ("osrl_step_seq", C.c_int, [C.c_void_p, C.POINTER(SeqBatch), C.c_void_p]),
+    ("osrl_step_seq", C.c_int, [C.c_void_p, C.POINTER(SeqBatch), C.POINTER(Noise), C.c_void_p]),
     ("osrl_seq_buffer_upload", C.c_int, [C.c_void_p, C.POINTER(SeqDatasetView)]),
     ("osrl_seq_gather", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(SeqBatch), C.c_void_p]),
     ("osrl_seq_alias_table", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),

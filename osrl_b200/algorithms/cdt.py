@@ -50,8 +50,8 @@ class CDT(EngineModel):
                 mul_cost_feat or cat_cost_feat or cost_prefix or action_head_layers != 1:
             raise NotImplementedError("osrl_b200 CDT covers the configured reference mode (time_emb, use_rew, use_cost, "
                                       "cost_transform, stochastic, action_head_layers=1, no prefix / cost features)")
-        if attention_dropout or residual_dropout or embedding_dropout:
-            raise NotImplementedError("CDT dropout > 0 is not built yet; pass 0 for the three dropouts")
+        self.attention_dropout, self.residual_dropout = float(attention_dropout), float(residual_dropout)
+        self.embedding_dropout = float(embedding_dropout)
         self.seq_len, self.embedding_dim, self.state_dim, self.action_dim = seq_len, embedding_dim, state_dim, action_dim
         self.episode_len, self.max_action, self.stochastic, self.device = episode_len, max_action, stochastic, device
         self.num_layers, self.num_heads = num_layers, num_heads
@@ -89,7 +89,9 @@ class CDT(EngineModel):
         return dict(state_dim=self.state_dim, action_dim=self.action_dim, max_action=self.max_action,
                     seq_len=self.seq_len, episode_len=self.episode_len, embedding_dim=self.embedding_dim,
                     num_layers=self.num_layers, num_heads=self.num_heads, use_rew=1, use_cost=1, cost_transform=1,
-                    stochastic=1, init_temperature=self.init_temperature, target_entropy=self.target_entropy)
+                    stochastic=1, init_temperature=self.init_temperature, target_entropy=self.target_entropy,
+                    attention_dropout=self.attention_dropout, residual_dropout=self.residual_dropout,
+                    embedding_dropout=self.embedding_dropout)
 
 
 class CDTTrainer(EngineTrainer):

@@ -6,6 +6,7 @@
 // cdt_kernels.cuh.  Residual-stream gradients are accumulated in place in `dres`.
 #include "cdt_kernels.cuh"
 #include "engine.h"
+#include <map>
 
 namespace osrl {
 
@@ -66,6 +67,18 @@ void build_cdt(Engine& e) {
   else if (D == 16) set_attn_attr<16>(smem_bwd);
   else set_attn_attr<32>(smem_bwd);
 
+  // dropout multipliers (noise slots "drop_*", plan.cu): null where the probability is 0
+  std::map<std::string, const float*> drop;
+  for (size_t i = 0; i < e.plan.noise.size(); ++i) drop[e.plan.noise[i].first] = e.noise_buf[i];
+  auto drop_of = [&](const std::string& name) -> const float* {
+    auto it = drop.find(name);
+    return it == drop.end() ? nullptr : it->second;
+  };
+  auto emit_mul = [&](const float* in, const float* mult, float* outp) {   // outp = in * mult over the N x E stream
+    const long long n4 = (long long)N * E / 4;
+    KOP(p, e, 12.0 * N * E, (k_mul_mask<<<1184, 256, 0, s>>>(in, mult, n4, outp)));
+  };
+
   // ---------------- forward
   float* te = e.ws((size_t)BT * E);
   float* ctg_t = e.ws(BT);
@@ -95,7 +108,15 @@ void build_cdt(Engine& e) {
   float* x = e.ws((size_t)N * E);
   float* mean0 = e.ws(N); float* rstd0 = e.ws(N);
   emit_ln_fwd(e, p, x0, L_.emb_norm_w, L_.emb_norm_b, x, mean0, rstd0, N, E);       // emb_norm (cdt.py:221)
+  const float* d_emb = drop_of("drop_emb");
+  if (d_emb) emit_mul(x, d_emb, x);                                                  // emb_drop (cdt.py:222)
   const float* mask = e.s_mask;
+  std::vector<const float*> d_attn(NL), d_ra(NL), d_rb(NL);
+  for (int i = 0; i < NL; ++i) {
+    d_attn[i] = drop_of("drop_attn" + std::to_string(i));
+    d_ra[i] = drop_of("drop_res" + std::to_string(i) + "a");
+    d_rb[i] = drop_of("drop_res" + std::to_string(i) + "b");
+  }
   for (int i = 0; i < NL; ++i) {
     const CdtLay::Blk& b = L_.blocks[i];
     Saved& s_ = sv[i];
@@ -110,17 +131,19 @@ void build_cdt(Engine& e) {
     emit_gemm(e, p, {task_fwd(s_.h1, E, N, e.P, b.in_proj, s_.qkv, 3 * E, ACT_NONE)});
     {
       const float* qkv = s_.qkv; float* att = s_.att; float* lse = s_.lse;
+      const float* pd = d_attn[i];
       Engine* ep = &e;
       p.add("k_attn_fwd", 16.0 * N * E, 4.0 * B * H * Lq * Lq * D, true, [=](cudaStream_t s) {
-        if (D == 8) k_attn_fwd<8><<<B, attn_threads, smem_fwd, s>>>(qkv, mask, Lq, H, 4, att, lse);
-        else if (D == 16) k_attn_fwd<16><<<B, attn_threads, smem_fwd, s>>>(qkv, mask, Lq, H, 4, att, lse);
-        else k_attn_fwd<32><<<B, attn_threads, smem_fwd, s>>>(qkv, mask, Lq, H, 4, att, lse);
+        if (D == 8) k_attn_fwd<8><<<B, attn_threads, smem_fwd, s>>>(qkv, mask, Lq, H, 4, att, lse, pd);
+        else if (D == 16) k_attn_fwd<16><<<B, attn_threads, smem_fwd, s>>>(qkv, mask, Lq, H, 4, att, lse, pd);
+        else k_attn_fwd<32><<<B, attn_threads, smem_fwd, s>>>(qkv, mask, Lq, H, 4, att, lse, pd);
         ep->launches++;
       });
     }
-    {  // x_mid = x_in + out_proj(att)            (net.py:438-439, dropout 0)
+    {  // x_mid = x_in + drop(out_proj(att))      (net.py:438-439)
       GemmTask t = task_fwd(s_.att, E, N, e.P, b.out_proj, s_.x_mid, E, ACT_NONE);
       t.resid = s_.x_in; t.ldr = E;
+      t.mmask = d_ra[i]; t.ldmm = E;
       emit_gemm(e, p, {t});
     }
     emit_ln_fwd(e, p, s_.x_mid, b.n2w, b.n2b, s_.h2, s_.m2, s_.r2, N, E);
@@ -129,9 +152,10 @@ void build_cdt(Engine& e) {
       t.aux = s_.z; t.ldaux = 4 * E;
       emit_gemm(e, p, {t});
     }
-    {  // x_out = x_mid + fc2(g)                  (net.py:440)
+    {  // x_out = x_mid + drop(fc2(g))            (net.py:440, mlp's trailing nn.Dropout :414)
       GemmTask t = task_fwd(s_.g, 4 * E, N, e.P, b.fc2, x_out, E, ACT_NONE);
       t.resid = s_.x_mid; t.ldr = E;
+      t.mmask = d_rb[i]; t.ldmm = E;
       emit_gemm(e, p, {t});
     }
     x = x_out;
@@ -175,25 +199,31 @@ void build_cdt(Engine& e) {
   float* dh = e.ws((size_t)N * E);       // d LayerNorm output
   float* datt = e.ws((size_t)N * E);
   float* dqkv = e.ws((size_t)N * 3 * E);
+  float* ddrop = (c.residual_dropout > 0.f) ? e.ws((size_t)N * E) : nullptr;   // dres * dropout multiplier
   for (int i = NL - 1; i >= 0; --i) {
     const CdtLay::Blk& b = L_.blocks[i];
     const Saved& s_ = sv[i];
-    // MLP branch: x_out = x_mid + fc2(GELU(fc1(LN2(x_mid))))
-    emit_gemm(e, p, {task_wgrad(dres, E, s_.g, 4 * E, N, e.G, b.fc2),
-                     task_dgrad(dres, E, N, e.P, b.fc2, dg, 4 * E, s_.z, 4 * E, ACT_GELU)});
+    // MLP branch: x_out = x_mid + drop(fc2(GELU(fc1(LN2(x_mid)))))
+    const float* dy2 = dres;
+    if (d_rb[i]) { emit_mul(dres, d_rb[i], ddrop); dy2 = ddrop; }
+    emit_gemm(e, p, {task_wgrad(dy2, E, s_.g, 4 * E, N, e.G, b.fc2),
+                     task_dgrad(dy2, E, N, e.P, b.fc2, dg, 4 * E, s_.z, 4 * E, ACT_GELU)});
     emit_gemm(e, p, {task_wgrad(dg, 4 * E, s_.h2, E, N, e.G, b.fc1),
                      task_dgrad(dg, 4 * E, N, e.P, b.fc1, dh, E, nullptr, 0, 0)});
     emit_ln_bwd(e, p, dh, s_.x_mid, s_.m2, s_.r2, b.n2w, b.n2b, dres, 1, N, E);
-    // attention branch: x_mid = x_in + out_proj(attn(LN1(x_in)))
-    emit_gemm(e, p, {task_wgrad(dres, E, s_.att, E, N, e.G, b.out_proj),
-                     task_dgrad(dres, E, N, e.P, b.out_proj, datt, E, nullptr, 0, 0)});
+    // attention branch: x_mid = x_in + drop(out_proj(attn(LN1(x_in))))
+    const float* dy1 = dres;
+    if (d_ra[i]) { emit_mul(dres, d_ra[i], ddrop); dy1 = ddrop; }
+    emit_gemm(e, p, {task_wgrad(dy1, E, s_.att, E, N, e.G, b.out_proj),
+                     task_dgrad(dy1, E, N, e.P, b.out_proj, datt, E, nullptr, 0, 0)});
     {
       const float *qkv = s_.qkv, *att = s_.att, *lse = s_.lse;
+      const float* pd = d_attn[i];
       Engine* ep = &e;
       p.add("k_attn_bwd", 36.0 * N * E, 10.0 * B * H * Lq * Lq * D, true, [=](cudaStream_t s) {
-        if (D == 8) k_attn_bwd<8><<<B, attn_threads, smem_bwd, s>>>(qkv, mask, Lq, H, 4, att, datt, lse, dqkv);
-        else if (D == 16) k_attn_bwd<16><<<B, attn_threads, smem_bwd, s>>>(qkv, mask, Lq, H, 4, att, datt, lse, dqkv);
-        else k_attn_bwd<32><<<B, attn_threads, smem_bwd, s>>>(qkv, mask, Lq, H, 4, att, datt, lse, dqkv);
+        if (D == 8) k_attn_bwd<8><<<B, attn_threads, smem_bwd, s>>>(qkv, mask, Lq, H, 4, att, datt, lse, dqkv, pd);
+        else if (D == 16) k_attn_bwd<16><<<B, attn_threads, smem_bwd, s>>>(qkv, mask, Lq, H, 4, att, datt, lse, dqkv, pd);
+        else k_attn_bwd<32><<<B, attn_threads, smem_bwd, s>>>(qkv, mask, Lq, H, 4, att, datt, lse, dqkv, pd);
         ep->launches++;
       });
     }
@@ -202,6 +232,7 @@ void build_cdt(Engine& e) {
     emit_ln_bwd(e, p, dh, s_.x_in, s_.m1, s_.r1, b.n1w, b.n1b, dres, 1, N, E);
   }
   float* dx0 = e.ws((size_t)N * E);
+  if (d_emb) emit_mul(dres, d_emb, dres);   // back through emb_drop
   emit_ln_bwd(e, p, dres, x0, mean0, rstd0, L_.emb_norm_w, L_.emb_norm_b, dx0, 0, N, E);
   // embedding gradients: token tau of every step is row (bt*4 + tau) -> leading dimension 4E
   emit_gemm(e, p, {task_wgrad(dx0 + 0 * E, 4 * E, e.s_returns, 1, BT, e.G, L_.return_emb),

@@ -154,13 +154,24 @@ static __global__ void k_ln_param_reduce(const float* __restrict__ part_dg, cons
   dg[c] = a; db[c] = b;
 }
 
+// ------------------------------------------------------------------ dropout: out = in * multiplier (in place allowed)
+static __global__ void k_mul_mask(const float* in, const float* __restrict__ mult, long long n4, float* out) {
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(in)[q], m = reinterpret_cast<const float4*>(mult)[q];
+    reinterpret_cast<float4*>(out)[q] = make_float4(a.x * m.x, a.y * m.y, a.z * m.z, a.w * m.w);
+  }
+}
+
 // ------------------------------------------------------------------ attention (nn.MultiheadAttention, net.py:406-441)
 // qkv [B, L, 3E] (q | k | v, head h at columns h*D..), key j is attendable by query i iff j <= i and
 // the step of token j is valid (key_padding_mask = ~mask repeated over the 4 tokens of a step, cdt.py:203-205).
 // One CTA per batch element, one thread per (head, query/key row).
 template <int D>
+// pdrop (optional) [B, H, L, L]: dropout multipliers of the attention weights (nn.MultiheadAttention dropout):
+// O = (softmax(S) * pdrop) V -- the normaliser is the un-dropped sum, so lse is unchanged.
 static __global__ void k_attn_fwd(const float* __restrict__ qkv, const float* __restrict__ mask, int L, int H,
-                                  int tok_per_step, float* __restrict__ out, float* __restrict__ lse) {
+                                  int tok_per_step, float* __restrict__ out, float* __restrict__ lse,
+                                  const float* __restrict__ pdrop) {
   extern __shared__ float sm[];
   const int E = H * D, b = blockIdx.x, T = L / tok_per_step;
   float* Ks = sm;              // [L][E]
@@ -178,6 +189,7 @@ static __global__ void k_attn_fwd(const float* __restrict__ qkv, const float* __
 #pragma unroll
   for (int c = 0; c < D; ++c) { q[c] = base[(size_t)i * 3 * E + h * D + c]; acc[c] = 0.f; }
   const float scale = rsqrtf((float)D);
+  const float* __restrict__ drow = pdrop ? pdrop + (((size_t)b * H + h) * L + i) * L : nullptr;
   float m = -INFINITY, l = 0.f;
   for (int j = 0; j <= i; ++j) {
     if (mask[(size_t)b * T + j / tok_per_step] <= 0.f) continue;
@@ -188,8 +200,9 @@ static __global__ void k_attn_fwd(const float* __restrict__ qkv, const float* __
     const float mn = fmaxf(m, s);
     const float corr = expf(m - mn), p = expf(s - mn);
     l = l * corr + p;
+    const float pv = drow ? p * drow[j] : p;
 #pragma unroll
-    for (int c = 0; c < D; ++c) acc[c] = acc[c] * corr + p * Vs[j * E + h * D + c];
+    for (int c = 0; c < D; ++c) acc[c] = acc[c] * corr + pv * Vs[j * E + h * D + c];
     m = mn;
   }
   const float inv = 1.f / l;
@@ -201,7 +214,8 @@ static __global__ void k_attn_fwd(const float* __restrict__ qkv, const float* __
 template <int D>
 static __global__ void k_attn_bwd(const float* __restrict__ qkv, const float* __restrict__ mask, int L, int H,
                                   int tok_per_step, const float* __restrict__ out, const float* __restrict__ dout,
-                                  const float* __restrict__ lse, float* __restrict__ dqkv) {
+                                  const float* __restrict__ lse, float* __restrict__ dqkv,
+                                  const float* __restrict__ pdrop) {
   extern __shared__ float sm[];
   const int E = H * D, b = blockIdx.x, T = L / tok_per_step;
   float* Qs = sm;
@@ -237,6 +251,7 @@ static __global__ void k_attn_bwd(const float* __restrict__ qkv, const float* __
 #pragma unroll
     for (int c = 0; c < D; ++c) dq[c] = 0.f;
     const float li = Ls[h * L + i], di = Ds[h * L + i];
+    const float* __restrict__ dmat = pdrop ? pdrop + ((size_t)b * H + h) * L * L : nullptr;   // [L][L] of this head
     for (int j = 0; j <= i; ++j) {
       if (mask[(size_t)b * T + j / tok_per_step] <= 0.f) continue;
       float s = 0.f, dp = 0.f;
@@ -246,6 +261,7 @@ static __global__ void k_attn_bwd(const float* __restrict__ qkv, const float* __
         dp = fmaf(dOs[i * E + h * D + c], Vs[j * E + h * D + c], dp);
       }
       const float p = expf(s * scale - li);
+      if (dmat) dp *= dmat[i * L + j];   // d softmax = (dO V^T) * dropout multiplier; rowsum(dP * P) is still dO.O
       const float ds = p * (dp - di) * scale;
 #pragma unroll
       for (int c = 0; c < D; ++c) dq[c] = fmaf(ds, Ks[j * E + h * D + c], dq[c]);
@@ -266,11 +282,13 @@ static __global__ void k_attn_bwd(const float* __restrict__ qkv, const float* __
           dp = fmaf(dOs[r * E + h * D + c], Vs[j * E + h * D + c], dp);
         }
         const float p = expf(s * scale - Ls[h * L + r]);
-        const float ds = p * (dp - Ds[h * L + r]) * scale;
+        const float mrj = dmat ? dmat[r * L + j] : 1.f;
+        const float ds = p * (dp * mrj - Ds[h * L + r]) * scale;
+        const float pv = p * mrj;
 #pragma unroll
         for (int c = 0; c < D; ++c) {
           dk[c] = fmaf(ds, Qs[r * E + h * D + c], dk[c]);
-          dv[c] = fmaf(p, dOs[r * E + h * D + c], dv[c]);
+          dv[c] = fmaf(pv, dOs[r * E + h * D + c], dv[c]);
         }
       }
     }

@@ -132,7 +132,7 @@ static bool split_packs(const std::vector<GemmTask>& tasks, F&& emit_one) {
 static int thin_kind(const GemmTask& t) {
   static const bool on = [] { const char* v = getenv("OSRL_THIN"); return !(v && v[0] == '0'); }();
   if (!on || gemm_mode() == "ffma") return THIN_NONE;
-  if (t.act == ACT_GELU || t.dact == ACT_GELU) return THIN_NONE;
+  if (t.act == ACT_GELU || t.dact == ACT_GELU || t.mmask) return THIN_NONE;
   if (t.K <= 16) return t.colsum ? THIN_NONE : THIN_K;
   if (!t.a_kc && !t.b_kc) {   // batch reduction: 16 k-groups per CTA walk K serially, long K stays on split-K tiles
     if (t.K > 4096) return THIN_NONE;
@@ -200,7 +200,7 @@ static void emit_tc5(Engine& e, Program& p, std::vector<GemmTask> tasks, bool ap
     tot += tm * tn;
     bytes += 4.0 * ((double)t.M * t.K + (double)t.K * t.N + (double)t.M * t.N);
     flops += 2.0 * (double)t.M * t.N * t.K;
-    full = full || t.act == ACT_GELU || t.dact == ACT_GELU;
+    full = full || t.act == ACT_GELU || t.dact == ACT_GELU || t.mmask != nullptr;
   }
   const TaskPack d = make_pack(tasks);
   const int nt = (int)tasks.size(), tiles = tot;
@@ -347,7 +347,7 @@ static void emit_tiled(Engine& e, Program& p, std::vector<GemmTask> tasks) {
   for (auto& t : tasks) kmax = std::max(kmax, t.ksplit > 1 ? t.klen : t.K);
   const bool kgroups = cfg > 0 && kmax <= 1024 && tiles <= 2 * 148;
   bool full = false;
-  for (auto& t : tasks) full = full || t.ksplit > 1 || t.act == ACT_GELU || t.dact == ACT_GELU;
+  for (auto& t : tasks) full = full || t.ksplit > 1 || t.act == ACT_GELU || t.dact == ACT_GELU || t.mmask != nullptr;
   p.add(mma ? mnames[cfg] : names[cfg], bytes, flops, true, [=](cudaStream_t s) {
 #define OSRL_DISPATCH(FULL_)                                                      \
     if (mma) {                                                                    \
@@ -512,6 +512,13 @@ void ens_bwd(std::vector<Stage>& st, const EnsLay& l, const float* W, float* Gse
 }
 
 // ------------------------------------------------------------------ engine life cycle
+// dropout probability of a noise slot ("drop_*" slots hold multipliers, see osrl_noise in the header); 0 = normals
+static float slot_drop_p(const osrl_config& c, const std::string& name) {
+  if (name.rfind("drop_emb", 0) == 0) return c.embedding_dropout;
+  if (name.rfind("drop_attn", 0) == 0) return c.attention_dropout;
+  if (name.rfind("drop_res", 0) == 0) return c.residual_dropout;
+  return 0.f;
+}
 static void drop_sampled_graphs(Engine& e) {   // they bake the dataset pointers
   for (cudaGraphExec_t* g : {&e.g_sampled, &e.g_pro, &e.g_mid, &e.g_last})
     if (*g) { cudaGraphExecDestroy(*g); *g = nullptr; }
@@ -542,7 +549,7 @@ static void build_pipelined(Engine& e, const std::vector<int>& vae_slots) {
   std::vector<NoiseSlot> sv, sr;
   for (int i = 0; i < (int)e.noise_buf.size(); ++i) {
     const bool is_vae = std::find(vae_slots.begin(), vae_slots.end(), i) != vae_slots.end();
-    NoiseSlot s{e.noise_buf[i], (long long)e.plan.noise[i].second, i, 1};
+    NoiseSlot s{e.noise_buf[i], (long long)e.plan.noise[i].second, i, 1, slot_drop_p(c, e.plan.noise[i].first)};
     NoiseSlot off = s;
     off.enabled = 0;
     sv.push_back(is_vae ? s : off);
@@ -621,7 +628,7 @@ static Engine* create(const osrl_config& cfg, int device) {
     for (auto& ns : e->plan.noise) {
       float* buf = e->ws((size_t)ns.second);
       e->noise_buf.push_back(buf);
-      slots.push_back({buf, (long long)ns.second, si++, 1});
+      slots.push_back({buf, (long long)ns.second, si++, 1, slot_drop_p(cfg, ns.first)});
     }
     e->d_slots_all = e->upload(slots);
     e->d_slots_dyn = e->upload(slots);
@@ -665,6 +672,11 @@ static void sample_front(Engine& e, cudaStream_t s) {
   if (c.algo == OSRL_ALGO_CDT) {
     launch_seq_gather(e, s, nullptr, nullptr, e.B, e.s_states, e.s_actions, e.s_returns, e.s_ctg, e.s_ts, e.s_mask,
                       e.s_costs, e.s_traj, e.s_start);
+    if (!e.noise_buf.empty()) {   // dropout multipliers
+      k_noise_fill<<<dim3(64, (unsigned)e.noise_buf.size()), 256, 0, s>>>(e.d_slots_all, (int)e.noise_buf.size(), c.seed,
+                                                                           &e.ds->step, (uint32_t)e.rank);
+      e.launches++;
+    }
     return;
   }
   const int warps_per_block = 8;
@@ -800,6 +812,33 @@ static void build_alias(const std::vector<double>& p, std::vector<float>& prob, 
 
 // ====================================================================== C ABI
 using namespace osrl;
+
+// noise of an explicit-batch step: provided slots are copied in, the others generated on the device
+static void stage_noise_impl(Engine& e, const osrl_noise* nz, cudaStream_t s) {
+  const int ns = (int)e.noise_buf.size();
+  if (!ns) return;
+  int provided = 0;
+  for (int i = 0; i < ns; ++i) {
+    const float* src = nz ? nz->slot[i] : nullptr;
+    if (!src) continue;
+    ++provided;
+    OSRL_CUDA(cudaMemcpyAsync(e.noise_buf[i], src, (size_t)e.plan.noise[i].second * sizeof(float),
+                              nz->on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+  }
+  if (provided == ns) return;
+  const NoiseSlot* slots = e.d_slots_all;  // every slot generated on the device
+  if (provided > 0) {                      // mixed: only the missing slots
+    std::vector<NoiseSlot> dyn;
+    for (int i = 0; i < ns; ++i)
+      dyn.push_back({e.noise_buf[i], (long long)e.plan.noise[i].second, i, (nz && nz->slot[i]) ? 0 : 1,
+                     slot_drop_p(e.plan.cfg, e.plan.noise[i].first)});
+    OSRL_CUDA(cudaMemcpyAsync(e.d_slots_dyn, dyn.data(), dyn.size() * sizeof(NoiseSlot), cudaMemcpyHostToDevice, s));
+    OSRL_CUDA(cudaStreamSynchronize(s));
+    slots = e.d_slots_dyn;
+  }
+  k_noise_fill<<<dim3(64, (unsigned)ns), 256, 0, s>>>(slots, ns, e.plan.cfg.seed, &e.ds->step, (uint32_t)e.rank);
+  e.launches++;
+}
 
 #define OSRL_TRY try {
 #define OSRL_CATCH                                   \
@@ -1092,37 +1131,14 @@ int osrl_step(osrl_engine* h, const osrl_batch* b, const osrl_noise* nz, void* s
     OSRL_CUDA(cudaMemcpyAsync(e.b_cost, b->costs, (size_t)B * sizeof(float), kind, s));
     OSRL_CUDA(cudaMemcpyAsync(e.b_done, b->done, (size_t)B * sizeof(float), kind, s));
   }
-  const int ns = (int)e.noise_buf.size();
-  if (ns) {
-    int provided = 0;
-    for (int i = 0; i < ns; ++i) {
-      const float* src = nz ? nz->slot[i] : nullptr;
-      if (!src) continue;
-      ++provided;
-      OSRL_CUDA(cudaMemcpyAsync(e.noise_buf[i], src, (size_t)e.plan.noise[i].second * sizeof(float),
-                                nz->on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
-    }
-    if (provided < ns) {
-      const NoiseSlot* slots = e.d_slots_all;  // every slot generated on the device
-      if (provided > 0) {                      // mixed: only the missing slots
-        std::vector<NoiseSlot> dyn;
-        for (int i = 0; i < ns; ++i)
-          dyn.push_back({e.noise_buf[i], (long long)e.plan.noise[i].second, i, (nz && nz->slot[i]) ? 0 : 1});
-        OSRL_CUDA(cudaMemcpyAsync(e.d_slots_dyn, dyn.data(), dyn.size() * sizeof(NoiseSlot), cudaMemcpyHostToDevice, s));
-        OSRL_CUDA(cudaStreamSynchronize(s));
-        slots = e.d_slots_dyn;
-      }
-      k_noise_fill<<<dim3(64, (unsigned)ns), 256, 0, s>>>(slots, ns, e.plan.cfg.seed, &e.ds->step, (uint32_t)e.rank);
-      e.launches++;
-    }
-  }
+  stage_noise_impl(e, nz, s);
   if (!e.g_body) e.g_body = capture(e, false);
   OSRL_CUDA(cudaGraphLaunch(e.g_body, s));
   e.launches += kernels_per_step(e, false);
   OSRL_CATCH
 }
 
-int osrl_step_seq(osrl_engine* h, const osrl_seq_batch* b, void* stream) {
+int osrl_step_seq(osrl_engine* h, const osrl_seq_batch* b, const osrl_noise* nz, void* stream) {
   OSRL_TRY
   OSRL_REQUIRE(h && b, "null argument");
   Engine& e = *h->e;
@@ -1142,6 +1158,7 @@ int osrl_step_seq(osrl_engine* h, const osrl_seq_batch* b, void* stream) {
   OSRL_CUDA(cudaMemcpyAsync(e.s_ts, b->time_steps, BT * sizeof(long long), kind, s));
   OSRL_CUDA(cudaMemcpyAsync(e.s_mask, b->mask, BT * sizeof(float), kind, s));
   OSRL_CUDA(cudaMemcpyAsync(e.s_costs, b->costs, BT * sizeof(float), kind, s));
+  stage_noise_impl(e, nz, s);
   if (!e.g_body) e.g_body = capture(e, false);
   OSRL_CUDA(cudaGraphLaunch(e.g_body, s));
   e.launches += kernels_per_step(e, false);

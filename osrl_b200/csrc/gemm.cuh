@@ -58,6 +58,8 @@ struct GemmTask {
   int pk_gstride;         // floats between the image sets of consecutive groups
   int pk_ks;              // k-slabs (of 32) per row block = ceil(pk_gcols / 32); consumer: same value
   int c_dead;             // producer hint: nothing reads C except through the packed images -> skip the fp32 store
+  const float* mmask;     // [M, ldmm] optional multiplier applied after act*scale, before the residual add (dropout)
+  int ldmm;
 };
 __host__ __device__ __forceinline__ size_t pk_offset(int row, int col, int ks_per_rb) {   // float offset in an image set
   const int rb = row >> 6, r = row & 63, ks = col >> 5, c = col & 31;
@@ -102,14 +104,14 @@ static __device__ __noinline__ float gelu_bwd(float s) {
 // once (Epi) and loads the bias of its columns once; the per-element path is then a handful of predicated ops.
 // FULL adds GELU (aux keeps the PRE-activation, the dgrad mask reads it back) and split-K accumulation.
 struct Epi {
-  float* C; float* aux; const float* resid; const float* dsrc; const float* bias;
-  int ldc, ldaux, ldr, ldd, act, clamp, dact, ksplit;
+  float* C; float* aux; const float* resid; const float* dsrc; const float* bias; const float* mmask;
+  int ldc, ldaux, ldr, ldd, ldmm, act, clamp, dact, ksplit;
   float scale, lo, hi;
 };
 __device__ __forceinline__ Epi make_epi(const GemmTask& t) {
   Epi e;
-  e.C = t.C; e.aux = t.aux; e.resid = t.resid; e.dsrc = t.dact_src; e.bias = t.bias;
-  e.ldc = t.ldc; e.ldaux = t.ldaux; e.ldr = t.ldr; e.ldd = t.ld_dact;
+  e.C = t.C; e.aux = t.aux; e.resid = t.resid; e.dsrc = t.dact_src; e.bias = t.bias; e.mmask = t.mmask;
+  e.ldc = t.ldc; e.ldaux = t.ldaux; e.ldr = t.ldr; e.ldd = t.ld_dact; e.ldmm = t.ldmm;
   e.act = t.act; e.clamp = t.clamp; e.dact = t.dact; e.ksplit = t.ksplit;
   e.scale = t.scale; e.lo = t.lo; e.hi = t.hi;
   return e;
@@ -127,6 +129,7 @@ __device__ __forceinline__ float epi_value(const Epi& e, float bias, int gi, int
     if (e.aux) e.aux[(size_t)gi * e.ldaux + gj] = v;
   }
   v *= e.scale;
+  if (FULL && e.mmask) v *= e.mmask[(size_t)gi * e.ldmm + gj];
   if (e.resid) v += e.resid[(size_t)gi * e.ldr + gj];
   if (e.clamp) v = fminf(fmaxf(v, e.lo), e.hi);
   if (e.dact) {

@@ -170,7 +170,8 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, fl
   z0 = r * c;
   z1 = r * s;
 }
-struct NoiseSlot { float* dst; long long count; int stream; int enabled; };
+// drop_p > 0: the slot holds dropout multipliers (0 with probability p, else 1/(1-p)) instead of normals
+struct NoiseSlot { float* dst; long long count; int stream; int enabled; float drop_p; };
 static __global__ void k_noise_fill(const NoiseSlot* slots, int nslots, uint64_t seed,
                                     const unsigned long long* __restrict__ step_ctr, uint32_t rank) {
   const NoiseSlot s = slots[blockIdx.y];
@@ -182,8 +183,14 @@ static __global__ void k_noise_fill(const NoiseSlot* slots, int nslots, uint64_t
                      (uint32_t)(STREAM_NOISE0 + s.stream) | ((uint32_t)(step >> 32) << 8), rank};
     philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
     float z[4];
-    box_muller(c[0], c[1], z[0], z[1]);
-    box_muller(c[2], c[3], z[2], z[3]);
+    if (s.drop_p > 0.f) {
+      const float keep = 1.f / (1.f - s.drop_p);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) z[k] = ((float)(c[k] >> 8) * (1.f / 16777216.f) < s.drop_p) ? 0.f : keep;
+    } else {
+      box_muller(c[0], c[1], z[0], z[1]);
+      box_muller(c[2], c[3], z[2], z[3]);
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       if (q * 4 + k < s.count) s.dst[q * 4 + k] = z[k];

@@ -253,8 +253,19 @@ Plan make_plan(const osrl_config& cfg) {
       OSRL_REQUIRE(T > 0 && NL > 0 && cfg.episode_len > 0, "bad CDT config");
       OSRL_REQUIRE(cfg.use_rew && cfg.use_cost && cfg.cost_transform && cfg.stochastic,
                    "this build covers the reference's configured CDT mode: use_rew, use_cost, cost_transform, stochastic");
-      OSRL_REQUIRE(cfg.attention_dropout == 0.f && cfg.residual_dropout == 0.f && cfg.embedding_dropout == 0.f,
-                   "CDT dropout > 0 is not built yet (round 2); construct the model with dropout 0");
+      for (float dp : {cfg.attention_dropout, cfg.residual_dropout, cfg.embedding_dropout})
+        OSRL_REQUIRE(dp >= 0.f && dp < 1.f, "dropout probabilities must be in [0, 1)");
+      {   // dropout multipliers travel as noise slots (replayable, see osrl_noise): one per dropout site
+        const int64_t NE = (int64_t)cfg.batch_size * 4 * T * E, NA = (int64_t)cfg.batch_size * H * 4 * T * 4 * T;
+        if (cfg.embedding_dropout > 0.f) p.noise.push_back({"drop_emb", NE});
+        for (int i = 0; i < NL; ++i) {
+          if (cfg.attention_dropout > 0.f) p.noise.push_back({"drop_attn" + std::to_string(i), NA});
+          if (cfg.residual_dropout > 0.f) {
+            p.noise.push_back({"drop_res" + std::to_string(i) + "a", NE});
+            p.noise.push_back({"drop_res" + std::to_string(i) + "b", NE});
+          }
+        }
+      }
       CdtLay& L_ = p.cdt;
       L_.E = E;
       L_.te_rows = cfg.episode_len + T;

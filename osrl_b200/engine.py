@@ -321,8 +321,9 @@ class Engine:
         check(self.lib.osrl_step(self.h, C.byref(b), nz_ptr, C.c_void_p(self._stream())))
         self._keep = keep  # pinned/device sources must outlive the async copies
 
-    def step_seq(self, batch: dict) -> None:
-        """One CDT train_one_step on a collated SequenceDataset batch (host or device tensors)."""
+    def step_seq(self, batch: dict, noise: Optional[dict] = None) -> None:
+        """One CDT train_one_step on a collated SequenceDataset batch (host or device tensors).  `noise`: dropout
+        multipliers by slot name (``noise_layout``) to replay; missing slots are drawn on the device."""
         keep, kinds = [], set()
         b = SeqBatch()
         b.rows, b.seq_len = self.batch_size, self.cfg.seq_len
@@ -339,7 +340,22 @@ class Engine:
         if len(kinds) != 1:
             raise ValueError("all batch tensors must live on the same side (host or this GPU)")
         b.on_host = kinds.pop()
-        check(self.lib.osrl_step_seq(self.h, C.byref(b), C.c_void_p(self._stream())))
+        nz = None
+        if noise is not None:
+            nz = Noise()
+            nkinds = set()
+            for i, name in enumerate(self.noise_layout):
+                if name in noise and noise[name] is not None:
+                    t, p, on_host = _as_f32(noise[name], self.device)
+                    if t.numel() != self.noise_layout[name]:
+                        raise ValueError(f"noise slot {name}: expected {self.noise_layout[name]} floats, got {t.numel()}")
+                    keep.append(t); nkinds.add(on_host)
+                    nz.slot[i] = p
+            if len(nkinds) > 1:
+                raise ValueError("all noise tensors must live on the same side")
+            nz.on_host = nkinds.pop() if nkinds else 1
+        check(self.lib.osrl_step_seq(self.h, C.byref(b), C.byref(nz) if nz is not None else None,
+                                     C.c_void_p(self._stream())))
         self._keep = keep
 
     def steps(self, k: int) -> None:

@@ -1,5 +1,6 @@
 """GPU parity of the CDT step (transformer fwd/bwd, masked losses, grad-norm clip, AdamW warm-up,
-temperature Adam) against the oracle and the reference-produced fixtures.  Dropout 0.
+temperature Adam) against the oracle and the reference-produced fixtures.  Dropout: the multipliers are replayed
+(fixture -> engine, or engine -> oracle), SURVEY.md 7.5-1.
 Tolerance policy: tests/test_gpu_parity.py module docstring."""
 import copy
 import json
@@ -132,6 +133,86 @@ def test_cdt_against_live_oracle(lib_built, case, gemm):
                 assert err <= max(2 * RTOL, 10 * cond), f"{case} param delta {k}: {err:.2e} (cond {cond:.1e})"
     assert strict >= 0.85 * total, (strict, total)
     assert abs(eng.scalars()["log_temperature"] - float(orc.log_temperature)) < 1e-6
+    eng.close()
+
+
+def _golden_masks(z, meta, s, orc):
+    """dropout multipliers of step s from the fixture's keep bits (make_golden.py)"""
+    out = {}
+    for k, (shape, pr) in orc.mask_shapes(meta["B"]).items():
+        bits = np.unpackbits(z[f"drop{s}/{k}"])[:int(np.prod(shape))].astype(np.float32)
+        out[k] = torch.from_numpy(bits / np.float32(1.0 - pr)).reshape(shape)
+    return out
+
+
+def test_cdt_dropout_golden(lib_built):
+    """cdt_drop_small.npz: the UNMODIFIED reference stepped on prescribed dropout multipliers (0.1 at the embedding,
+    attention-weight and both residual sites, as in cdt_configs.py); the engine replays the same multipliers."""
+    z, meta = load_golden("cdt_drop_small")
+    B, steps = meta["B"], meta["steps"]
+    orc = ocdt.CDTOracle(_cfg(meta))
+    eng = _engine(meta, B)
+    assert list(eng.noise_layout) == list(orc.mask_shapes(B)), (list(eng.noise_layout), list(orc.mask_shapes(B)))
+    init = {k: torch.from_numpy(z["init/" + k]) for k in meta["keys"]}
+    eng.load_params(init)
+    for s in range(steps):
+        eng.step_seq({k: z[f"batch{s}/{k}"] for k in CDT_KEYS}, _golden_masks(z, meta, s, orc))
+        got = eng.stats()
+        for k, w in zip(meta["stat_keys"], z["stats"][s]):
+            assert abs(got[k] - w) <= 2e-5 * max(abs(w), 1e-3) + 1e-7, f"step {s} {k}: {got[k]} vs reference {w}"
+    got = eng.read_params()
+    for k in meta["keys"]:
+        if "in_proj_bias" in k:
+            continue
+        ref = torch.from_numpy(z["final/" + k])
+        err = float((got[k] - ref).norm())
+        bound = 1e-3 * float((ref - init[k]).norm()) + 4e-7 * float(ref.norm()) + 1e-9
+        assert err <= bound, f"{k}: err {err:.3e} > {bound:.3e}"
+    eng.close()
+
+
+def test_cdt_dropout_device_masks_vs_live_oracle(lib_built):
+    """Multipliers drawn on the device (Philox): right values and rates, and the oracle stepped on the dumped
+    multipliers agrees with the engine (stats and gradients)."""
+    z, meta = load_golden("cdt_drop_small")
+    B = meta["B"]
+    cfg = _cfg(meta)
+    torch.manual_seed(0)
+    orc = ocdt.CDTOracle(cfg)
+    eng = _engine(meta, B)
+    eng.load_params(orc.params)
+    rng = np.random.default_rng(5)
+    for s in range(2):
+        b = make_seq_batch(rng, B, cfg.seq_len, cfg.state_dim, cfg.action_dim)
+        eng.step_seq(b)                      # no noise given: every slot drawn on the device
+        nz = eng.last_noise()
+        for k, (shape, pr) in orc.mask_shapes(B).items():
+            v = nz[k]
+            keep = np.float32(1.0 / (1.0 - pr))
+            assert np.all((v == 0) | (np.abs(v - keep) < 1e-6)), k
+            assert abs(float((v == 0).mean()) - pr) < 0.02, (k, float((v == 0).mean()))
+        o64 = _to_double(orc)
+        masks = {k: torch.from_numpy(v) for k, v in nz.items()}
+        s32 = orc.step(*_args(b), noise=masks)
+        with algos.precision(torch.float64):
+            s64 = o64.step(*_args(b, torch.float64), noise={k: v.double() for k, v in masks.items()})
+        got = eng.stats()
+        for k, w in s32.items():
+            scale = max(abs(s64[k]), 1e-3)
+            tol = max(RTOL, 10 * abs(w - s64[k]) / scale)
+            assert abs(got[k] - w) <= tol * scale + 1e-7, f"step {s} stat {k}: {got[k]} vs {w}"
+        G = eng.read_section("grad")
+        bad = []
+        for k, g in orc.last_grads.items():
+            g64 = o64.last_grads[k]
+            if float(g64.abs().max()) == 0.0:
+                continue
+            tol = max(2 * RTOL, 10 * maxrel(g, g64))
+            err = maxrel(G[k], g)
+            if err > tol:
+                bad.append((k, err))
+                assert err <= 2e-1, f"step {s} grad {k}: {err:.2e}"
+        assert len(bad) <= max(1, int(0.2 * len(orc.last_grads))), bad[:6]
     eng.close()
 
 
