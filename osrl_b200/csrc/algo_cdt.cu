@@ -179,8 +179,18 @@ void build_cdt(Engine& e) {
     const int warm = c.lr_warmup_steps > 0 ? c.lr_warmup_steps : 1, grp = e.plan.g_cdt;
     DevState* ds = e.ds;
     float* stat = e.stats;
-    KOP(p, e, 0.0, (k_cdt_loss<<<1, 512, 0, s>>>(mh, ah, actions, costs, states, mask, B, T, a, o, wc, wsw, tent, lr,
-                                                 warm, grp, ds, dmh, dah, stat)));
+    const int world = e.world;
+    if (world == 1) {
+      KOP(p, e, 0.0, (k_cdt_loss<<<1, 512, 0, s>>>(mh, ah, actions, costs, states, mask, B, T, a, o, wc, wsw, tent, lr,
+                                                   warm, grp, ds, dmh, dah, stat, 0, nullptr, 1)));
+    } else {   // masked means over the global batch: all-reduce the six partial sums between the two phases
+      double* sums = (double*)e.ws(16);
+      KOP(p, e, 0.0, (k_cdt_loss<<<1, 512, 0, s>>>(mh, ah, actions, costs, states, mask, B, T, a, o, wc, wsw, tent, lr,
+                                                   warm, grp, ds, dmh, dah, stat, 1, sums, world)));
+      emit_allreduce(e, p, (float*)sums, 6, /*f64=*/true);
+      KOP(p, e, 0.0, (k_cdt_loss<<<1, 512, 0, s>>>(mh, ah, actions, costs, states, mask, B, T, a, o, wc, wsw, tent, lr,
+                                                   warm, grp, ds, dmh, dah, stat, 2, sums, world)));
+    }
   }
 
   // ---------------- backward
@@ -249,6 +259,7 @@ void build_cdt(Engine& e) {
   }
   // ---------------- clip_grad_norm_ (cdt.py:399) + AdamW with warm-up (cdt.py:321-330)
   const Group& g = e.plan.groups[e.plan.g_cdt];
+  emit_allreduce(e, p, e.G + g.begin, g.end - g.begin);   // data parallel: global gradient before the global-norm clip
   float* coef = nullptr;
   if (c.clip_grad > 0.f) {
     const int nb = 296;

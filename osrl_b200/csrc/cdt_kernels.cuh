@@ -324,11 +324,15 @@ static __global__ void k_cdt_loss(const float* __restrict__ mh, const float* __r
                                   const float* __restrict__ states, const float* __restrict__ mask, int B, int T, int a,
                                   int o, float w_cost, float w_state, float target_entropy, float base_lr, int warmup,
                                   int group, DevState* ds, float* __restrict__ dmh, float* __restrict__ dah,
-                                  float* __restrict__ stat) {
+                                  float* __restrict__ stat, int phase, double* __restrict__ sums, int world) {
+  // phase 0: single GPU, everything in one launch.  Data parallel: phase 1 writes this rank's six partial sums to
+  // `sums` (all-reduced by the caller), phase 2 reads the global sums back -- the masked means (cdt.py:358-359,385)
+  // are means over the GLOBAL batch, so their denominators are global counts and the gradients need no 1/world.
   __shared__ double sh[33];
   const int BT = B * T, wa = 2 + o;
   const double HALF_LOG_2PI = 0.91893853320467274178;
   double s_valid = 0, s_lp = 0, s_ent = 0, s_nll = 0, s_corr = 0, s_sl = 0;
+  if (phase != 2)
   for (int r = threadIdx.x; r < BT; r += blockDim.x) {
     const float m = mask[r];
     if (m > 0.f) {
@@ -357,18 +361,32 @@ static __global__ void k_cdt_loss(const float* __restrict__ mh, const float* __r
       s_sl += e * (double)m;
     }
   }
-  const double n_valid = block_sum_d(s_valid, sh);
-  const double ll = block_sum_d(s_lp, sh) / (n_valid * a);
-  const double ent = block_sum_d(s_ent, sh) / (n_valid * a);
-  const double cost_loss = block_sum_d(s_nll, sh) / (double)BT;
-  const double acc = block_sum_d(s_corr, sh) / n_valid;
-  const double state_loss = (T > 1) ? block_sum_d(s_sl, sh) / ((double)B * (T - 1) * o) : 0.0;
+  double t_valid, t_lp, t_ent, t_nll, t_corr, t_sl;
+  if (phase == 2) {
+    t_valid = sums[0]; t_lp = sums[1]; t_ent = sums[2]; t_nll = sums[3]; t_corr = sums[4]; t_sl = sums[5];
+  } else {
+    t_valid = block_sum_d(s_valid, sh); t_lp = block_sum_d(s_lp, sh); t_ent = block_sum_d(s_ent, sh);
+    t_nll = block_sum_d(s_nll, sh); t_corr = block_sum_d(s_corr, sh); t_sl = block_sum_d(s_sl, sh);
+    if (phase == 1) {
+      if (threadIdx.x == 0) {
+        sums[0] = t_valid; sums[1] = t_lp; sums[2] = t_ent; sums[3] = t_nll; sums[4] = t_corr; sums[5] = t_sl;
+      }
+      return;
+    }
+  }
+  const double gBT = (double)BT * world, gB = (double)B * world;
+  const double n_valid = t_valid;
+  const double ll = t_lp / (n_valid * a);
+  const double ent = t_ent / (n_valid * a);
+  const double cost_loss = t_nll / gBT;
+  const double acc = t_corr / n_valid;
+  const double state_loss = (T > 1) ? t_sl / (gB * (T - 1) * o) : 0.0;
   const double temp = exp(ds->log_temperature);
   const double act_loss = -(ll + temp * ent);
   const float ca = (float)(1.0 / (n_valid * a));
   const float tf = (float)temp;
-  const float cc = w_cost / (float)BT;
-  const float cs = (T > 1) ? w_state * 2.f / ((float)B * (T - 1) * o) : 0.f;
+  const float cc = (float)(w_cost / gBT);
+  const float cs = (T > 1) ? (float)(w_state * 2.0 / (gB * (T - 1) * o)) : 0.f;
   for (int r = threadIdx.x; r < BT; r += blockDim.x) {
     const float m = mask[r] > 0.f ? 1.f : 0.f;
     for (int j = 0; j < a; ++j) {

@@ -439,7 +439,7 @@ static void check(int r, const char* what) {
 }
 }  // namespace nccl
 
-void emit_allreduce(Engine& e, Program& p, float* buf, int64_t count) {
+void emit_allreduce(Engine& e, Program& p, float* buf, int64_t count, bool f64) {
   if (e.world <= 1) return;
   Engine* ep = &e;
   const bool side = (&p == &e.pa);   // the pipelined VAE branch reduces on its own communicator: the two branches'
@@ -447,7 +447,8 @@ void emit_allreduce(Engine& e, Program& p, float* buf, int64_t count) {
   p.add("ncclAllReduce", 4.0 * (double)count, 0.0, false, [=](cudaStream_t s) {
     void* comm = side ? ep->comm2 : ep->comm;
     if (!comm) throw Err(OSRL_ERR_STATE, "world_size > 1 but osrl_comm_init was not called");
-    nccl::check(nccl::AllReduce(buf, buf, (size_t)count, /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm, s), "ncclAllReduce");
+    nccl::check(nccl::AllReduce(buf, buf, (size_t)count, f64 ? /*ncclFloat64*/ 8 : /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm, s),
+                "ncclAllReduce");
   });
 }
 
@@ -616,7 +617,6 @@ static Engine* create(const osrl_config& cfg, int device) {
     e->b_rew = e->ws(B); e->b_cost = e->ws(B); e->b_done = e->ws(B);
     e->b_idx = (int64_t*)e->ws((size_t)B * 2);
     if (cfg.algo == OSRL_ALGO_CDT) {
-      OSRL_REQUIRE(cfg.world_size == 1, "CDT data-parallel is not built yet");
       const size_t BT = (size_t)B * cfg.seq_len;
       e->s_states = e->ws(BT * o); e->s_actions = e->ws(BT * a); e->s_returns = e->ws(BT); e->s_ctg = e->ws(BT);
       e->s_mask = e->ws(BT); e->s_costs = e->ws(BT);

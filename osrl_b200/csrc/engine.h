@@ -205,7 +205,7 @@ void emit_gemm(Engine& e, Program& p, const std::vector<GemmTask>& tasks);
 void emit_copy(Engine& e, Program& p, const std::vector<CopyTask>& tasks);
 void emit_adam(Engine& e, Program& p, int group, int64_t begin, int64_t end, bool polyak,
                const float* clip_coef = nullptr);
-void emit_allreduce(Engine& e, Program& p, float* buf, int64_t count);
+void emit_allreduce(Engine& e, Program& p, float* buf, int64_t count, bool f64 = false);
 CopyTask copy_cols(float* dst, int ldd, int dcol0, const float* src, int lds, int scol0, int rows, int cols,
                    int row_div = 1, int row_mod = 1 << 30);
 

@@ -125,6 +125,65 @@ def run_pipelined(algo: str, steps: int = 5, Bg: int = 32):
     return bool(ok.item())
 
 
+def run_cdt(steps: int = 3, Bg: int = 16):
+    """CDT under data parallelism: the masked means are means over the GLOBAL batch (valid-token counts differ per
+    rank), so N ranks x B/N sequences must equal one oracle on the concatenated batch."""
+    from oracle import cdt as ocdt
+    from oracle.make_golden import CDT_KEYS, make_seq_batch
+    from osrl_b200 import Engine, comm_unique_id
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(dev)
+    cfg = ocdt.CDTConfig(5, 3, 1.0, seq_len=10, episode_len=1000, embedding_dim=32, num_layers=2, num_heads=4,
+                         learning_rate=1e-3, lr_warmup_steps=4)
+    torch.manual_seed(0)
+    full = ocdt.CDTOracle(cfg)
+    init = {k: v.clone() for k, v in full.params.items()}
+    B = Bg // world
+    eng = Engine("cdt", batch_size=B, device=dev, seed=3, world_size=world, rank=rank, state_dim=5, action_dim=3,
+                 max_action=1.0, seq_len=10, episode_len=1000, embedding_dim=32, num_layers=2, num_heads=4, use_rew=1,
+                 use_cost=1, cost_transform=1, stochastic=1, target_entropy=-3.0, learning_rate=1e-3, lr_warmup_steps=4,
+                 loss_cost_weight=cfg.loss_cost_weight, loss_state_weight=cfg.loss_state_weight,
+                 weight_decay=cfg.weight_decay, betas=cfg.betas, clip_grad=cfg.clip_grad,
+                 init_temperature=cfg.init_temperature)
+    eng.load_params(init)
+    ids = [comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    eng.init_comm(ids[0])
+    rng = np.random.default_rng(3)
+    worst = 0.0
+    for s in range(steps):
+        b = make_seq_batch(rng, Bg, cfg.seq_len, cfg.state_dim, cfg.action_dim)
+        args = []
+        for k in CDT_KEYS:
+            t = torch.from_numpy(np.asarray(b[k]))
+            args.append(t if k == "time_steps" else (t.float() if k != "mask" else t.double()))
+        ref_stats = full.step(*args)
+        eng.step_seq({k: shard(v, rank, world) for k, v in b.items()})
+        got = eng.stats()
+        for k, w in ref_stats.items():
+            r = abs(got[k] - w) / (2e-5 * max(abs(w), 1e-3) + 1e-7)
+            if r > 1.0 and rank == 0:
+                print(f"[cdt dp] step {s} stat {k}: engine {got[k]} oracle {w} ratio {r:.1f}", flush=True)
+            worst = max(worst, r)
+    P = eng.read_params()
+    for k, ref in full.params.items():
+        if "in_proj_bias" in k:
+            continue
+        ref = ref.detach()
+        err = float((P[k] - ref).norm())
+        bound = 1e-3 * float((ref - init[k]).norm()) + 4e-7 * float(ref.norm()) + 1e-9
+        if err > bound and rank == 0:
+            print(f"[cdt dp] param {k}: err {err:.3e} bound {bound:.3e}", flush=True)
+        worst = max(worst, err / bound)
+    ok = torch.tensor([1.0 if worst <= 1.0 else 0.0]).cuda()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(json.dumps({"algo": "cdt", "backend": "nccl", "world": world, "worst_ratio": worst, "ok": bool(ok.item())}))
+    eng.close()
+    return bool(ok.item())
+
+
 def _mp_entry(rank, world, algo, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -138,6 +197,7 @@ def _mp_entry(rank, world, algo, port, q):
 if __name__ == "__main__":   # torchrun entry (GPU): python -m torch.distributed.run ... tests/dp_worker.py bcql
     algo_list = sys.argv[1:] or ["bcql"]
     dist.init_process_group("nccl")
-    good = all(run_pipelined(a[5:]) if a.startswith("pipe:") else run(a, "nccl") for a in algo_list)
+    good = all(run_cdt() if a == "cdt" else (run_pipelined(a[5:]) if a.startswith("pipe:") else run(a, "nccl"))
+               for a in algo_list)
     dist.destroy_process_group()
     sys.exit(0 if good else 1)

@@ -13,6 +13,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_two_gpu_equivalence_nccl(lib_built):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
-           "127.0.0.1", "--master-port", "29613", os.path.join(ROOT, "tests", "dp_worker.py"), "bc", "bcql", "bearl", "pipe:bcql"]
+           "127.0.0.1", "--master-port", "29613", os.path.join(ROOT, "tests", "dp_worker.py"), "bc", "bcql", "bearl", "pipe:bcql", "cdt"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
