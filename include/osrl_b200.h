@@ -199,7 +199,12 @@ int osrl_step(osrl_engine* e, const osrl_batch* batch, const osrl_noise* noise, 
  * LR warm-up, temperature Adam -- one sequence minibatch, no host sync. */
 int osrl_step_seq(osrl_engine* e, const osrl_seq_batch* batch, const osrl_noise* noise_or_null, void* stream);
 /* k steps with minibatches drawn on the device from the resident dataset (replaces the loop
- * body train_bcql.py:142-148 including DataLoader draw and .to(device)). */
+ * body train_bcql.py:142-148 including DataLoader draw and .to(device)).  For the VAE algorithms (BCQ-Lag, CPQ,
+ * BEAR-Lag) and k >= 2 the steps are software-pipelined: the VAE update of step s+1 (bcql.py:122-132), which depends
+ * on nothing the rest of step s writes, runs on a second graph branch while the critic / actor updates of step s
+ * read a snapshot of the VAE weights.  Every parameter sees the same kernels on the same data in the same order, so
+ * the state after the call is bit-identical to k calls with k = 1 (tests/test_gpu_parity.py).  OSRL_PIPELINE=0
+ * disables it. */
 int osrl_steps(osrl_engine* e, int k, void* stream);
 
 /* Stats of the most recent step, in the order of osrl_stat_names (logger.store keys,
