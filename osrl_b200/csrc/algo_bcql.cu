@@ -116,10 +116,8 @@ void build_bcql(Engine& e, int phase) {
     const float *tqv = tq.q, *tqcv = tqc.q, *oqv = oq.q, *oqcv = oqc.q;
     const int nq = cr.n, nqc = cc.n;
     float* st1 = e.stats + 1; float* st2 = e.stats + 2;
-    KOP(p, e, 0.0, (k_q_backup<<<(B + 127) / 128, 128, 0, s>>>(tqv, B, S, nq, lm, gm, rew, done, 1, y_q)));
-    KOP(p, e, 0.0, (k_q_backup<<<(B + 127) / 128, 128, 0, s>>>(tqcv, B, S, nqc, lm, gm, cost, done, 0, y_qc)));
-    KOP(p, e, 0.0, (k_critic_loss<<<1, 1024, 0, s>>>(oqv, y_q, B, nq, dq, st1, iw, 0.f, nullptr)));
-    KOP(p, e, 0.0, (k_critic_loss<<<1, 1024, 0, s>>>(oqcv, y_qc, B, nqc, dqc, st2, iw, 0.f, nullptr)));
+    const BackupLossArgs a0{tqv, nq, rew, 1, y_q, oqv, dq, st1}, a1{tqcv, nqc, cost, 0, y_qc, oqcv, dqc, st2};
+    KOP(p, e, 0.0, (k_backup_critic_loss2<<<2, 1024, 0, s>>>(a0, a1, done, B, S, lm, gm, iw)));
   }
   {
     EnsBuf gq = ens_alloc(e, cr, B), gqc = ens_alloc(e, cc, B);

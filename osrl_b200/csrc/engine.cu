@@ -170,6 +170,8 @@ static void emit_thin(Engine& e, Program& p, std::vector<GemmTask> tasks) {
     }
     int tn = 1;
     t.klen = 16;   // THIN_N: rows per CTA (two per warp)
+    t.a_vec = ((uintptr_t)t.A % 16 == 0) && (t.lda % 4 == 0) && ((t.a_kc ? t.K : t.M) % 4 == 0);
+    t.b_vec = ((uintptr_t)t.B % 16 == 0) && (t.ldb % 4 == 0) && ((t.b_kc ? t.K : t.N) % 4 == 0);
     const int n = thin_tiles(t, t.thin, &tn);
     t.tile0 = tot; t.tiles_n = tn; t.tiles_mn = n; t.ksplit = 1;
     tot += n;

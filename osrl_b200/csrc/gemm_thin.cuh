@@ -69,6 +69,42 @@ __device__ __forceinline__ void thin_k_body(const GemmTask& t, int lt, float* sm
   const int rows = min(THIN_K_ROWS, t.M - m0);
   __syncthreads();
   if (j >= t.N) return;
+  // the common first layer: ReLU(x W^T + b) and nothing else.  Full 16-row tiles are unrolled so the row part of
+  // every address is an immediate; the generic epilogue costs more instructions than the 16 FMAs it follows
+  // (the 21 MB stacked first layer of the 8 target Q networks was issue-bound on it).
+  const bool plain = ep.act == ACT_RELU && !ep.aux && !ep.resid && !ep.clamp && !ep.dact && ep.scale == 1.f &&
+                     rows == THIN_K_ROWS;
+  if (plain && t.pk_hi && t.c_dead) {
+    const int grp = j / t.pk_gcols, col = j - grp * t.pk_gcols;
+    // m0 is a multiple of 16: rows m0..m0+15 lie in one 64-row block, 8-row groups g0 and g0+1
+    const size_t base = ((size_t)(m0 >> 6) * t.pk_ks + (col >> 5)) * 2048 + (size_t)(((m0 & 63) >> 3) * 256) + (col & 3);
+    float* __restrict__ phi = t.pk_hi + (size_t)grp * t.pk_gstride + base;
+    float* __restrict__ plo = t.pk_lo + (size_t)grp * t.pk_gstride + base;
+    const int ck = (col & 31) >> 2;
+#pragma unroll
+    for (int r = 0; r < THIN_K_ROWS; ++r) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) acc = fmaf(As[r][k], b[k], acc);
+      const float v = fmaxf(acc + bias, 0.f);   // (bias last, like the generic epilogue: keeps the ReLU kinks where they were)
+      const int off = (r >> 3) * 256 + (r & 7) * 32 + ((ck ^ (r & 7)) << 2);
+      const float hi = thin_rna_tf32(v);
+      phi[off] = hi;
+      plo[off] = thin_rna_tf32(v - hi);
+    }
+    return;
+  }
+  if (plain && !t.pk_hi) {
+    float* __restrict__ crow = ep.C + (size_t)m0 * ep.ldc + j;
+#pragma unroll
+    for (int r = 0; r < THIN_K_ROWS; ++r) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) acc = fmaf(As[r][k], b[k], acc);
+      crow[(size_t)r * ep.ldc] = fmaxf(acc + bias, 0.f);
+    }
+    return;
+  }
   if (t.pk_hi) {   // packed tf32 hi/lo images for a tcgen05 consumer (see GemmTask), optionally instead of C
     const int grp = j / t.pk_gcols, col = j - grp * t.pk_gcols, ksr = t.pk_ks;
     float* __restrict__ phi = t.pk_hi + (size_t)grp * t.pk_gstride;
@@ -110,8 +146,47 @@ __device__ __forceinline__ void thin_k_body(const GemmTask& t, int lt, float* sm
 // One warp per row, lanes stride k; B (N x K, a few KB) is read through L1, where every warp after the first
 // finds it.  (Measured: holding a whole A row in registers, or staging B through shared memory, is slower --
 // the 4-deep unrolled loop below already keeps enough loads in flight and stays under 64 registers.)
+// 5..16 outputs per row with k-contiguous, 16-byte aligned operands (the VAE's mean / log-std heads): lane =
+// (k-quarter, output n) -- every lane owns ONE output and a slice of k read as float4, so nothing but one
+// accumulator lives in registers (the lanes-stride-k form needs N accumulators and N loads per k in flight and ran
+// 3-5x slower for N = 8 at the 64-register cap); the k slices are combined with one or two shuffles.
+template <int NL>   // lanes per row across n: 8 or 16
+__device__ __forceinline__ void thin_n_split_body(const GemmTask& t, int lt) {
+  constexpr int KQ = 32 / NL;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = lane % NL, kq = lane / NL;
+  const int N = t.N, K = t.K, M = t.M, lda = t.lda, ldb = t.ldb;
+  const float* __restrict__ A = t.A;
+  const float* __restrict__ B = t.B;
+  const int rows_per_tile = t.klen;
+  const int row1 = min(M, (lt + 1) * rows_per_tile);
+  const Epi ep = make_epi(t);
+  const float bias = (t.bias && n < N) ? t.bias[n] : 0.f;
+  const int k4tot = K / 4, per = (k4tot + KQ - 1) / KQ;
+  const int q0 = kq * per, q1 = min(k4tot, q0 + per);
+  const float4* __restrict__ b4 = reinterpret_cast<const float4*>(B + (size_t)min(n, N - 1) * ldb);
+  for (int row = lt * rows_per_tile + warp; row < row1; row += THIN_THREADS / 32) {
+    const float4* __restrict__ a4 = reinterpret_cast<const float4*>(A + (size_t)row * lda);
+    float acc = 0.f;
+#pragma unroll 5
+    for (int q = q0; q < q1; ++q) {
+      const float4 a = a4[q], b = b4[q];
+      acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+    }
+#pragma unroll
+    for (int o = NL; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (kq == 0 && n < N) epi_store<false>(ep, bias, row, n, acc);
+  }
+}
+
 template <int NMAX>
 __device__ __forceinline__ void thin_n_body(const GemmTask& t, int lt) {
+  if constexpr (NMAX >= 8) {
+    if (t.b_kc && t.a_vec && t.b_vec) {   // (set by the host: bases, leading dimensions and K 4-float aligned)
+      thin_n_split_body<NMAX>(t, lt);
+      return;
+    }
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int N = t.N, K = t.K, M = t.M, lda = t.lda, ldb = t.ldb;
   const bool bkc = t.b_kc != 0;

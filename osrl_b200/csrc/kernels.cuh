@@ -79,9 +79,11 @@ struct AdamGroupCfg {
   int warmup;  // >0: lr * min((t)/warmup, 1) with t = step count after increment (LambdaLR, cdt.py:327-330)
 };
 static __global__ void k_prologue(DevState* ds, const AdamGroupCfg* g, int ngroups, unsigned mask) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  for (int i = 0; i < ngroups; ++i) {
-    if (!((mask >> i) & 1u)) continue;   // pipelined graphs advance the VAE group and the others separately
+  if (blockIdx.x != 0) return;
+  {
+    const int i = threadIdx.x;           // one thread per optimiser group (the double-precision pow()s are ~1.5 us each)
+    if (i >= ngroups) return;
+    if (!((mask >> i) & 1u)) return;     // pipelined graphs advance the VAE group and the others separately
     const int t = ds->adam_t[i] + 1;
     ds->adam_t[i] = t;
     double lr = (double)g[i].lr;
@@ -361,6 +363,43 @@ static __global__ void k_critic_loss(const float* __restrict__ q, const float* _
   }
   s = block_sum(s, sh);
   if (threadIdx.x == 0) stat[0] = s * inv + (extra ? extra_const_ptr_mul * extra[0] : 0.f);
+}
+
+// Both critics' backup + loss in one launch (block 0: reward critic, block 1: cost critic): the four kernels above are
+// four dependent 3-5 us launches on 256 rows otherwise.  Same arithmetic, same order per element.
+struct BackupLossArgs {
+  const float* tq; int n;              // target ensemble outputs [B*S, n]
+  const float* r; int use_done;        // reward / cost; (1 - done) factor only for the reward critic (bcql.py:150,174)
+  float* y;                            // [B] backup
+  const float* q; float* dq; float* stat;
+};
+static __global__ void k_backup_critic_loss2(BackupLossArgs a0, BackupLossArgs a1, const float* __restrict__ done, int B,
+                                             int S, float lmbda, float gamma, float inv_world) {
+  __shared__ float sh[33];
+  const BackupLossArgs a = blockIdx.x ? a1 : a0;
+  const int n = a.n, h = n / 2;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    float best = -INFINITY;
+    for (int s = 0; s < S; ++s) {
+      const float* row = a.tq + ((size_t)b * S + s) * n;
+      float q1 = row[0], q2 = row[h];
+      for (int i = 1; i < h; ++i) { q1 = fminf(q1, row[i]); q2 = fminf(q2, row[h + i]); }
+      const float v = lmbda * fminf(q1, q2) + (1.f - lmbda) * fmaxf(q1, q2);
+      best = fmaxf(best, v);
+    }
+    const float nd = a.use_done ? (1.f - done[b]) : 1.f;
+    a.y[b] = a.r[b] + gamma * nd * best;
+  }
+  __syncthreads();
+  float s = 0.f;
+  const float inv = 1.f / (float)B;
+  for (int e = threadIdx.x; e < B * n; e += blockDim.x) {
+    const float d = a.q[e] - a.y[e / n];
+    s += d * d;
+    a.dq[e] = 2.f * d * inv * inv_world;
+  }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) a.stat[0] = s * inv;
 }
 
 // ------------------------------------------------------------------ data-parallel partial means (summed by NCCL)
