@@ -295,6 +295,11 @@ def run_ours(args):
             a[0] += pms; a[1] += by; a[2] += fl; a[3] += 1
         tot = sum(a[0] for a in agg.values())
 
+        traffic = {}
+        tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")   # dram read+write per launch, one ncu --set full capture
+        if os.path.exists(tp):
+            traffic = {k_: v["traffic_bytes_per_launch"] for k_, v in json.load(open(tp))["kernels"].items()}
+
         def entry(k_):
             d = agg[k_]
             tensor = k_ in ("k_gemm_tc5", "k_gemm_mma")     # tensor-core kernels; everything else moves bytes
@@ -303,7 +308,7 @@ def run_ours(args):
             ent = {"bound": "tensor" if tensor else "hbm", "kernel": k_,
                    "achieved": tfs if tensor else gbs, "peak": peak_tf if tensor else peak_gbs,
                    "unit": "TFLOP/s" if tensor else "GB/s", "frac": (tfs / peak_tf) if tensor else (gbs / peak_gbs),
-                   "traffic": None, "launches_per_step": d[3], "share_of_step_time": d[0] / tot,
+                   "traffic": traffic.get(k_), "launches_per_step": d[3], "share_of_step_time": d[0] / tot,
                    "avg_launch_us": 1e3 * d[0] / d[3], "algorithmic_bytes_per_step": d[1],
                    "algorithmic_flops_per_step": d[2]}
             if tensor:   # fp32-accurate 3xTF32: three TF32 MMAs (half the bf16 rate) per algorithmic product
@@ -315,6 +320,9 @@ def run_ours(args):
         roof = entry(order[0])
         roof["peak_source"] = peak_src
         roof["timing"] = "CUDA events around every launch of the step on the engine's stream (osrl_profile, 30 reps)"
+        roof["traffic_source"] = ("profiles/r01_ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch, "
+                                  "ncu --set full (cold caches under replay); algorithmic bytes per launch = "
+                                  "algorithmic_bytes_per_step / launches_per_step")
         roof["other_kernels"] = [entry(k_) for k_ in order[1:4]]
         roof["step_level"] = {"bytes_per_step": STEP_BYTES, "hbm_gbs": STEP_BYTES * sync_steps_per_s / 1e9,
                               "flops_per_step": STEP_FLOPS, "tflops": STEP_FLOPS * sync_steps_per_s / 1e12}
