@@ -372,6 +372,19 @@ def run_ours(args):
 
 
 def main():
+    # libraries (NCCL's version banner, torchrun helpers) write to fd 1; the contract is ONE JSON line on stdout, so
+    # everything but that line is sent to stderr
+    global print
+    real_out = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    _print = print
+
+    def print(*a, **k):  # noqa: A001  (only the result lines go through here)
+        k.setdefault("file", real_out)
+        k.setdefault("flush", True)
+        _print(*a, **k)
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
