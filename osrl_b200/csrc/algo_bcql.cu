@@ -30,8 +30,10 @@ void build_bc(Engine& e) {
 
 // ====================================================================== BCQ-Lag
 // phase 0: the whole step into e.body.  Pipelined graphs (engine.cu) build the step a second time in two halves
-// that can run concurrently: phase 1 = the VAE update alone (into e.pa, reading the NEXT minibatch e.nb_*), phase 2 =
-// everything else (into e.pm, reading the current minibatch and the VAE weights from the snapshot e.Psnap).
+// that can run concurrently: phase 1 (into e.pa, reading the NEXT minibatch e.nb_*) = the VAE update and, right
+// after it, the two VAE decodes of that step (target pass on 2R rows, actor pass on B rows): they depend only on
+// the VAE, the minibatch and noise, so their outputs are handed over (Engine::handoff) to phase 2 = everything else
+// (into e.pm, reading the current minibatch), which then starts at the actor_old perturbation.
 void build_bcql(Engine& e, int phase) {
   const osrl_config& c = e.plan.cfg;
   const Plan& pl = e.plan;
@@ -59,15 +61,27 @@ void build_bcql(Engine& e, int phase) {
   float* p_dec_in = e.ws((size_t)B * din);   // actor step
   float* p_ain = e.ws((size_t)B * in);
   float* p_qin = e.ws((size_t)B * in);
+  // pipelined halves: decode outputs travel through (next, cur) buffer pairs copied before the graph forks
+  float *t_av = nullptr, *p_av = nullptr;   // [2R, a] / [B, a] VAE actions: written in phase 1, read in phase 2
+  const bool dside = e.decode_side;         // (off: the decodes stay in phase 2 and read the VAE weight snapshot)
+  if (!dside) {
+  } else if (phase == 1) {
+    t_av = e.ws((size_t)2 * R * a); p_av = e.ws((size_t)B * a);
+    e.handoff.push_back({t_av, e.ws((size_t)2 * R * a), (size_t)2 * R * a * sizeof(float)});
+    e.handoff.push_back({p_av, e.ws((size_t)B * a), (size_t)B * a * sizeof(float)});
+  } else if (phase == 2) {
+    OSRL_REQUIRE(e.handoff.size() == 2, "phase 1 must be built first");
+    t_av = e.handoff[0].cur; p_av = e.handoff[1].cur;
+  }
+  const bool do_dec_inputs = dside ? phase != 2 : phase != 1;   // [obs | z] decoder inputs: wherever the decodes run
+  const float* dec_nobs = phase == 1 ? e.nb_nobs : e.b_nobs;
   {
     std::vector<CopyTask> ct;
     ct.push_back(copy_cols(sa, in, 0, bobs, o, 0, B, o));     // (both halves use [obs | act]: VAE loss, online critics)
     ct.push_back(copy_cols(sa, in, o, bact, a, 0, B, a));
     if (do_vae) ct.push_back(copy_cols(v_dec_in, din, 0, bobs, o, 0, B, o));
-    if (do_rest) {
-      ct.push_back(copy_cols(t_dec_in, din, 0, e.b_nobs, o, 0, 2 * R, o, S, B));   // repeat_interleave (bcql.py:138)
-      ct.push_back(copy_cols(t_ain, in, 0, e.b_nobs, o, 0, 2 * R, o, S, B));
-      ct.push_back(copy_cols(t_qin, in, 0, e.b_nobs, o, 0, 2 * R, o, S, B));
+    if (do_dec_inputs) {
+      ct.push_back(copy_cols(t_dec_in, din, 0, dec_nobs, o, 0, 2 * R, o, S, B));   // repeat_interleave (bcql.py:138)
       CopyTask z1 = copy_cols(t_dec_in, din, o, n_zc, L, 0, R, L);                 // z.clamp(-0.5, 0.5) (net.py:334)
       z1.clamp = 1; z1.lo = -0.5f; z1.hi = 0.5f;
       CopyTask z2 = copy_cols(t_dec_in + (size_t)R * din, din, o, n_zcc, L, 0, R, L);
@@ -75,22 +89,39 @@ void build_bcql(Engine& e, int phase) {
       CopyTask z3 = copy_cols(p_dec_in, din, o, n_za, L, 0, B, L);
       z3.clamp = 1; z3.lo = -0.5f; z3.hi = 0.5f;
       ct.push_back(z1); ct.push_back(z2); ct.push_back(z3);
-      ct.push_back(copy_cols(p_dec_in, din, 0, e.b_obs, o, 0, B, o));
+      ct.push_back(copy_cols(p_dec_in, din, 0, bobs, o, 0, B, o));
+    }
+    if (do_rest) {
+      ct.push_back(copy_cols(t_ain, in, 0, e.b_nobs, o, 0, 2 * R, o, S, B));
+      ct.push_back(copy_cols(t_qin, in, 0, e.b_nobs, o, 0, 2 * R, o, S, B));
       ct.push_back(copy_cols(p_ain, in, 0, e.b_obs, o, 0, B, o));
       ct.push_back(copy_cols(p_qin, in, 0, e.b_obs, o, 0, B, o));
+      if (phase == 2 && dside) {   // VAE actions decoded by the other half one replay earlier
+        ct.push_back(copy_cols(t_ain, in, o, t_av, a, 0, 2 * R, a));
+        ct.push_back(copy_cols(p_ain, in, o, p_av, a, 0, B, a));
+      }
     }
     emit_copy(e, p, ct);
   }
 
   // ---------------- 1. VAE update (bcql.py:122-132)
   if (do_vae) emit_vae_update(e, p, sa, v_dec_in, n_vae, bact, 0);
-  if (!do_rest) return;
+  if (phase == 1 && !dside) return;
+  if (phase == 1) {   // the step's two decodes with the freshly updated VAE (bcql.py:141,164,189), handed to phase 2
+    float* th1 = e.ws((size_t)2 * R * V); float* th2 = e.ws((size_t)2 * R * V);
+    emit_vae_decode(e, p, e.P, t_dec_in, 2 * R, th1, th2, t_av, a, 0, true);
+    float* ph1 = e.ws((size_t)B * V); float* ph2 = e.ws((size_t)B * V);
+    emit_vae_decode(e, p, e.P, p_dec_in, B, ph1, ph2, p_av, a, 0);
+    return;
+  }
 
   // ---------------- 2+3. critic and cost-critic updates (bcql.py:134-179), merged launch-by-launch
   // target actions on 2R rows: current VAE decode -> actor_old perturbation
   {
-    float* th1 = e.ws((size_t)2 * R * V); float* th2 = e.ws((size_t)2 * R * V);
-    emit_vae_decode(e, p, Wvae, t_dec_in, 2 * R, th1, th2, t_ain + o, in, 0, true);
+    if (phase == 0 || !dside) {
+      float* th1 = e.ws((size_t)2 * R * V); float* th2 = e.ws((size_t)2 * R * V);
+      emit_vae_decode(e, p, Wvae, t_dec_in, 2 * R, th1, th2, t_ain + o, in, 0, true);
+    }
     std::vector<float*> ah;
     GemmTask last = mlp_fwd_hidden(e, p, e.T, act, t_ain, in, 2 * R, ACT_TANH, ah, t_qin + o, in, true);
     last.act = ACT_TANH; last.scale = philim;           // net.py:61: phi*act_limit*pi(.)
@@ -139,8 +170,10 @@ void build_bcql(Engine& e, int phase) {
   float* pt = e.ws((size_t)B * a);  // tanh(l3) of the perturbation net
   std::vector<float*> pah;
   {
-    float* ph1 = e.ws((size_t)B * V); float* ph2 = e.ws((size_t)B * V);
-    emit_vae_decode(e, p, Wvae, p_dec_in, B, ph1, ph2, p_ain + o, in, 0);
+    if (phase == 0 || !dside) {
+      float* ph1 = e.ws((size_t)B * V); float* ph2 = e.ws((size_t)B * V);
+      emit_vae_decode(e, p, Wvae, p_dec_in, B, ph1, ph2, p_ain + o, in, 0);
+    }
     GemmTask last = mlp_fwd_hidden(e, p, e.P, act, p_ain, in, B, ACT_TANH, pah, p_qin + o, in);
     last.act = ACT_TANH; last.scale = philim;
     last.aux = pt; last.ldaux = a;

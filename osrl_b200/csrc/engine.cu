@@ -574,7 +574,14 @@ static void build_pipelined(Engine& e, const std::vector<int>& vae_slots) {
 static void build_program(Engine& e) {
   switch (e.plan.cfg.algo) {
     case OSRL_ALGO_BC: build_bc(e); break;
-    case OSRL_ALGO_BCQL: build_bcql(e); build_pipelined(e, {0}); break;
+    case OSRL_ALGO_BCQL: {
+      build_bcql(e);
+      const char* v = getenv("OSRL_PIPELINE_DECODE");   // VAE branch also runs the step's two VAE decodes
+      e.decode_side = v ? v[0] != '0' : false;
+      if (e.decode_side) build_pipelined(e, {0, 1, 2, 3});
+      else build_pipelined(e, {0});
+      break;
+    }
     case OSRL_ALGO_CPQ: build_cpq(e); build_pipelined(e, {0}); break;
     case OSRL_ALGO_BEARL: build_bearl(e); build_pipelined(e, {0}); break;
     case OSRL_ALGO_CDT: build_cdt(e); break;
@@ -747,6 +754,8 @@ static void snapshot_vae(Engine& e, cudaStream_t s) {
   const Group& g = e.plan.groups[e.plan.g_vae];
   OSRL_CUDA(cudaMemcpyAsync(e.Psnap + g.begin, e.P + g.begin, (size_t)(g.end - g.begin) * sizeof(float),
                             cudaMemcpyDeviceToDevice, s));
+  for (auto& hd : e.handoff)   // what the VAE branch produced for the step the main branch is about to run
+    OSRL_CUDA(cudaMemcpyAsync(hd.cur, hd.next, hd.bytes, cudaMemcpyDeviceToDevice, s));
 }
 // which: 0 = first VAE update alone, 1 = steady state (fork / join), 2 = last step's remainder alone
 static cudaGraphExec_t capture_pipelined(Engine& e, int which) {

@@ -162,6 +162,9 @@ struct Engine {
   float *nb_obs = nullptr, *nb_nobs = nullptr, *nb_act = nullptr, *nb_rew = nullptr, *nb_cost = nullptr, *nb_done = nullptr;
   int64_t* nb_idx = nullptr;
   float* Psnap = nullptr;
+  struct Handoff { float* next; float* cur; size_t bytes; };   // side-branch results of step s+1 -> main branch, copied
+  std::vector<Handoff> handoff;                                // next -> cur before each fork
+  bool decode_side = false;   // BCQ-Lag: the step's VAE decodes run on the VAE branch too (OSRL_PIPELINE_DECODE)
   NoiseSlot *d_slots_vae = nullptr, *d_slots_rest = nullptr;
   cudaGraphExec_t g_pro = nullptr, g_mid = nullptr, g_last = nullptr;
   cudaStream_t side_stream = nullptr;
