@@ -577,7 +577,7 @@ static void build_program(Engine& e) {
     case OSRL_ALGO_BCQL: {
       build_bcql(e);
       const char* v = getenv("OSRL_PIPELINE_DECODE");   // VAE branch also runs the step's two VAE decodes
-      e.decode_side = v ? v[0] != '0' : false;
+      e.decode_side = v ? v[0] != '0' : true;
       if (e.decode_side) build_pipelined(e, {0, 1, 2, 3});
       else build_pipelined(e, {0});
       break;
