@@ -131,6 +131,8 @@ class CDTOracle:
         self.target_entropy = -float(a) if cfg.target_entropy is None else cfg.target_entropy
         self.steps = 0
         self.last_noise: Dict[str, torch.Tensor] = {}
+        self.dp = None      # tests: an object with all_reduce(tensor) / world (torch.distributed) -- restates the
+                            # engine's data-parallel decomposition (global masked-mean denominators, summed gradients)
 
     # ---- dropout multipliers, one tensor per site, in the reference's call order (cdt.py:222; net.py:428-440:
     # attention weights inside nn.MultiheadAttention, self.drop(attention_out), the mlp's trailing nn.Dropout)
@@ -216,20 +218,43 @@ class CDTOracle:
         valid = mask > 0
         logp = -((actions - mu) ** 2) / (2 * std ** 2) - log_std - math.log(math.sqrt(2 * math.pi))
         ent = 0.5 + 0.5 * math.log(2 * math.pi) + log_std
-        ll = logp[valid].mean()                                                      # cdt.py:358
-        entropy = ent[valid].mean()                                                  # :359
         temp = self.log_temperature.exp().detach()
-        act_loss = -(ll + temp * entropy)                                            # :365
         cl = F.nll_loss(cost_preds.reshape(-1, 2), costs.flatten().long(), reduction="none")
-        cost_loss = (cl * mask.flatten()).mean()                                     # :378-380
         pred = cost_preds.reshape(-1, 2).max(dim=1)[1]
-        acc = (pred.eq(costs.flatten().long()) * mask.flatten()).sum() / mask.sum()
         sl = F.mse_loss(state_preds[:, :-1], states[:, 1:], reduction="none")
-        state_loss = (sl * mask[:, :-1].unsqueeze(-1)).mean()                        # :388-392
+        if self.dp is None:
+            ll = logp[valid].mean()                                                      # cdt.py:358
+            entropy = ent[valid].mean()                                                  # :359
+            cost_loss = (cl * mask.flatten()).mean()                                     # :378-380
+            acc = (pred.eq(costs.flatten().long()) * mask.flatten()).sum() / mask.sum()
+            state_loss = (sl * mask[:, :-1].unsqueeze(-1)).mean()                        # :388-392
+        else:
+            # data parallel (what k_cdt_loss does in two phases): the means are over the GLOBAL batch, so every rank
+            # divides its partial sums by the all-reduced counts; the summed gradients are then the global gradient
+            def gsum(x):
+                t = x.detach().double().reshape(1).clone()
+                self.dp.all_reduce(t)
+                return float(t)
+            n_valid = gsum(valid.sum()) * logp.shape[-1]
+            n_bt = gsum(torch.tensor(float(mask.numel())))
+            n_sl = gsum(torch.tensor(float(sl.numel())))
+            ll_l, ent_l = logp[valid].sum() / n_valid, ent[valid].sum() / n_valid
+            cost_l = (cl * mask.flatten()).sum() / n_bt
+            state_l = (sl * mask[:, :-1].unsqueeze(-1)).sum() / n_sl
+            # local contributions carry the gradient, the reported / temperature values are the global sums
+            ll = ll_l + (gsum(ll_l) - ll_l.detach())
+            entropy = ent_l + (gsum(ent_l) - ent_l.detach())
+            cost_loss = cost_l + (gsum(cost_l) - cost_l.detach())
+            state_loss = state_l + (gsum(state_l) - state_l.detach())
+            acc = torch.tensor(gsum((pred.eq(costs.flatten().long()) * mask.flatten()).sum()) / gsum(mask.sum()))
+        act_loss = -(ll + temp * entropy)                                            # :365
         loss = act_loss + cfg.loss_cost_weight * cost_loss + cfg.loss_state_weight * state_loss
         g = C.grads_of(loss, p, self.names)
         C.require_grad(p, self.names, False)
         g = {k: v.to(p[k].dtype) for k, v in g.items()}
+        if self.dp is not None:                 # gradient all-reduce (sum), before the global-norm clip
+            for v in g.values():
+                self.dp.all_reduce(v)
         # clip_grad_norm_ (cdt.py:399)
         total = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(v) for v in g.values()]))
         coef = torch.clamp(cfg.clip_grad / (total + 1e-6), max=1.0)

@@ -184,11 +184,54 @@ def run_cdt(steps: int = 3, Bg: int = 16):
     return bool(ok.item())
 
 
+def run_cdt_gloo(steps: int = 3, Bg: int = 8):
+    """CPU restatement of the CDT data-parallel decomposition (oracle with partial sums + all-reduced counts and
+    gradients on B/N sequences per rank) == the single oracle on the concatenated batch."""
+    from oracle import cdt as ocdt
+    from oracle.make_golden import CDT_KEYS, make_seq_batch
+    rank, world = dist.get_rank(), dist.get_world_size()
+    cfg = ocdt.CDTConfig(5, 3, 1.0, seq_len=10, episode_len=1000, embedding_dim=32, num_layers=2, num_heads=4,
+                         learning_rate=1e-3, lr_warmup_steps=4)
+    torch.manual_seed(0)
+    full = ocdt.CDTOracle(cfg)
+    torch.manual_seed(0)
+    part = ocdt.CDTOracle(cfg)
+    part.dp = dist
+    init = {k: v.clone() for k, v in full.params.items()}
+    rng = np.random.default_rng(3)
+    worst = 0.0
+
+    def args_of(b):
+        out = []
+        for k in CDT_KEYS:
+            t = torch.from_numpy(np.asarray(b[k]))
+            out.append(t if k == "time_steps" else (t.float() if k != "mask" else t.double()))
+        return out
+
+    for s in range(steps):
+        b = make_seq_batch(rng, Bg, cfg.seq_len, cfg.state_dim, cfg.action_dim)
+        ref = full.step(*args_of(b))
+        got = part.step(*args_of({k: shard(v, rank, world) for k, v in b.items()}))
+        for k, w in ref.items():
+            worst = max(worst, abs(got[k] - w) / (2e-5 * max(abs(w), 1e-3) + 1e-7))
+    for k, ref in full.params.items():
+        if "in_proj_bias" in k:
+            continue
+        err = float((part.params[k] - ref).norm())
+        bound = 1e-3 * float((ref - init[k]).norm()) + 4e-7 * float(ref.norm()) + 1e-9
+        worst = max(worst, err / bound)
+    ok = torch.tensor([1.0 if worst <= 1.0 else 0.0])
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(json.dumps({"algo": "cdt", "backend": "gloo", "world": world, "worst_ratio": worst, "ok": bool(ok.item())}))
+    return bool(ok.item())
+
+
 def _mp_entry(rank, world, algo, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(2)
-    ok = run(algo, "gloo")
+    ok = run_cdt_gloo() if algo == "cdt" else run(algo, "gloo")
     if rank == 0:
         q.put(ok)
     dist.destroy_process_group()
