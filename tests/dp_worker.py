@@ -26,6 +26,11 @@ CFGS = {
                   vae_hidden_sizes=48, sample_action_num=10, num_q=2, num_qc=2, actor_lr=1e-3, critic_lr=1e-3,
                   vae_lr=1e-3, start_update_policy_step=0, cost_limit=0.05),
     "bc": dict(state_dim=28, action_dim=2, max_action=1.0, a_hidden_sizes=[32, 32], actor_lr=1e-3),
+    # CPQ: the 0.75-quantile of the OOD KL (cpq.py:183) is taken per shard; it only feeds log_alpha and a logged
+    # term (no gradient), so the parameters still equal the single-rank step (stats are not compared here)
+    "cpq": dict(state_dim=8, action_dim=2, max_action=1.0, a_hidden_sizes=[32, 32], c_hidden_sizes=[32, 32],
+                vae_hidden_sizes=48, sample_action_num=10, num_q=2, num_qc=2, actor_lr=1e-3, critic_lr=1e-3,
+                vae_lr=1e-3, alpha_lr=1e-3),
 }
 # noise slot -> rows per batch row (slots are [B*rows, cols] b-major, so a rank takes a contiguous block)
 KEYS = ("observations", "next_observations", "actions", "rewards", "costs", "done")
@@ -64,6 +69,11 @@ def run(algo: str, backend: str, steps: int = 3, Bg: int = 32):
         bl = {k: shard(v, rank, world) for k, v in b.items()}
         nl = {}
         for k, v in nz_full.items():
+            if k.startswith("ood"):                  # CPQ's OOD draws are S-major: [S, B, .] (torch.tile, cpq.py:169-173)
+                S = cfg["sample_action_num"]
+                w_ = v.reshape(S, Bg, -1)[:, rank * B:(rank + 1) * B]
+                nl[k] = w_.reshape(S, B, -1) if v.dim() == 3 else w_.reshape(S * B, -1)
+                continue
             flat = v.reshape(Bg, -1) if v.shape[0] == Bg else v.reshape(Bg, -1)
             nl[k] = shard(flat, rank, world).reshape(-1, *v.shape[1:]) if v.dim() > 1 else shard(v, rank, world)
             if v.dim() >= 2 and v.shape[0] != Bg:   # [B*S, L] style: b-major blocks

@@ -17,7 +17,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("algo", ["bc", "bcql", "bearl", "cdt"])
+@pytest.mark.parametrize("algo", ["bc", "bcql", "bearl", "cpq", "cdt"])
 def test_two_rank_equivalence_gloo(algo):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
