@@ -169,7 +169,7 @@ def main():
         run_case(osrl, name, algo, cfg, B, steps, full)
 
 
-if __name__ == "__main__" and sys.argv[1:] != ["cdt"]:
+if __name__ == "__main__" and not ({"cdt", "coptidice"} & set(sys.argv[1:])):
     main()
 
 
@@ -359,3 +359,77 @@ def check_sequence_sampler():
 
 if __name__ == "__main__" and "cdt" in sys.argv[1:]:
     check_sequence_sampler()
+
+
+# =========================================================================== COptiDICE (next row)
+def main_coptidice():
+    """Pin oracle.coptidice against the unmodified reference (coptidice.py:125-227) and write the fixture the CUDA
+    implementation will be held to.  Both consume torch's global generator in the same order (obs noise, action
+    noise, the actor's unused rsample), re-seeded identically before each step."""
+    from oracle import coptidice as oc
+    osrl = ref_shim.import_reference()
+    cfg = oc.COptiDICEConfig(8, 2, 1.0, f_type="softchi", init_state_propotion=0.25, a_hidden_sizes=[32, 32],
+                             c_hidden_sizes=[32, 32], num_nu=2, num_chi=2, actor_lr=1e-3, critic_lr=1e-3, scalar_lr=1e-3)
+    B, steps = 32, 4
+    rng = np.random.default_rng(21)
+    obs_std = rng.uniform(0.5, 1.5, (1, cfg.state_dim)).astype(np.float32)
+    act_std = rng.uniform(0.3, 0.8, (1, cfg.action_dim)).astype(np.float32)
+    torch.manual_seed(0)
+    ref = osrl.algorithms.COptiDICE(cfg.state_dim, cfg.action_dim, cfg.max_action, cfg.f_type, cfg.init_state_propotion,
+                                    obs_std, act_std, cfg.a_hidden_sizes, cfg.c_hidden_sizes, cfg.gamma, cfg.alpha,
+                                    cfg.cost_ub_epsilon, cfg.num_nu, cfg.num_chi, cfg.cost_limit, cfg.episode_len, "cpu")
+    trainer = osrl.algorithms.COptiDICETrainer(ref, None, logger=ref_shim.NullLogger(), actor_lr=cfg.actor_lr,
+                                               critic_lr=cfg.critic_lr, scalar_lr=cfg.scalar_lr, device="cpu")
+    torch.manual_seed(0)
+    orc = oc.COptiDICEOracle(cfg, obs_std, act_std)
+    sd = ref.state_dict()
+    assert list(sd.keys()) == [k for k in orc.params if k not in ("tau", "lmbda")], list(sd.keys())[:8]
+    for k, v in sd.items():
+        assert torch.equal(v, orc.params[k]), ("init differs", k)
+    init = {k: v.clone() for k, v in orc.params.items()}
+    keys = ("observations", "next_observations", "actions", "rewards", "costs", "done")
+    out = {}
+    worst = 0.0
+    stats_all = []
+    for s in range(steps):
+        b = synth.make_batch(rng, B, cfg.state_dim, cfg.action_dim)
+        b["is_init"] = (rng.random(B) < 0.25).astype(np.float32)
+        args = [torch.from_numpy(b[k]) for k in keys] + [torch.from_numpy(b["is_init"])]
+        n0 = len(trainer.logger.rows)
+        torch.manual_seed(1000 + s)
+        trainer.train_one_step(args)
+        row = {}
+        for r in trainer.logger.rows[n0:]:
+            row.update(r)
+        torch.manual_seed(1000 + s)
+        got = orc.step(*args)
+        assert set(row) == set(got), set(row) ^ set(got)
+        for k in row:
+            e = abs(row[k] - got[k]) / (abs(row[k]) + 1e-6)
+            worst = max(worst, e)
+            assert e < 2e-5, (s, k, row[k], got[k])
+        stats_all.append([row[k] for k in sorted(row)])
+        for k, v in b.items():
+            out[f"batch{s}/{k}"] = v
+        for k, v in orc.last_noise.items():
+            out[f"noise{s}/{k}"] = v.numpy()
+    perr = max(rel_err(orc.params[k], v) for k, v in ref.state_dict().items())
+    serr = max(abs(float(ref.tau) - float(orc.params["tau"])), abs(float(ref.lmbda) - float(orc.params["lmbda"])))
+    assert perr < 2e-5 and serr < 1e-6, (perr, serr)
+    print(f"[golden] coptidice_small: oracle == reference over {steps} steps (stat rel err {worst:.2e}, "
+          f"param rel err {perr:.2e}, tau/lambda abs err {serr:.1e})")
+    cfgd = dataclasses.asdict(cfg)
+    out["meta"] = json.dumps({"algo": "coptidice", "cfg": cfgd, "B": B, "steps": steps, "keys": list(init.keys()),
+                              "stat_keys": sorted(row.keys()), "torch": torch.__version__})
+    out["stats"] = np.array(stats_all, dtype=np.float64)
+    out["observations_std"], out["actions_std"] = obs_std, act_std
+    for k, v in init.items():
+        out["init/" + k] = v.numpy()
+    for k, v in ref.state_dict().items():
+        out["final/" + k] = v.numpy()
+    out["final/tau"], out["final/lmbda"] = ref.tau.detach().numpy(), ref.lmbda.detach().numpy()
+    np.savez_compressed(os.path.join(OUT, "coptidice_small.npz"), **out)
+
+
+if __name__ == "__main__" and "coptidice" in sys.argv[1:]:
+    main_coptidice()
