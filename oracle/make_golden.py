@@ -38,6 +38,14 @@ CASES = {
     "bearl_small": ("bearl", algos.BEARLConfig(8, 2, 1.0, [32, 32], [32, 32], 48, 10, num_q=2, num_qc=2,
                                                start_update_policy_step=0, actor_lr=1e-3, critic_lr=1e-3,
                                                vae_lr=1e-3), 16, 3, True),
+    # active constraint branch: qc_thres < 0 and O(1) PID gains -> lambda = O(0.1..1), qc_penalty != 0 (net.py:376-387,
+    # bcql.py:189-198, bearl.py:233-260); the default configs keep lambda ~ 1e-5 over the first steps
+    "bcql_pid_small": ("bcql", algos.BCQLConfig(8, 2, 1.0, [32, 32], [32, 32], 48, 10, num_q=2, num_qc=2,
+                                                PID=[1.0, 0.3, 0.5], cost_limit=-1, actor_lr=1e-3, critic_lr=1e-3,
+                                                vae_lr=1e-3), 16, 4, True),
+    "bearl_pid_small": ("bearl", algos.BEARLConfig(8, 2, 1.0, [32, 32], [32, 32], 48, 10, num_q=2, num_qc=2,
+                                                   PID=[1.0, 0.3, 0.5], cost_limit=-1, start_update_policy_step=0,
+                                                   actor_lr=1e-3, critic_lr=1e-3, vae_lr=1e-3), 16, 4, True),
     # BASELINE.json configs[0..2,4] at full layer sizes (checksums only)
     "bc_full": ("bc", algos.BCConfig(28, 2, 1.0, [256, 256], 1e-3), 256, 3, False),
     "bcql_full": ("bcql", algos.BCQLConfig(8, 2, 1.0, [256, 256], [256, 256], 400, 10, num_q=2, num_qc=2,
@@ -48,6 +56,12 @@ CASES = {
     "bearl_full": ("bearl", algos.BEARLConfig(8, 2, 1.0, [256, 256], [256, 256], 400, 10, num_q=2, num_qc=2,
                                               start_update_policy_step=0, actor_lr=1e-3, critic_lr=1e-3,
                                               vae_lr=1e-3), 512, 2, False),
+    "bcql_pid_full": ("bcql", algos.BCQLConfig(8, 2, 1.0, [256, 256], [256, 256], 400, 10, num_q=2, num_qc=2,
+                                               PID=[1.0, 0.3, 0.5], cost_limit=-1, actor_lr=1e-3, critic_lr=1e-3,
+                                               vae_lr=1e-3), 256, 3, False),
+    "bearl_pid_full": ("bearl", algos.BEARLConfig(8, 2, 1.0, [256, 256], [256, 256], 400, 10, num_q=2, num_qc=2,
+                                                  PID=[1.0, 0.3, 0.5], cost_limit=-1, start_update_policy_step=0,
+                                                  actor_lr=1e-3, critic_lr=1e-3, vae_lr=1e-3), 512, 2, False),
 }
 
 ORACLES = {"bc": algos.BCOracle, "bcql": algos.BCQLOracle, "cpq": algos.CPQOracle, "bearl": algos.BEARLOracle}
@@ -315,6 +329,14 @@ def run_cdt_case(osrl, name, cfg, B, steps, full):
 def main_cdt():
     from oracle import cdt as ocdt
     osrl = ref_shim.import_reference()
+    if "cdt_b2048" in sys.argv[1:]:
+        # BASELINE.json configs[3] at its own size: B=2048, seq_len 10, 3 layers, E=128, dropout 0.1 at all three
+        # sites (cdt_configs.py:22-44,498-511).  81,920 tokens -> the split-K weight-gradient path.  Checksums and
+        # stats only; the GPU test re-draws the same multipliers from the same torch CPU generator (seed 4242).
+        run_cdt_case(osrl, "cdt_b2048", ocdt.CDTConfig(17, 6, 1.0, seq_len=10, episode_len=1000, embedding_dim=128,
+                                                       num_layers=3, num_heads=8, attention_dropout=0.1,
+                                                       residual_dropout=0.1, embedding_dropout=0.1), 2048, 2, False)
+        return
     run_cdt_case(osrl, "cdt_small", ocdt.CDTConfig(5, 3, 1.0, seq_len=10, episode_len=1000, embedding_dim=32,
                                                    num_layers=2, num_heads=4, learning_rate=1e-3, lr_warmup_steps=4), 8, 3, True)
     run_cdt_case(osrl, "cdt_full", ocdt.CDTConfig(17, 6, 1.0, seq_len=10, episode_len=1000, embedding_dim=128,

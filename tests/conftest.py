@@ -19,3 +19,16 @@ def lib_built():
     if not os.path.exists(_lib.LIB_PATH):
         build.build()
     return _lib.load()
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Dump the measured parity margins of a GPU session (tests/helpers.py: record_margin)."""
+    import json
+    from tests import helpers
+    if not helpers.MARGINS:
+        return
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    rows = dict(sorted(helpers.MARGINS.items(), key=lambda kv: -kv[1]["worst_ratio"]))
+    with open(os.path.join(out, "parity_margins.json"), "w") as f:
+        json.dump({"exitstatus": int(exitstatus), "margins": rows}, f, indent=1)

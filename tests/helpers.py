@@ -72,3 +72,19 @@ def maxrel(a, b):
 
 def l2rel(a, b):
     return float((a.double() - b.double()).norm()) / (float(b.double().norm()) + 1e-300)
+
+
+# ---- measured parity margins ("print and commit the measured worst error per quantity").  Every GPU
+# comparison reports (test, quantity, err, tol); conftest writes the per-quantity worst err / tol of the session to
+# gpurun_out/parity_margins.json, which is committed as profiles/r02_parity_margins.json.
+MARGINS = {}
+
+
+def record_margin(test: str, quantity: str, err: float, tol: float):
+    key = f"{test}::{quantity}"
+    cur = MARGINS.get(key)
+    ratio = float(err) / float(tol) if tol > 0 else float("inf")
+    if cur is None or ratio > cur["worst_ratio"]:
+        MARGINS[key] = {"worst_ratio": ratio, "err": float(err), "tol": float(tol), "n": (cur["n"] if cur else 0) + 1}
+    else:
+        cur["n"] += 1

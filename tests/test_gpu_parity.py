@@ -23,7 +23,7 @@ import pytest
 import torch
 
 from oracle import synth
-from tests.helpers import RTOL, batch_tuple, l2rel, load_golden, make_oracle, maxrel, probe_step
+from tests.helpers import RTOL, batch_tuple, l2rel, load_golden, make_oracle, maxrel, probe_step, record_margin
 
 pytestmark = pytest.mark.gpu
 BATCH_KEYS = ("observations", "next_observations", "actions", "rewards", "costs", "done")
@@ -56,6 +56,7 @@ def _compare_step(tag, eng, s32, s64, g32, g64, before, p64, gemm="tc5"):
         tol = max(RTOL, 10 * cond)
         total += 1
         strict += tol == RTOL
+        record_margin("step_vs_oracle/" + gemm, "stat " + k, abs(got[k] - w), tol * scale + 1e-7)
         assert abs(got[k] - w) <= tol * scale + 1e-7, f"{tag} stat {k}: engine {got[k]} vs reference {w} (cond {cond:.1e})"
     G = eng.read_section("grad")
     outliers = []
@@ -65,9 +66,12 @@ def _compare_step(tag, eng, s32, s64, g32, g64, before, p64, gemm="tc5"):
         total += 1
         strict += tol == 2 * RTOL
         err = maxrel(G[k], g)
+        record_margin("step_vs_oracle/" + gemm, "grad (max-rel, all tensors)", err, tol)
         if err > tol:
             outliers.append((k, err, cond))
             assert err <= cap, f"{tag} grad {k}: rel err {err:.2e} (cond {cond:.1e})"
+    record_margin("step_vs_oracle/" + gemm, "grad outlier tensors (fraction of budget)", len(outliers),
+                  max(1, int(max_frac * len(g32))))
     assert len(outliers) <= max(1, int(max_frac * len(g32))), f"{tag}: too many gradient tensors off: {outliers[:6]}"
     return strict, total
 
@@ -85,12 +89,14 @@ def _compare_params(tag, eng, orc, before, p64):
         cond = l2rel(d_ref, p64[k] - before[k].double()) if k in p64 else 0.0
         tol = max(2 * RTOL, 10 * cond)      # 2e-5: one ulp of a 0.1-sized fp32 parameter is 7e-6 of a 1e-3 delta
         err = l2rel(d_eng, d_ref)
+        record_margin("step_vs_oracle", "param delta (l2-rel)", err, tol)
         assert err <= tol, f"{tag} param delta {k}: l2 rel err {err:.2e} > {tol:.1e} (cond {cond:.1e})"
     return strict, total
 
 
 @pytest.mark.parametrize("gemm", GEMMS)
-@pytest.mark.parametrize("case", ["bc_small", "bcql_small", "cpq_small", "bearl_small"])
+@pytest.mark.parametrize("case", ["bc_small", "bcql_small", "cpq_small", "bearl_small", "bcql_pid_small",
+                                  "bearl_pid_small"])
 def test_small_golden(lib_built, case, gemm):
     """Engine vs fixtures written by the UNMODIFIED reference (tests/golden, oracle/make_golden.py):
     same init, batches and noise; stats per step and final parameters."""
@@ -106,6 +112,7 @@ def test_small_golden(lib_built, case, gemm):
         got = eng.stats()
         for k, w in zip(meta["stat_keys"], z["stats"][s]):
             tol = 1e-4 if k == "loss/mmd_loss" else 2e-5   # mmd: sqrt of a 1e-3 difference of O(1) kernel means
+            record_margin("golden/" + gemm, "stat " + k, abs(got[k] - w), tol * max(abs(w), 1e-3) + 1e-7)
             assert abs(got[k] - w) <= tol * max(abs(w), 1e-3) + 1e-7, f"{case} step {s} {k}: {got[k]} vs {w}"
     got = eng.read_params()
     for k in meta["keys"]:
@@ -115,13 +122,15 @@ def test_small_golden(lib_built, case, gemm):
             # fp32 resolution of the parameter itself (Polyak targets move by only tau*lr per step)
             err = float((got[k] - ref).norm())
             bound = 5e-4 * float((ref - init[k]).norm()) + 4e-7 * float(ref.norm())
+            record_margin("golden/" + gemm, "final params after k steps (l2 of delta)", err, bound)
             assert err <= bound, f"{case}: {k} err {err:.3e} > {bound:.3e} after {steps} steps"
     eng.close()
 
 
 @pytest.mark.parametrize("gemm", GEMMS)
 @pytest.mark.parametrize("case", ["bc_small", "bcql_small", "cpq_small", "bearl_small",
-                                  "bc_full", "bcql_full", "cpq_full", "bearl_full"])
+                                  "bc_full", "bcql_full", "cpq_full", "bearl_full",
+                                  "bcql_pid_small", "bearl_pid_small", "bcql_pid_full", "bearl_pid_full"])
 def test_against_live_oracle(lib_built, case, gemm):
     """Per-step stats, gradients and parameter deltas vs the live oracle on the same seeds (full cases use
     BASELINE.json's layer sizes), with conditioning-scaled 1e-5 tolerances (module docstring)."""
