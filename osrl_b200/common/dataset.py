@@ -1,16 +1,105 @@
-"""Minibatch sources with the reference's class names (osrl/common/dataset.py:633-847).
+"""Minibatch sources and one-time dataset preprocessing with the reference's names (osrl/common/dataset.py).
 
-Both keep the reference's constructor and iterator contract (so they can be handed to
-``torch.utils.data.DataLoader`` by the unchanged example scripts) and additionally know how to make
-themselves resident in HBM (``to_engine`` / ``trainer.set_dataset``): the data is packed once and all later
-draws happen on the device (``osrl_steps``).
+`TransitionDataset` / `SequenceDataset` keep the reference's constructor and iterator contract (so they can be handed
+to ``torch.utils.data.DataLoader`` by the unchanged example scripts) and additionally know how to make themselves
+resident in HBM (``to_engine`` / ``trainer.set_dataset``): the data is packed once and all later draws happen on the
+device (``osrl_steps``).  The preprocessing helpers (`process_bc_dataset`, Pareto-frontier augmentation, sampling
+probabilities) run once before training -- off the hot path -- and are restated here on flat arrays; the 2-D Pareto
+front is a sort + scan, so the reference's `oapackage` dependency (dataset.py:9-12, 82-87, 358-365) is not needed.
 """
 from __future__ import annotations
 
+import heapq
 import random
+from collections import Counter
 
 import numpy as np
 from torch.utils.data import IterableDataset
+
+
+def episode_returns(x: np.ndarray, offsets: np.ndarray, gamma: float) -> np.ndarray:
+    """First element of discounted_cumsum (dataset.py:19-27) of every episode [offsets[i], offsets[i+1]), evaluated for
+    all episodes in lock-step from their last transition backwards: per episode the same float operations in the same
+    order as the reference's loop (acc = x[t] + gamma * acc, in x's dtype), without the per-transition Python loop."""
+    lens = np.diff(offsets)
+    ends = offsets[1:] - 1
+    acc = x[ends].copy()
+    for back in range(1, int(lens.max()) if lens.size else 0):
+        live = lens > back
+        idx = ends[live] - back
+        acc[live] = x[idx] + gamma * acc[live]
+    return acc
+
+
+def pareto_front_2d(cost: np.ndarray, rew: np.ndarray) -> list:
+    """Indices of the points not dominated under (minimise cost, maximise reward) -- what the reference obtains from
+    oapackage.ParetoDoubleLong on (-cost, reward) (dataset.py:82-87): sort by cost, scan with the best reward so far.
+    Points with identical (cost, reward) on the front are all kept."""
+    order = np.lexsort((-rew, cost))          # cost ascending, reward descending inside equal costs
+    keep, best = [], -np.inf
+    i, n = 0, len(order)
+    while i < n:
+        j = i
+        c = cost[order[i]]
+        while j < n and cost[order[j]] == c:
+            j += 1
+        top = rew[order[i]]
+        if top > best:                        # strictly better reward than anything cheaper
+            keep.extend(int(order[k]) for k in range(i, j) if rew[order[k]] == top)
+            best = top
+        i = j
+    return sorted(keep)
+
+
+def process_bc_dataset(dataset: dict, cost_limit: float, gamma: float, bc_mode: str):
+    """Filter a transition dataset for the BC variants, in place (dataset.py:30-134; train_bc.py:77).
+
+    Adds "cost_returns" / "rew_returns" (the episode's discounted return, repeated on each of its transitions; a
+    trailing unfinished episode keeps 0), then keeps the transitions of: every episode ("all", "multi-task" -- which
+    also appends the cost return as an observation feature), episodes within the limit ("safe"), beyond twice the limit
+    ("risky"), within (0.5, 1.5] x limit ("boundary"), or within a fifth of the reward range of the fitted Pareto
+    frontier ("frontier")."""
+    done = np.logical_or(dataset["terminals"] == 1, dataset["timeouts"] == 1)
+    ends = np.flatnonzero(done)
+    n = dataset["observations"].shape[0]
+    offsets = np.concatenate([[0], ends + 1]).astype(np.int64)
+    dataset["cost_returns"] = np.zeros_like(dataset["costs"])
+    dataset["rew_returns"] = np.zeros_like(dataset["rewards"])
+    cost_ret = episode_returns(dataset["costs"], offsets, gamma)
+    rew_ret = episode_returns(dataset["rewards"], offsets, gamma)
+    lens = np.diff(offsets)
+    covered = int(offsets[-1])
+    dataset["cost_returns"][:covered] = np.repeat(cost_ret, lens)
+    dataset["rew_returns"][:covered] = np.repeat(rew_ret, lens)
+
+    cr = dataset["cost_returns"]
+    if bc_mode in ("all", "multi-task"):
+        keep = np.ones(n, dtype=bool)
+    elif bc_mode == "safe":
+        keep = cr <= cost_limit
+    elif bc_mode == "risky":
+        keep = cr >= 2 * cost_limit
+    elif bc_mode == "boundary":
+        keep = np.logical_and(0.5 * cost_limit < cr, cr <= 1.5 * cost_limit)
+    elif bc_mode == "frontier":
+        c64, r64 = cost_ret.astype(np.float64), rew_ret.astype(np.float64)
+        span = (np.max(r64) - np.min(r64)) / 5
+        pf = pareto_front_2d(c64, r64)
+        frontier = None
+        for deg in (0, 1, 2):                 # lowest degree that explains 90 % of the front's variance
+            frontier = np.poly1d(np.polyfit(c64[pf], r64[pf], deg=deg))
+            resid = np.sum((r64[pf] - frontier(c64[pf])) ** 2)
+            if 1 - resid / np.sum((r64[pf] - np.mean(r64[pf])) ** 2) >= 0.9:
+                break
+        curve = frontier(cr)
+        keep = np.logical_and(curve - span <= dataset["rew_returns"], dataset["rew_returns"] <= curve + span)
+    else:
+        raise NotImplementedError
+    for k, v in dataset.items():
+        dataset[k] = v[keep]
+    if bc_mode == "multi-task":
+        dataset["observations"] = np.hstack((dataset["observations"], dataset["cost_returns"].reshape(-1, 1)))
+    print(f"original size = {n}, cost limit = {cost_limit}, filtered size = {int(np.sum(keep))}")
 
 
 class TransitionDataset(IterableDataset):

@@ -12,6 +12,13 @@ void emit_vae_decode(Engine& e, Program& p, const float* W, const float* dec_in,
                      float* out, int ldout, int mode, bool nograd) {
   const VaeLay& v = e.plan.vae;
   const int V = v.d1.out, ldin = v.d1.in;
+  if (fz_mlp_ok(v.d1, v.d2, v.d3)) {   // the whole decoder in one fused launch
+    FzTask t = fz_fwd3(dec_in, ldin, rows, W, v.d1, v.d2, v.d3, ACT_RELU, nograd ? nullptr : h1, V, nograd ? nullptr : h2,
+                       V, out, ldout);
+    if (mode == 0) { t.ract = ACT_TANH; t.rscale = e.plan.cfg.max_action; }
+    emit_fz(e, p, {t});
+    return;
+  }
   GemmTask first = task_fwd(dec_in, ldin, rows, W, v.d1, h1, V, ACT_RELU);
   if (nograd) { first.pk_gcols = V; first.c_dead = 1; }
   flush(e, p, {first});
@@ -36,6 +43,32 @@ void emit_vae_update(Engine& e, Program& p, const float* sa, float* dec_in, cons
   float* dz = e.ws((size_t)B * L); float* dml = e.ws((size_t)B * 2 * L);
   float* dh2 = e.ws((size_t)B * V); float* dh1 = e.ws((size_t)B * V);
   float* stat = e.stats + stat_index;
+  if (fz_mlp_ok(v.e1, v.e2, v.heads) && fz_mlp_ok(v.d1, v.d2, v.d3) && L <= 16) {
+    // fused: encoder, decoder, and the two backward chains are one launch each; weight gradients in two
+    const float lim = c.max_action, beta = c.beta;
+    emit_fz(e, p, {fz_fwd3(sa, o + a, B, e.P, v.e1, v.e2, v.heads, ACT_RELU, h1, V, h2, V, ml, 2 * L)});
+    KOP(p, e, 20.0 * B * L, (k_vae_reparam<<<(B * L + 255) / 256, 256, 0, s>>>(ml, eps, B, L, sd, dec_in, o + L, o)));
+    {
+      FzTask t = fz_fwd3(dec_in, o + L, B, e.P, v.d1, v.d2, v.d3, ACT_RELU, g1, V, g2, V, u, a);
+      t.ract = ACT_TANH; t.rscale = lim;
+      emit_fz(e, p, {t});
+    }
+    KOP(p, e, 12.0 * B * a + 12.0 * B * L, (k_vae_loss<<<1, 1024, 0, s>>>(u, act, B, a, lim, ml, sd, L, beta, dpre3, stat, iw)));
+    {
+      FzTask t = fz_bwd_mid(dpre3, a, B, e.P, v.d2, v.d3, ACT_RELU, g1, V, g2, V, dg2, V, dg1, V);
+      fz_add_dx(t, fz_new_group(), 0, 1, e.P, v.d1, o, L, dz, L);   // d loss / d z: the latent columns of d1's input
+      emit_fz(e, p, {t});
+    }
+    KOP(p, e, 28.0 * B * L, (k_vae_reparam_bwd<<<(B * L + 255) / 256, 256, 0, s>>>(dz, L, 0, ml, sd, eps, B, L, beta, dml, iw)));
+    emit_fz(e, p, {fz_bwd_mid(dml, 2 * L, B, e.P, v.e2, v.heads, ACT_RELU, h1, V, h2, V, dh2, V, dh1, V)});
+    emit_fz(e, p, {fz_wgrad(dg2, V, g1, V, B, e.G, v.d2), fz_wgrad(dh2, V, h1, V, B, e.G, v.e2)});
+    flush(e, p, {task_wgrad(dpre3, a, g2, V, B, e.G, v.d3), task_wgrad(dg1, V, dec_in, o + L, B, e.G, v.d1),
+                 task_wgrad(dml, 2 * L, h2, V, B, e.G, v.heads), task_wgrad(dh1, V, sa, o + a, B, e.G, v.e1)});
+    const Group& g = e.plan.groups[e.plan.g_vae];
+    emit_allreduce(e, p, e.G + g.begin, g.end - g.begin);
+    emit_adam(e, p, e.plan.g_vae, g.begin, g.end, false);
+    return;
+  }
   // encoder
   flush(e, p, {task_fwd(sa, o + a, B, e.P, v.e1, h1, V, ACT_RELU)});
   flush(e, p, {task_fwd(h1, V, B, e.P, v.e2, h2, V, ACT_RELU)});
@@ -71,6 +104,19 @@ GemmTask mlp_fwd_hidden(Engine& e, Program& p, const float* W, const MlpLay& m, 
   const float* cur = X;
   int ld = ldx;
   h.clear();
+  if (n == 3 && fz_mlp_ok(m.L[0], m.L[1], m.L[2])) {
+    // fused network: nothing is launched here -- the returned task is a marker that carries the caller's last-layer
+    // epilogue to emit_gemm, which completes the fused task (Engine::fz_pending) and launches it
+    float *y0 = nullptr, *y1 = nullptr;
+    if (!nograd) {
+      y0 = e.ws((size_t)rows * m.L[0].out); y1 = e.ws((size_t)rows * m.L[1].out);
+      h.push_back(y0); h.push_back(y1);
+    }
+    e.fz_pending.push_back(fz_fwd3(X, ldx, rows, W, m.L[0], m.L[1], m.L[2], hact, y0, m.L[0].out, y1, m.L[1].out, out, ldout));
+    GemmTask mk = task_fwd(nullptr, m.L[1].out, rows, W, m.L[2], out, ldout, ACT_NONE);
+    mk.fz_pending = (int)e.fz_pending.size();
+    return mk;
+  }
   for (int j = 0; j + 1 < n; ++j) {
     float* y = e.ws((size_t)rows * m.L[j].out);
     GemmTask lay = task_fwd(cur, ld, rows, W, m.L[j], y, m.L[j].out, hact);
@@ -89,6 +135,15 @@ void mlp_bwd(Engine& e, Program& p, const float* W, float* Gsec, const MlpLay& m
   const int n = (int)m.L.size();
   const float* dy = dpre;
   int lddy = m.L[n - 1].out;
+  if (n == 3 && fz_mlp_ok(m.L[0], m.L[1], m.L[2]) && h.size() == 2) {
+    const int H0 = m.L[0].out, H1 = m.L[1].out;
+    float* d1 = e.ws((size_t)rows * H1);
+    float* d0 = e.ws((size_t)rows * H0);
+    emit_fz(e, p, {fz_bwd_mid(dpre, lddy, rows, W, m.L[1], m.L[2], hact, h[0], H0, h[1], H1, d1, H1, d0, H0)});
+    emit_fz(e, p, {fz_wgrad(d1, H1, h[0], H0, rows, Gsec, m.L[1])});
+    emit_gemm(e, p, {task_wgrad(dpre, lddy, h[1], H1, rows, Gsec, m.L[2]), task_wgrad(d0, H0, X, ldx, rows, Gsec, m.L[0])});
+    return;
+  }
   for (int j = n - 1; j >= 0; --j) {
     const float* xin = j == 0 ? X : h[j - 1];
     const int ldin = j == 0 ? ldx : m.L[j - 1].out;
@@ -108,6 +163,9 @@ void mlp_bwd(Engine& e, Program& p, const float* W, float* Gsec, const MlpLay& m
 
 namespace osrl {
 void emit_stages(Engine& e, Program& p, std::vector<Stage>& st) {
-  for (auto& s : st) emit_gemm(e, p, s.tasks);
+  for (auto& s : st) {
+    emit_fz(e, p, s.fz);
+    emit_gemm(e, p, s.tasks);
+  }
 }
 }  // namespace osrl

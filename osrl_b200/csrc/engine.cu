@@ -3,6 +3,7 @@
 #include "gemm_mma.cuh"
 #include "gemm_tc5.cuh"
 #include "gemm_thin.cuh"
+#include "gemm_fz.cuh"
 #include "cdt_kernels.cuh"
 
 #include <dlfcn.h>
@@ -105,12 +106,14 @@ static void prepare_mma() {
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
 }
 // OSRL_GEMM (read when an engine's program is built): "ffma" = CUDA-core kernel (gemm.cuh); "mma" = 3xTF32
-// mma.sync kernel for everything; default = mma.sync + the tcgen05/TMEM kernel (gemm_tc5.cuh) for the large
-// forward layers.
+// mma.sync kernel for everything; "tc5" = mma.sync + the tcgen05/TMEM kernel (gemm_tc5.cuh) for the large forward
+// layers (round 1); default "fz" = the fused tcgen05 kernel (gemm_fz.cuh): whole 3-layer network passes in one launch,
+// every other tiled GEMM (all operand layouts) on tcgen05 as well.
 static std::string gemm_mode() {
   const char* e = getenv("OSRL_GEMM");
-  return e ? std::string(e) : std::string("tc5");
+  return e ? std::string(e) : std::string("fz");
 }
+bool fz_on() { return gemm_mode() == "fz"; }
 static bool use_mma() { return gemm_mode() != "ffma"; }
 static TaskPack make_pack(const std::vector<GemmTask>& tasks) {
   OSRL_REQUIRE(tasks.size() <= (size_t)PACK_MAX, "task pack overflow");
@@ -224,7 +227,27 @@ static void emit_tc5(Engine& e, Program& p, std::vector<GemmTask> tasks, bool ap
     ep->launches++;
   });
 }
+using FzKern = void (*)(const FzPack, int);
+static FzKern fz_kernel(int asrc, int bkc, int red) {
+  switch (asrc * 4 + bkc * 2 + red) {
+#define FZ_CASE(a, b, r) case a * 4 + b * 2 + r: return fz::k_fz<a, b, r>;
+    FZ_CASE(0, 0, 0) FZ_CASE(0, 0, 1) FZ_CASE(0, 1, 0) FZ_CASE(0, 1, 1)
+    FZ_CASE(1, 0, 0) FZ_CASE(1, 0, 1) FZ_CASE(1, 1, 0) FZ_CASE(1, 1, 1)
+    FZ_CASE(2, 0, 0) FZ_CASE(2, 0, 1) FZ_CASE(2, 1, 0) FZ_CASE(2, 1, 1)
+    FZ_CASE(3, 0, 0) FZ_CASE(3, 0, 1) FZ_CASE(3, 1, 0) FZ_CASE(3, 1, 1)
+#undef FZ_CASE
+  }
+  return nullptr;
+}
+static int fz_variant(const FzTask& t) {
+  const int asrc = t.a_gen == GEN_FIRST ? fz::A_FIRST : (t.a_gen == GEN_LASTD ? fz::A_LASTD : (t.a_kc ? fz::A_KC : fz::A_MC));
+  return asrc * 4 + (t.b_kc ? 2 : 0) + (t.red ? 1 : 0);
+}
 void prepare_kernels() {
+  // 227 KB per CTA minus the kernel's static shared memory (barriers + reduce-weight table, ~4.3 KB)
+  for (int v = 0; v < 16; ++v)
+    OSRL_CUDA(cudaFuncSetAttribute((const void*)fz_kernel(v >> 2, (v >> 1) & 1, v & 1),
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   prepare_gemm<OSRL_GEMM_CFG0>();
   prepare_gemm<OSRL_GEMM_CFG1>();
   prepare_gemm<OSRL_GEMM_CFG2>();
@@ -255,17 +278,182 @@ static int count_tiles(std::vector<GemmTask>& ts, int BM, int BN, bool assign) {
   }
   return tot;
 }
+
+// ------------------------------------------------------------------ fused tcgen05 path (gemm_fz.cuh)
+FzTask fz_blank() {
+  FzTask t;
+  memset(&t, 0, sizeof(t));
+  t.scale = 1.f; t.rscale = 1.f; t.a_kc = 1; t.b_kc = 1; t.c_store = 1;
+  return t;
+}
+bool fz_mlp_ok(const Lin& l0, const Lin& l1, const Lin& l2) {
+  return fz_on() && l0.in <= fz::GK_MAX && l2.out <= fz::RED_MAX && l0.out == l1.in && l1.out == l2.in &&
+         l1.in % 4 == 0 && l1.out % 4 == 0;
+}
+int fz_new_group() {
+  static int next = 0;
+  return ++next;
+}
+FzTask fz_from_gemm(const GemmTask& g) {
+  FzTask t = fz_blank();
+  t.A = g.A; t.B = g.B; t.C = g.C; t.M = g.M; t.N = g.N; t.K = g.K; t.lda = g.lda; t.ldb = g.ldb; t.ldc = g.ldc;
+  t.a_kc = g.a_kc; t.b_kc = g.b_kc;
+  t.bias = g.bias; t.resid = g.resid; t.dact_src = g.dact_src; t.aux = g.aux;
+  t.ldr = g.ldr; t.ld_dact = g.ld_dact; t.ldaux = g.ldaux; t.act = g.act; t.clamp = g.clamp; t.dact = g.dact;
+  t.scale = g.scale; t.lo = g.lo; t.hi = g.hi; t.colsum = g.colsum;
+  return t;
+}
+FzTask fz_fwd3(const float* X, int ldx, int rows, const float* W, const Lin& l0, const Lin& l1, const Lin& l2, int hact,
+               float* h1, int ldh1, float* h2, int ldh2, float* out, int ldo) {
+  FzTask t = fz_blank();
+  t.a_gen = GEN_FIRST; t.gx = X; t.ldgx = ldx; t.gk = l0.in; t.gw = W + l0.w; t.gw_ld = l0.in; t.gb = W + l0.b;
+  t.gact = hact; t.gstore = h1; t.ldgs = ldh1;
+  t.B = W + l1.w; t.ldb = l1.in; t.b_kc = 1;
+  t.M = rows; t.N = l1.out; t.K = l1.in;
+  t.bias = W + l1.b; t.act = hact;
+  t.C = h2; t.ldc = ldh2; t.c_store = h2 != nullptr;
+  t.red = 1; t.red_n = l2.out; t.rw = W + l2.w; t.rs_j = l2.in; t.rs_n = 1; t.rbias = W + l2.b;
+  t.r_group = fz_new_group(); t.r_slot0 = 0; t.r_slots = (l1.out + fz::BN - 1) / fz::BN;
+  t.rout = out; t.ldro = ldo;
+  return t;
+}
+FzTask fz_bwd_mid(const float* dq, int lddq, int rows, const float* W, const Lin& l1, const Lin& l2, int hact,
+                  const float* h1, int ldh1, const float* h2, int ldh2, float* d1, int ldd1, float* d0, int ldd0) {
+  FzTask t = fz_blank();
+  t.a_gen = GEN_LASTD; t.gx = dq; t.ldgx = lddq; t.gk = l2.out; t.gw = W + l2.w; t.gw_ld = l2.in; t.gact = hact;
+  t.gmask = h2; t.ldgm = ldh2; t.gstore = d1; t.ldgs = ldd1;
+  t.B = W + l1.w; t.ldb = l1.in; t.b_kc = 0;          // d0[r, j] = sum_k d1[r, k] W1[k, j]
+  t.M = rows; t.N = l1.in; t.K = l1.out;
+  t.dact = hact; t.dact_src = h1; t.ld_dact = ldh1;
+  t.C = d0; t.ldc = ldd0; t.c_store = d0 != nullptr;
+  return t;
+}
+void fz_add_dx(FzTask& t, int group, int member, int members, const float* W, const Lin& l0, int col0, int ncols,
+               float* dX, int lddx) {
+  OSRL_REQUIRE(ncols <= fz::RED_MAX && t.N == l0.out, "fz_add_dx: bad first layer");
+  const int tn = (t.N + fz::BN - 1) / fz::BN;
+  t.red = 1; t.red_n = ncols; t.rw = W + l0.w + col0; t.rs_j = 1; t.rs_n = l0.in;
+  t.r_group = group; t.r_slot0 = member * tn; t.r_slots = members * tn;
+  t.rout = dX; t.ldro = lddx;
+}
+FzTask fz_wgrad(const float* dY, int lddy, const float* X, int ldx, int rows, float* Gsec, const Lin& l) {
+  FzTask t = fz_blank();
+  t.A = dY; t.lda = lddy; t.a_kc = 0;
+  t.B = X; t.ldb = ldx; t.b_kc = 0;
+  t.C = Gsec + l.w; t.ldc = l.in;
+  t.M = l.out; t.N = l.in; t.K = rows;
+  t.colsum = Gsec + l.b;
+  return t;
+}
+void emit_fz(Engine& e, Program& p, std::vector<FzTask> tasks) {
+  if (tasks.empty()) return;
+  {   // one kernel variant per launch (gemm_fz.cuh): split the list by variant, keeping the order inside each
+    const int v0 = fz_variant(tasks[0]);
+    std::vector<FzTask> same, other;
+    for (auto& t : tasks) (fz_variant(t) == v0 ? same : other).push_back(t);
+    if (!other.empty()) {
+      emit_fz(e, p, same);
+      emit_fz(e, p, other);
+      return;
+    }
+  }
+  if (tasks.size() > (size_t)FZ_PACK) {
+    for (size_t i = 0; i < tasks.size(); i += FZ_PACK)
+      emit_fz(e, p, std::vector<FzTask>(tasks.begin() + i, tasks.begin() + std::min(tasks.size(), i + FZ_PACK)));
+    return;
+  }
+  int tot = 0, genf = 0;
+  double bytes = 0.0, flops = 0.0;
+  bool fused = false;
+  for (auto& t : tasks) {
+    OSRL_REQUIRE(t.M > 0 && t.N > 0 && t.K > 0, "empty fused gemm task");
+    const int tm = (t.M + fz::BM - 1) / fz::BM, tn = (t.N + fz::BN - 1) / fz::BN;
+    t.tile0 = tot; t.tiles_n = tn;
+    tot += tm * tn;
+    if (t.a_gen == GEN_NONE) {
+      OSRL_REQUIRE(t.A != nullptr, "fused gemm task without an A operand");
+      t.a_vec = ((uintptr_t)t.A % 16 == 0) && (t.lda % 4 == 0) && ((t.a_kc ? t.K : t.M) % 4 == 0);
+      OSRL_REQUIRE(t.a_vec, "fused gemm: A rows must be 16-byte aligned (bulk copies)");
+    } else {
+      OSRL_REQUIRE(t.gk >= 1 && t.gk <= fz::GK_MAX && t.K % 4 == 0, "A generation needs gk <= 16 and K % 4 == 0");
+      if (t.gstore) OSRL_REQUIRE((uintptr_t)t.gstore % 16 == 0 && t.ldgs % 4 == 0, "gstore must be 16-byte aligned");
+      if (t.a_gen == GEN_LASTD)
+        OSRL_REQUIRE(t.gmask && (uintptr_t)t.gmask % 16 == 0 && t.ldgm % 4 == 0, "gmask must be 16-byte aligned");
+      fused = true;
+    }
+    t.b_vec = ((uintptr_t)t.B % 16 == 0) && (t.ldb % 4 == 0) && ((t.b_kc ? t.K : t.N) % 4 == 0);
+    OSRL_REQUIRE(t.b_vec && t.K % 4 == 0, "fused gemm: B rows must be 16-byte aligned (bulk copies)");
+    t.epi_vec = (!t.c_store || ((uintptr_t)t.C % 16 == 0 && t.ldc % 4 == 0)) &&
+                (!t.dact || ((uintptr_t)t.dact_src % 16 == 0 && t.ld_dact % 4 == 0));
+    if (t.colsum) OSRL_REQUIRE(!t.a_kc && t.a_gen == GEN_NONE, "colsum needs an mn-contiguous A operand");
+    if (t.red) {
+      OSRL_REQUIRE(t.red_n >= 1 && t.red_n <= fz::RED_MAX && t.rout && t.r_group > 0 && t.r_slots >= tn, "bad reduce epilogue");
+      Engine::FzAlloc* al = nullptr;
+      for (auto& g : e.fz_groups)
+        if (g.first == t.r_group) al = &g.second;
+      if (!al) {
+        Engine::FzAlloc a;
+        a.rpart = e.ws((size_t)t.r_slots * t.M * t.red_n);
+        a.rcnt = (unsigned*)e.ws((size_t)tm);
+        e.fz_groups.push_back({t.r_group, a});
+        al = &e.fz_groups.back().second;
+      }
+      t.rpart = al->rpart; t.rcnt = al->rcnt;
+      fused = true;
+    }
+    genf = std::max(genf, fz::gen_floats(t));
+    const double kin = t.a_gen == GEN_NONE ? (double)t.K : (double)t.gk;   // operands actually read from memory
+    bytes += 4.0 * ((double)t.M * kin + (double)t.K * t.N + (t.c_store ? (double)t.M * t.N : 0.0) +
+                    (t.gstore ? (double)t.M * t.K : 0.0) + (t.red ? (double)t.M * t.red_n : 0.0));
+    flops += 2.0 * (double)t.M * t.N * t.K + 2.0 * (double)t.M * t.K * (t.a_gen ? t.gk : 0) +
+             2.0 * (double)t.M * t.N * (t.red ? t.red_n : 0);
+  }
+  FzPack d;
+  memset(&d, 0, sizeof(d));
+  for (size_t i = 0; i < tasks.size(); ++i) { d.t[i] = tasks[i]; d.tile0[i] = tasks[i].tile0; }
+  if (getenv("OSRL_FZ_DBG")) {   // kernel timeline (clock64 stamps per CTA), printed by osrl_debug_gemm
+    d.dbg = (long long*)e.ws((size_t)tot * 64 * 2);
+    e.fz_dbg = d.dbg; e.fz_dbg_ctas = tot;
+  }
+  const long long* dbg_buf = d.dbg;
+  const int nt = (int)tasks.size(), tiles = tot;
+  const int smem = fz::smem_fixed() + genf * 4;
+  OSRL_REQUIRE(smem <= 200 * 1024, "fused kernel: generation tables do not fit shared memory");
+  Engine* ep = &e;
+  const int var = fz_variant(tasks[0]);
+  const FzKern kern = fz_kernel(var >> 2, (var >> 1) & 1, var & 1);
+  static const char* an[4] = {"a_kc", "a_mc", "first", "lastd"};
+  const std::string name = std::string("k_fz<") + an[var >> 2] + ((var >> 1) & 1 ? ",b_kc" : ",b_nc") + (var & 1 ? ",red>" : ">");
+  (void)fused;
+  if (dbg_buf) e.fz_dbg_all.push_back({(long long*)dbg_buf, tot, name});
+  p.add(name, bytes, flops, true, [=](cudaStream_t s) {
+    kern<<<tiles, fz::THREADS, smem, s>>>(d, nt);
+    ep->launches++;
+  });
+}
 static void emit_tiled(Engine& e, Program& p, std::vector<GemmTask> tasks);
 void emit_gemm(Engine& e, Program& p, const std::vector<GemmTask>& tasks_in) {
   if (tasks_in.empty()) return;
   std::vector<GemmTask> tasks;
   {
     std::vector<GemmTask> thin;
+    std::vector<FzTask> fused;
     for (auto t : tasks_in) {
+      if (t.fz_pending > 0) {   // the last layer of a fused network: move its epilogue into the reduce epilogue
+        OSRL_REQUIRE(t.fz_pending <= (int)e.fz_pending.size(), "bad fused-network marker");
+        FzTask f = e.fz_pending[t.fz_pending - 1];
+        OSRL_REQUIRE(!t.dact && !t.colsum && !t.mmask, "unsupported epilogue on a fused last layer");
+        f.ract = t.act; f.rscale = t.scale; f.rresid = t.resid; f.ldrr = t.ldr;
+        f.rclamp = t.clamp; f.rlo = t.lo; f.rhi = t.hi; f.raux = t.aux; f.ldraux = t.ldaux;
+        f.rout = t.C; f.ldro = t.ldc;
+        fused.push_back(f);
+        continue;
+      }
       OSRL_REQUIRE(t.M > 0 && t.N > 0 && t.K > 0, "empty gemm task");
       t.thin = thin_kind(t);
       (t.thin ? thin : tasks).push_back(t);
     }
+    if (!fused.empty()) emit_fz(e, p, fused);
     if (!thin.empty()) emit_thin(e, p, thin);
     if (tasks.empty()) return;
   }
@@ -298,7 +486,19 @@ void emit_gemm(Engine& e, Program& p, const std::vector<GemmTask>& tasks_in) {
         if (cs) cudaMemsetAsync(cs, 0, sb, s);
       });
     }
-  if (gemm_mode() == "tc5") {   // large forward layers -> tcgen05 kernel, the rest stays on mma.sync
+  if (fz_on()) {   // every tiled problem the fused kernel's plain mode covers goes to tcgen05
+    std::vector<FzTask> fzt;
+    std::vector<GemmTask> rest;
+    for (auto& t : tasks) {
+      const bool full = t.act == ACT_GELU || t.dact == ACT_GELU || t.mmask != nullptr || t.ksplit > 1;
+      // (operand rows are fetched with 16-byte bulk copies: unaligned layouts, e.g. K = 41 first layers, stay on mma.sync)
+      if (full || (t.colsum && t.a_kc) || !t.a_vec || !t.b_vec || t.K % 4 != 0) rest.push_back(t);
+      else fzt.push_back(fz_from_gemm(t));
+    }
+    emit_fz(e, p, fzt);
+    if (rest.empty()) return;
+    tasks = rest;
+  } else if (gemm_mode() == "tc5") {   // large forward layers -> tcgen05 kernel, the rest stays on mma.sync
     std::vector<GemmTask> big, packed, rest;
     for (auto& t : tasks) {
       const Engine::PackReg* reg = nullptr;   // were these activations announced as packed hi/lo images?
@@ -462,10 +662,36 @@ EnsBuf ens_alloc(Engine& e, const EnsLay& l, int rows) {
   b.q = e.ws((size_t)rows * l.n);
   return b;
 }
+// member i of an ensemble as three plain layers (fused path)
+static void ens_member(const EnsLay& l, int i, Lin& l0, Lin& l1, Lin& l2) {
+  l0.in = l.in; l0.out = l.h[0];
+  l0.w = l.first.w + (int64_t)i * l.h[0] * l.in;
+  l0.b = l.first.b + (int64_t)i * l.h[0];
+  l1 = l.mid[0][i];
+  l2.in = l.h[1]; l2.out = 1;
+  l2.w = l.w_last + (int64_t)i * l.h[1];
+  l2.b = l.b_last + i;
+}
+static bool ens_fz_ok(const EnsLay& l) {
+  if (!fz_on() || l.h.size() != 2) return false;
+  Lin l0, l1, l2;
+  ens_member(l, 0, l0, l1, l2);
+  return fz_mlp_ok(l0, l1, l2);
+}
 void ens_fwd(std::vector<Stage>& st, const EnsLay& l, const float* W, const float* X, int ldx, int rows, EnsBuf& buf,
              bool nograd) {
   const int nh = (int)l.h.size();
   OSRL_REQUIRE((int)st.size() >= nh + 1, "ens_fwd: not enough stages");
+  if (ens_fz_ok(l)) {   // one fused launch: first layer generated, middle layer on tcgen05, Q head in the reduce epilogue
+    for (int i = 0; i < l.n; ++i) {
+      Lin l0, l1, l2;
+      ens_member(l, i, l0, l1, l2);
+      st[0].fz.push_back(fz_fwd3(X, ldx, rows, W, l0, l1, l2, ACT_RELU,
+                                 nograd ? nullptr : buf.h[0] + (size_t)i * l.h[0], l.n * l.h[0],
+                                 nograd ? nullptr : buf.h[1] + (size_t)i * l.h[1], l.n * l.h[1], buf.q + i, l.n));
+    }
+    return;
+  }
   GemmTask first = task_fwd(X, ldx, rows, W, l.first, buf.h[0], l.n * l.h[0], ACT_RELU);
   if (nograd && nh > 1) { first.pk_gcols = l.h[0]; first.c_dead = 1; }
   st[0].tasks.push_back(first);
@@ -486,6 +712,28 @@ void ens_bwd(std::vector<Stage>& st, const EnsLay& l, const float* W, float* Gse
              const EnsBuf& act, EnsBuf& grad, const float* dq, float* dX, int lddx, int xcol0, int xcols) {
   const int nh = (int)l.h.size();
   OSRL_REQUIRE((int)st.size() >= nh + 1, "ens_bwd: not enough stages");
+  if (ens_fz_ok(l) && (!dX || xcols <= fz::RED_MAX)) {
+    // stage 0: per member, last-layer dgrad generated -> middle-layer dgrad on tcgen05 -> (input gradient summed over
+    // the ensemble in the reduce epilogue); stage 1: weight gradients (middle layers on tcgen05, thin ones beside)
+    const int grp = dX ? fz_new_group() : 0;
+    for (int i = 0; i < l.n; ++i) {
+      Lin l0, l1, l2;
+      ens_member(l, i, l0, l1, l2);
+      FzTask t = fz_bwd_mid(dq + i, l.n, rows, W, l1, l2, ACT_RELU, act.h[0] + (size_t)i * l.h[0], l.n * l.h[0],
+                            act.h[1] + (size_t)i * l.h[1], l.n * l.h[1],
+                            Gsec ? grad.h[1] + (size_t)i * l.h[1] : nullptr, l.n * l.h[1],
+                            Gsec ? grad.h[0] + (size_t)i * l.h[0] : nullptr, l.n * l.h[0]);
+      if (dX) fz_add_dx(t, grp, i, l.n, W, l0, xcol0, xcols, dX, lddx);
+      st[0].fz.push_back(t);
+      if (Gsec) {
+        st[1].fz.push_back(fz_wgrad(grad.h[1] + (size_t)i * l.h[1], l.n * l.h[1], act.h[0] + (size_t)i * l.h[0],
+                                    l.n * l.h[0], rows, Gsec, l1));
+        st[1].tasks.push_back(task_wgrad(dq + i, l.n, act.h[1] + (size_t)i * l.h[1], l.n * l.h[1], rows, Gsec, l2));
+      }
+    }
+    if (Gsec) st[1].tasks.push_back(task_wgrad(grad.h[0], l.n * l.h[0], X, ldx, rows, Gsec, l.first));
+    return;
+  }
   // last layer (1 unit): dH = dq (x) w_last, masked by relu'(H)
   for (int i = 0; i < l.n; ++i) {
     Lin last;
@@ -1359,6 +1607,21 @@ int osrl_debug_gemm(osrl_engine* h, const char* impl, int M, int N, int K, const
             N, K, a_kc, b_kc, ms * 1e3f / reps, prog.ops.size(), reps);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
   }
+  if (e.fz_dbg) {
+    std::vector<long long> h((size_t)e.fz_dbg_ctas * 64);
+    OSRL_CUDA(cudaMemcpy(h.data(), e.fz_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < std::min(e.fz_dbg_ctas, 3); ++c) {
+      const long long* r = h.data() + (size_t)c * 64;
+      fprintf(stderr, "[fz timeline cta %d] (cycles since start) setup %lld tables %lld |", c, r[1] - r[0], r[2] - r[0]);
+      for (int k = 0; k < 8; ++k) fprintf(stderr, " st%d %lld..%lld", k, r[8 + 2 * k] - r[0], r[9 + 2 * k] - r[0]);
+      fprintf(stderr, " | loop_end %lld acc %lld ph1 %lld ph2 %lld ph3 %lld end %lld\n", r[3] - r[0], r[4] - r[0], r[5] - r[0],
+              r[6] - r[0], r[7] - r[0], r[63] - r[0]);
+      fprintf(stderr, "[fz timeline cta %d] mma:", c);
+      for (int k = 0; k < 8; ++k) fprintf(stderr, " k%d %lld..%lld", k, r[32 + 2 * k] - r[0], r[33 + 2 * k] - r[0]);
+      fprintf(stderr, "\n");
+    }
+    e.fz_dbg = nullptr;
+  }
   OSRL_CUDA(cudaMemcpy(C, dC, (size_t)M * N * sizeof(float), cudaMemcpyDeviceToHost));
   if (colsum) OSRL_CUDA(cudaMemcpy(colsum, dS, (size_t)M * sizeof(float), cudaMemcpyDeviceToHost));
   while (e.allocs.size() > before) { cudaFree(e.allocs.back()); e.allocs.pop_back(); }
@@ -1413,6 +1676,32 @@ int osrl_profile(osrl_engine* h, int reps, int* n_ops, const char** names, doubl
     if (names) names[i] = e.body.meta[i].name.c_str();
     if (bytes) bytes[i] = e.body.meta[i].bytes;
     if (flops) flops[i] = e.body.meta[i].flops;
+  }
+  OSRL_CATCH
+}
+
+int osrl_debug_fz_timelines(osrl_engine* h) {
+  OSRL_TRY
+  OSRL_REQUIRE(h, "null argument");
+  Engine& e = *h->e;
+  OSRL_CUDA(cudaSetDevice(e.device));
+  OSRL_CUDA(cudaDeviceSynchronize());
+  int idx = 0;
+  for (auto& dbg : e.fz_dbg_all) {
+    std::vector<long long> hbuf((size_t)dbg.ctas * 64);
+    OSRL_CUDA(cudaMemcpy(hbuf.data(), dbg.buf, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    long long worst = 0;
+    int wc = 0;
+    for (int c = 0; c < dbg.ctas; ++c) {
+      const long long d = hbuf[(size_t)c * 64 + 63] - hbuf[(size_t)c * 64];
+      if (d > worst) { worst = d; wc = c; }
+    }
+    const long long* r = hbuf.data() + (size_t)wc * 64;
+    fprintf(stderr, "[fz %2d %-22s ctas %4d] slowest cta %d: setup %lld tables %lld |", idx++, dbg.name.c_str(), dbg.ctas, wc,
+            r[1] - r[0], r[2] - r[0]);
+    for (int k = 0; k < 8; k += 1) fprintf(stderr, " %lld..%lld", r[8 + 2 * k] - r[0], r[9 + 2 * k] - r[0]);
+    fprintf(stderr, " | loop_end %lld acc %lld ph1 %lld ph2 %lld ph3 %lld end %lld\n", r[3] - r[0], r[4] - r[0], r[5] - r[0],
+            r[6] - r[0], r[7] - r[0], r[63] - r[0]);
   }
   OSRL_CATCH
 }

@@ -9,6 +9,7 @@
 
 #include "../../include/osrl_b200.h"
 #include "gemm.cuh"
+#include "gemm_fz.cuh"
 #include "kernels.cuh"
 
 namespace osrl {
@@ -177,6 +178,15 @@ struct Engine {
   struct PackReg { const float* C; int ldc, M, N, gcols, gstride, ks, dead; float* hi; float* lo; };
   std::vector<PackReg> pack_regs;
   int64_t launches = 0;
+  // fused tcgen05 path (gemm_fz.cuh): networks whose last layer is still being described by the caller
+  // (mlp_fwd_hidden returns a marker GemmTask, emit_gemm completes and launches the fused task)
+  std::vector<FzTask> fz_pending;
+  long long* fz_dbg = nullptr;   // OSRL_FZ_DBG timeline of the last fused launch (debug)
+  int fz_dbg_ctas = 0;
+  struct FzDbg { long long* buf; int ctas; std::string name; };
+  std::vector<FzDbg> fz_dbg_all;
+  struct FzAlloc { float* rpart; unsigned* rcnt; };
+  std::vector<std::pair<int, FzAlloc>> fz_groups;   // reduce-group id -> partial-sum buffers (emit_fz)
   // data parallel
   void* comm = nullptr;
   void* comm2 = nullptr;   // pipelined VAE branch
@@ -197,7 +207,28 @@ struct Engine {
 // program-building helpers (engine.cu)
 struct Stage {
   std::vector<GemmTask> tasks;
+  std::vector<FzTask> fz;   // fused tcgen05 tasks of this stage (launched before `tasks`)
 };
+// ---- fused path (engine.cu).  fz_on(): OSRL_GEMM=fz (the default).  A network qualifies when it has two hidden
+// layers whose widths are multiples of 4 (16-byte rows), a first layer of <= 16 inputs and a last one of <= 16 outputs.
+bool fz_on();
+bool fz_mlp_ok(const Lin& l0, const Lin& l1, const Lin& l2);
+FzTask fz_blank();
+// forward of a whole 3-layer network: X [rows, l0.in] -> act(l0) -> act(l1) -> l2 -> out [rows, l2.out].
+// h1 / h2 (optional): fp32 copies of the hidden activations for the backward pass.  The final epilogue
+// (FzTask::ract / rscale / rresid / rclamp / raux) is the caller's to set.
+FzTask fz_fwd3(const float* X, int ldx, int rows, const float* W, const Lin& l0, const Lin& l1, const Lin& l2, int hact,
+               float* h1, int ldh1, float* h2, int ldh2, float* out, int ldo);
+// backward through the last and middle layers: dq [rows, l2.out] -> d1 = (dq W2) * act'(h2) (stored if d1 given)
+// -> d0 = (d1 W1) * act'(h1) (stored if d0 given).  fz_add_dx() then folds the first layer's input gradient in.
+FzTask fz_bwd_mid(const float* dq, int lddq, int rows, const float* W, const Lin& l1, const Lin& l2, int hact,
+                  const float* h1, int ldh1, const float* h2, int ldh2, float* d1, int ldd1, float* d0, int ldd0);
+// dX [rows, ncols] = sum over the `members` tasks of a group of  d0 W0[:, col0 : col0+ncols]
+int fz_new_group();
+void fz_add_dx(FzTask& t, int group, int member, int members, const float* W, const Lin& l0, int col0, int ncols,
+               float* dX, int lddx);
+FzTask fz_wgrad(const float* dY, int lddy, const float* X, int ldx, int rows, float* Gsec, const Lin& l);
+void emit_fz(Engine& e, Program& p, std::vector<FzTask> tasks);
 GemmTask task_fwd(const float* X, int ldx, int rows, const float* W, const Lin& l, float* Y, int ldy, int act,
                   float scale = 1.f);
 GemmTask task_dgrad(const float* dY, int lddy, int rows, const float* W, const Lin& l, float* dX, int lddx,

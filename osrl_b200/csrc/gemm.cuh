@@ -60,6 +60,8 @@ struct GemmTask {
   int c_dead;             // producer hint: nothing reads C except through the packed images -> skip the fp32 store
   const float* mmask;     // [M, ldmm] optional multiplier applied after act*scale, before the residual add (dropout)
   int ldmm;
+  int fz_pending;         // > 0: marker for Engine::fz_pending[fz_pending - 1] -- this task only carries the last layer's
+                          // epilogue of a fused network (gemm_fz.cuh); emit_gemm completes and launches the fused task
 };
 __host__ __device__ __forceinline__ size_t pk_offset(int row, int col, int ks_per_rb) {   // float offset in an image set
   const int rb = row >> 6, r = row & 63, ks = col >> 5, c = col & 31;

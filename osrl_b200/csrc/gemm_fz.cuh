@@ -40,6 +40,7 @@ struct FzTask {
   int ldr, ld_dact, ldaux, act, clamp, dact;
   float scale, lo, hi;
   int c_store;             // 0: C is not written (only the reduce epilogue consumes the tile)
+  int epi_vec;             // C / dact_src rows are 16-byte aligned (host-computed): float4 epilogue accesses
   float* colsum;           // [M] sum_k A[m,k] (bias gradient; a_kc == 0 only), written by the tn == 0 tiles
   // ---- A generation
   int a_gen;               // FzGen
@@ -55,6 +56,7 @@ struct FzTask {
   float* rpart;                        // [r_slots][M][red_n] partial sums
   unsigned* rcnt;                      // [ceil(M/128)] arrival counters (zero between launches)
   int r_slot0, r_slots;
+  int r_group;                         // host only: tasks with the same id share rpart / rcnt (allocated by emit_fz)
   const float* rbias;
   int ract, rclamp; float rscale, rlo, rhi;
   const float* rresid; int ldrr;
@@ -63,70 +65,154 @@ struct FzTask {
   int tile0, tiles_n;
 };
 constexpr int FZ_PACK = 16;
-struct FzPack { FzTask t[FZ_PACK]; };
+struct FzPack {
+  int tile0[FZ_PACK];   // first tile of every task, packed: the owner lookup touches one constant-cache line, not sixteen
+  FzTask t[FZ_PACK];
+  long long* dbg;       // optional per-CTA clock64 timeline (64 slots per CTA)
+};
 static_assert(sizeof(FzPack) <= 16000, "task pack is a kernel parameter");
 
 namespace fz {
 
 using tc5::mbar_init; using tc5::mbar_arrive; using tc5::mbar_wait; using tc5::make_desc; using tc5::mma_tf32_ss;
-using tc5::commit; using tc5::rna_tf32; using tc5::split4; using tc5::smem_u32;
+using tc5::commit; using tc5::smem_u32;
 
 constexpr int BM = 128, BN = 64, BK = 32;
-constexpr int PRODUCERS = 256, THREADS = PRODUCERS + 32;
-constexpr int A_T = BM * BK * 4, B_T = BN * BK * 4;
-constexpr int STAGE_BYTES = 2 * A_T + 2 * B_T;   // 48 KB
+constexpr int CONV = 512;                         // converter / epilogue threads (warps 0-15): the k-loop is bound by
+                                                  // their instruction issue, so there are four per scheduler
+constexpr int LOADERS = 128;                      // loader threads (4 warps)
+constexpr int THREADS = CONV + 32 + LOADERS;      // converters, MMA issuer warp, loaders
+constexpr int B_T = BN * BK * 4;
+constexpr int STAGE_BYTES = 2 * B_T;              // operand stage in shared memory: {B_hi, B_lo}, 16 KB
+constexpr int NOP = 3;                            // operand stages (B in shared memory, A in tensor memory)
+constexpr int NRAW = 3;                           // raw (fp32, as stored in global memory) stages
+// raw tiles keep global row order with a padded row stride so that the converters' shared loads are conflict-free:
+//   k-contiguous operand  rows x 32 floats, stride 36;   mn-contiguous operand  32 k-rows x rows floats, stride rows + 8
+constexpr int RAW_KC_LD = 36, RAW_A_MC_LD = BM + 8, RAW_B_NC_LD = BN + 8;
+constexpr int RAW_A_BYTES = BM * RAW_KC_LD * 4;   // 18432 (>= 32 * 136 * 4)
+constexpr int RAW_B_BYTES = BN * RAW_KC_LD * 4;   // 9216  (== 32 * 72 * 4)
+constexpr int RAW_STAGE = RAW_A_BYTES + RAW_B_BYTES;
 constexpr int TP = BN + 4;
-constexpr int TMEM_COLS = 256;                   // three 64-column accumulators
+// Tensor memory: three 64-column accumulators, then per operand stage the A slab as the MMA's TMEM operand -- 128 rows
+// (lanes) x 32 k (columns), hi and lo.  A never touches shared memory: with A and B both in shared memory a k-slab
+// cost ~1350 shared-memory wavefronts (raw slab in/out, hi/lo stores, 12 MMAs re-reading a 4 KB A and a 2 KB B tile)
+// and the slab time WAS that number; A in TMEM removes the A stores and the MMAs' A reads (~640 wavefronts).
+constexpr int TMEM_COLS = 512;
+constexpr int TM_ACC = 0, TM_A = 3 * BN;          // column of stage s: hi at TM_A + s*64, lo at TM_A + s*64 + 32
 constexpr int RED_MAX = 16, GK_MAX = 16;
+constexpr int XS_LD = GK_MAX + 1;
 constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-static inline int gen_floats(const FzTask& t) {   // shared-memory floats of the generation tables
+static inline int gen_floats(const FzTask& t) {   // shared-memory floats of the generation tables + input rows
   if (t.a_gen == GEN_NONE) return 0;
   const int kpad = (t.K + BK - 1) / BK * BK;
-  return (t.gk + 1) * kpad;
+  return (t.gk + 1) * kpad + BM * XS_LD;
 }
-template <int NSTAGE>
-constexpr int ring_bytes() { return NSTAGE * STAGE_BYTES; }
+constexpr int smem_fixed() { return NOP * STAGE_BYTES + NRAW * RAW_STAGE + 1024; }   // (the epilogue tile reuses the raw ring)
 
 __device__ __forceinline__ int find_task(const FzPack& P, int ntasks, int tile) {
   int ti = 0;
 #pragma unroll
   for (int i = 1; i < FZ_PACK; ++i)
-    if (i < ntasks && P.t[i].tile0 <= tile) ti = i;
+    if (i < ntasks && P.tile0[i] <= tile) ti = i;
   return ti;
-}
-__device__ __forceinline__ float4 ld4_guard(const float* p, bool ok, bool vec, int nvalid) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (!ok) return v;
-  if (vec) return *reinterpret_cast<const float4*>(p);
-  v.x = p[0];
-  if (nvalid > 1) v.y = p[1];
-  if (nvalid > 2) v.z = p[2];
-  if (nvalid > 3) v.w = p[3];
-  return v;
 }
 __device__ __forceinline__ float dact_mul(float v, float h, int kind) {   // v * act'(.) from the stored activation
   return kind == ACT_RELU ? (h > 0.f ? v : 0.f) : (kind == ACT_TANH ? v * (1.f - h * h) : v);
 }
 // k-major SWIZZLE_128B tile: byte offset of 16-byte chunk ck (0..7) of row r
 __device__ __forceinline__ int sw_off(int r, int ck) { return (r >> 3) * 1024 + (r & 7) * 128 + ((ck ^ (r & 7)) << 4); }
+// tf32 rounding to nearest (ties away, what cvt.rna.tf32.f32 does) with two integer ALU ops: ptxas expands the cvt
+// into an ~8-instruction sequence, and a k-step converts 6144 operand elements twice
+__device__ __forceinline__ float rnd_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
+  hi.x = rnd_tf32(v.x); hi.y = rnd_tf32(v.y); hi.z = rnd_tf32(v.z); hi.w = rnd_tf32(v.w);
+  lo.x = rnd_tf32(v.x - hi.x); lo.y = rnd_tf32(v.y - hi.y); lo.z = rnd_tf32(v.z - hi.z); lo.w = rnd_tf32(v.w - hi.w);
+}
+// explicit shared-space accesses (32-bit shared addresses): the operand ring is addressed arithmetically, and the
+// compiler otherwise falls back to generic ST / LD
+__device__ __forceinline__ void sts128(uint32_t a, const float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+// 16 consecutive 32-bit columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+               "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor]
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_c),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async16z(uint32_t dst, const void* src, bool valid) {   // zero-fills when !valid
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
 
-template <int NSTAGE, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) k_fz(const __grid_constant__ FzPack P, int ntasks) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[NSTAGE], empty_bar[NSTAGE], acc_bar;
+// Kernel variants are compile-time: the operand source (ASRC), the B layout (BKC) and the reduce epilogue (RED) are
+// template parameters and a launch only holds tasks of one variant (a single kernel with run-time branches was
+// 180 KB of SASS and stalled on instruction fetch).
+//
+// Warp roles.  Warp 9 (loader): streams the operands exactly as they lie in global memory into the raw ring with
+// 16-byte cp.async copies (completion counted on an mbarrier) -- NRAW k-slabs ahead, no registers, and, unlike register
+// prefetching, invisible to the membar that fence.proxy.async implies (a producer that prefetched through registers
+// paid one L2 round trip per k-slab there).  Warps 0-7 (converters): raw slab -> hi/lo tf32 split ->
+// swizzled operand stage (or generate the A operand), fence.proxy.async, arrive.  Warp 8: one lane issues the MMAs.
+enum ASrc { A_KC = 0, A_MC = 1, A_FIRST = 2, A_LASTD = 3 };
+
+template <int ASRC, int BKC, int RED>
+__global__ void __launch_bounds__(THREADS, 1) k_fz(const __grid_constant__ FzPack P, int ntasks) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t op_full[NOP], op_empty[NOP], raw_full[NRAW], raw_empty[NRAW], acc_bar;
   __shared__ uint32_t tmem_base_s;
   __shared__ int last_flag;
-  __shared__ float rws[RED_MAX * BN];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  float* gen_s = reinterpret_cast<float*>(smem + NSTAGE * STAGE_BYTES);
+  __shared__ __align__(16) float rws[RED ? RED_MAX * BN : 4];
+  __shared__ float cs_s[ASRC == A_MC ? 4 * BM : 1];
+  constexpr bool GEN = ASRC == A_FIRST || ASRC == A_LASTD;
+  constexpr bool RAW_A = ASRC != A_FIRST;       // (A_LASTD: the raw A slab holds the stored activations h2)
+
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;   // operand ring (SWIZZLE_128B: 1 KB aligned)
+  const uint32_t rbase = sbase + NOP * STAGE_BYTES;                 // raw ring
+  const uint32_t gbase = rbase + NRAW * RAW_STAGE;                  // generation tables
+  uint8_t* smem_gen = smem_raw + (gbase - smem_u32(smem_raw));
+  float* gen_s = reinterpret_cast<float*>(smem_gen);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long* dbg = P.dbg ? P.dbg + (size_t)blockIdx.x * 64 : nullptr;
+#define FZ_STAMP(slot) do { if (dbg && tid == 0) dbg[slot] = clock64(); } while (0)
+#define FZ_STAMP_MMA(slot) do { if (dbg) dbg[slot] = clock64(); } while (0)
+  FZ_STAMP(0);
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) {
-      mbar_init(&full_bar[s], PRODUCERS / 32);
-      mbar_init(&empty_bar[s], 1);
-    }
+    for (int s = 0; s < NOP; ++s) { mbar_init(&op_full[s], CONV / 32); mbar_init(&op_empty[s], 1); }
+    for (int s = 0; s < NRAW; ++s) { mbar_init(&raw_full[s], LOADERS); mbar_init(&raw_empty[s], CONV / 32); }
     mbar_init(&acc_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -139,6 +225,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_fz(const __grid_constant__ Fz
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
+  FZ_STAMP(1);
   const FzTask& t = P.t[find_task(P, ntasks, blockIdx.x)];
   const int lt = blockIdx.x - t.tile0;
   const int tm = lt / t.tiles_n, tn = lt % t.tiles_n;
@@ -146,244 +233,237 @@ __global__ void __launch_bounds__(THREADS, MINB) k_fz(const __grid_constant__ Fz
   const int M = t.M, N = t.N, K = t.K;
   const int nk = (K + BK - 1) / BK, kpad = nk * BK;
 
-  if (warp < PRODUCERS / 32) {
-    const int gen = t.a_gen, gk = t.gk;
-    // ------------------------------------------------ tables: generation weights, reduce weights
-    if (gen == GEN_FIRST) {        // W1^T [gk][kpad] then b1 [kpad], zero padded
-      const float* __restrict__ gw = t.gw;
-      const int gwld = t.gw_ld;
-      for (int e = tid; e < gk * kpad; e += PRODUCERS) {
-        const int k = e / gk, i = e - k * gk;       // consecutive threads read consecutive floats of W1
-        gen_s[i * kpad + k] = k < K ? gw[(size_t)k * gwld + i] : 0.f;
+  if (warp > CONV / 32) {
+    // ------------------------------------------------ loaders: 16-byte cp.async pieces, NRAW slabs in flight; a slab's
+    // arrival is counted on raw_full by cp.async.mbarrier.arrive (one per loader thread).  (One cp.async.bulk per
+    // 128-byte row was tried first: the copy engine serialises small requests at ~55 cycles each, 10 k cycles per slab;
+    // a single loader warp needed ~2 k cycles to issue a slab's 48 copies per lane.)
+    const int lt_ = tid - (CONV + 32);
+    const float* __restrict__ Asrc = ASRC == A_LASTD ? t.gmask : t.A;
+    const int lda = ASRC == A_LASTD ? t.ldgm : t.lda, ldb = t.ldb;
+    const float* __restrict__ B = t.B;
+    // per-thread piece coordinates (fixed over the k-loop)
+    const int a_r = ASRC == A_MC ? (lt_ >> 5) : (lt_ >> 3), a_c = ASRC == A_MC ? (lt_ & 31) : (lt_ & 7);
+    const int b_r = BKC ? (lt_ >> 3) : (lt_ >> 4), b_c = BKC ? (lt_ & 7) : (lt_ & 15);
+    for (int kt = 0; kt < nk; ++kt) {
+      const int s = kt % NRAW, k0 = kt * BK;
+      if (kt >= NRAW) mbar_wait(&raw_empty[s], ((kt / NRAW) - 1) & 1);
+      const uint32_t ra = rbase + s * RAW_STAGE, rb = ra + RAW_A_BYTES;
+      if constexpr (RAW_A) {
+        if constexpr (ASRC == A_MC) {   // pieces (k-row a_r + 4i, m-chunk a_c)
+          const bool okm = m0 + a_c * 4 < M;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int kr = a_r + 4 * i;
+            const bool ok = okm && (k0 + kr < K);
+            cp_async16z(ra + (kr * RAW_A_MC_LD + a_c * 4) * 4, ok ? Asrc + (size_t)(k0 + kr) * lda + m0 + a_c * 4 : Asrc, ok);
+          }
+        } else {                        // pieces (row a_r + 16i, k-chunk a_c)
+          const bool okk = k0 + a_c * 4 < K;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = a_r + 16 * i;
+            const bool ok = okk && (m0 + r < M);
+            cp_async16z(ra + (r * RAW_KC_LD + a_c * 4) * 4, ok ? Asrc + (size_t)(m0 + r) * lda + k0 + a_c * 4 : Asrc, ok);
+          }
+        }
       }
-      for (int k = tid; k < kpad; k += PRODUCERS) gen_s[gk * kpad + k] = (k < K && t.gb) ? t.gb[k] : 0.f;
-    } else if (gen == GEN_LASTD) { // W3 [gk][kpad]
+      if constexpr (BKC) {
+        const bool okk = k0 + b_c * 4 < K;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = b_r + 16 * i;
+          const bool ok = okk && (n0 + r < N);
+          cp_async16z(rb + (r * RAW_KC_LD + b_c * 4) * 4, ok ? B + (size_t)(n0 + r) * ldb + k0 + b_c * 4 : B, ok);
+        }
+      } else {
+        const bool okn = n0 + b_c * 4 < N;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int kr = b_r + 8 * i;
+          const bool ok = okn && (k0 + kr < K);
+          cp_async16z(rb + (kr * RAW_B_NC_LD + b_c * 4) * 4, ok ? B + (size_t)(k0 + kr) * ldb + n0 + b_c * 4 : B, ok);
+        }
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&raw_full[s])) : "memory");
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp < CONV / 32) {
+    const int gk = t.gk;
+    float* xs = gen_s;
+    // ------------------------------------------------ tables: generation weights, reduce weights
+    if constexpr (ASRC == A_FIRST) {        // W1^T [gk][kpad] then b1 [kpad], zero padded
       const float* __restrict__ gw = t.gw;
       const int gwld = t.gw_ld;
-      for (int e = tid; e < gk * kpad; e += PRODUCERS) {
-        const int j = e / kpad, k = e - j * kpad;
-        gen_s[e] = k < K ? gw[(size_t)j * gwld + k] : 0.f;
+      for (int k = tid; k < kpad; k += CONV) {      // thread = one row of W1: gk contiguous floats in, a column of W1^T out
+        const float* __restrict__ src = gw + (size_t)k * gwld;
+#pragma unroll 4
+        for (int i = 0; i < gk; ++i) gen_s[i * kpad + k] = k < K ? src[i] : 0.f;
+        gen_s[gk * kpad + k] = (k < K && t.gb) ? t.gb[k] : 0.f;
+      }
+    } else if constexpr (ASRC == A_LASTD) { // W3 [gk][kpad]
+      const float* __restrict__ gw = t.gw;
+      const int gwld = t.gw_ld;
+      for (int j = 0; j < gk; ++j)
+        for (int k = tid; k < kpad; k += CONV) gen_s[j * kpad + k] = k < K ? gw[(size_t)j * gwld + k] : 0.f;
+    }
+    if constexpr (GEN) {
+      xs = gen_s + (gk + 1) * kpad;
+      if (tid < BM) {
+        const bool ok = m0 + tid < M;
+        const float* __restrict__ src = t.gx + (size_t)(m0 + (ok ? tid : 0)) * t.ldgx;
+#pragma unroll 4
+        for (int i = 0; i < gk; ++i) xs[tid * XS_LD + i] = ok ? src[i] : 0.f;
       }
     }
-    if (t.red) {
+    if constexpr (RED) {
       const float* __restrict__ rw = t.rw;
-      for (int e = tid; e < t.red_n * BN; e += PRODUCERS) {
+      for (int e = tid; e < t.red_n * BN; e += CONV) {
         const int j = e / BN, n = e - j * BN;
         rws[e] = (n0 + n < N) ? rw[(size_t)j * t.rs_j + (size_t)(n0 + n) * t.rs_n] : 0.f;
       }
     }
-    // per-thread row of the generation input: thread = (row r = tid/2, k-half = tid%2)
-    const int gr = tid >> 1, gh = tid & 1;
-    float xr[GK_MAX];
-#pragma unroll
-    for (int i = 0; i < GK_MAX; ++i) xr[i] = 0.f;
-    if (gen != GEN_NONE && m0 + gr < M) {
-      const float* __restrict__ xp = t.gx + (size_t)(m0 + gr) * t.ldgx;
-#pragma unroll
-      for (int i = 0; i < GK_MAX; ++i)
-        if (i < gk) xr[i] = xp[i];
-    }
-    if (gen != GEN_NONE || t.red) asm volatile("bar.sync 1, %0;" ::"n"(PRODUCERS) : "memory");
+    // A operand: thread = (row = this warp's TMEM lane quarter * 32 + lane, k-quarter of the 32-float slab)
+    const int row = (warp & 3) * 32 + lane, kq = warp >> 2;
+    if constexpr (GEN || RED) asm volatile("bar.sync 1, %0;" ::"n"(CONV) : "memory");
+    FZ_STAMP(2);
 
-    const float* __restrict__ A = t.A;
-    const float* __restrict__ B = t.B;
-    const int lda = t.lda, ldb = t.ldb;
-    const bool akc = t.a_kc != 0, bkc = t.b_kc != 0, avec = t.a_vec != 0, bvec = t.b_vec != 0;
-    const bool want_cs = (t.colsum != nullptr) && tn == 0 && !akc && gen == GEN_NONE;
-    const bool gstore = (t.gstore != nullptr) && tn == 0;
-    float cs[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) cs[i] = 0.f;
+    const bool want_cs = ASRC == A_MC && (t.colsum != nullptr) && tn == 0;
+    const bool gstore = GEN && (t.gstore != nullptr) && tn == 0;
+    float cs = 0.f;
+    const int m7 = lane >> 2, k3 = lane & 3;   // transposing B converter: lane = (n low bits, k low bits)
+    const bool rowok = m0 + row < M;
 
-    auto load = [&](int kt, float4 (&va)[4], float4 (&vb)[2]) {
-      const int k0 = kt * BK;
-      if (gen == GEN_LASTD) {            // stored activations whose derivative masks the generated values
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int k = k0 + gh * 16 + 4 * i;
-          va[i] = ld4_guard(t.gmask + (size_t)(m0 + gr) * t.ldgm + k, (m0 + gr < M) && k < K, true, 4);
-        }
-      } else if (gen == GEN_NONE) {
-        if (akc) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int c = tid + PRODUCERS * i, r = c >> 3, ck = c & 7;
-            const int gkk = k0 + ck * 4;
-            va[i] = ld4_guard(A + (size_t)(m0 + r) * lda + gkk, (m0 + r < M) && gkk < K, avec, K - gkk);
-          }
-        } else {                         // A[k*lda + m]: lane = k, this warp's 16 m's as four float4
-          const int k = k0 + lane;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int m = m0 + warp * 16 + 4 * i;
-            va[i] = ld4_guard(A + (size_t)k * lda + m, k < K && m < M, avec, M - m);
-          }
-        }
+    for (int kt = 0; kt < nk; ++kt) {
+      const int so = kt % NOP, sr = kt % NRAW, k0 = kt * BK;
+      mbar_wait(&raw_full[sr], (kt / NRAW) & 1);
+      if (kt >= NOP) {
+        mbar_wait(&op_empty[so], ((kt / NOP) - 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
-      if (bkc) {
+      if (kt < 8) FZ_STAMP(8 + 2 * kt);
+      const uint32_t st = sbase + so * STAGE_BYTES;
+      const uint32_t ra = rbase + sr * RAW_STAGE, rb = ra + RAW_A_BYTES;
+      // ---- A operand: 8 values of this thread's row -> hi / lo -> tensor memory
+      float av[8];
+      if constexpr (GEN) {
+        float4 g[2];
+        const float* __restrict__ wt = gen_s + k0 + kq * 8;
+        const float* __restrict__ xrow = xs + row * XS_LD;
+        const int ga = t.gact;
+        g[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        g[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+        for (int i = 0; i < gk; ++i) {      // (run-time trip count keeps the loop body small)
+          const float x = xrow[i];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int c = tid + PRODUCERS * i, r = c >> 3, ck = c & 7;
-          const int gkk = k0 + ck * 4;
-          vb[i] = ld4_guard(B + (size_t)(n0 + r) * ldb + gkk, (n0 + r < N) && gkk < K, bvec, K - gkk);
-        }
-      } else {                           // B[k*ldb + n]: lane = k, this warp's 8 n's as two float4
-        const int k = k0 + lane;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int n = n0 + warp * 8 + 4 * i;
-          vb[i] = ld4_guard(B + (size_t)k * ldb + n, k < K && n < N, bvec, N - n);
-        }
-      }
-    };
-    auto store = [&](int kt, const float4 (&va)[4], const float4 (&vb)[2]) {
-      const int s = kt % NSTAGE, k0 = kt * BK;
-      if (kt >= NSTAGE) mbar_wait(&empty_bar[s], ((kt / NSTAGE) - 1) & 1);
-      uint8_t* st = smem + (size_t)s * STAGE_BYTES;
-      if (gen != GEN_NONE) {
-        float4 g[4];
-        if (gen == GEN_FIRST) {
-          const float* __restrict__ wt = gen_s + k0 + gh * 16;
-          float acc[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-#pragma unroll
-          for (int i = 0; i < GK_MAX; ++i) {
-            if (i < gk) {
-              const float x = xr[i];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 w = *reinterpret_cast<const float4*>(wt + i * kpad + 4 * q);
-                acc[4 * q] = fmaf(x, w.x, acc[4 * q]); acc[4 * q + 1] = fmaf(x, w.y, acc[4 * q + 1]);
-                acc[4 * q + 2] = fmaf(x, w.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(x, w.w, acc[4 * q + 3]);
-              }
-            }
+          for (int q = 0; q < 2; ++q) {
+            const float4 w = *reinterpret_cast<const float4*>(wt + i * kpad + 4 * q);
+            g[q].x = fmaf(x, w.x, g[q].x); g[q].y = fmaf(x, w.y, g[q].y);
+            g[q].z = fmaf(x, w.z, g[q].z); g[q].w = fmaf(x, w.w, g[q].w);
           }
-          const float* __restrict__ bp = gen_s + gk * kpad + k0 + gh * 16;
-          const int ga = t.gact;
+        }
+        if constexpr (ASRC == A_FIRST) {
+          const float* __restrict__ bp = gen_s + gk * kpad + k0 + kq * 8;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < 2; ++q) {
             const float4 b = *reinterpret_cast<const float4*>(bp + 4 * q);
-            g[q].x = apply_act(acc[4 * q] + b.x, ga); g[q].y = apply_act(acc[4 * q + 1] + b.y, ga);
-            g[q].z = apply_act(acc[4 * q + 2] + b.z, ga); g[q].w = apply_act(acc[4 * q + 3] + b.w, ga);
-            if (k0 + gh * 16 + 4 * q >= K) g[q] = make_float4(0.f, 0.f, 0.f, 0.f);   // k padding (K % 4 == 0)
+            g[q].x = apply_act(g[q].x + b.x, ga); g[q].y = apply_act(g[q].y + b.y, ga);
+            g[q].z = apply_act(g[q].z + b.z, ga); g[q].w = apply_act(g[q].w + b.w, ga);
+            if (k0 + kq * 8 + 4 * q >= K) g[q] = make_float4(0.f, 0.f, 0.f, 0.f);   // k padding (K % 4 == 0)
           }
         } else {
-          const float* __restrict__ wt = gen_s + k0 + gh * 16;
-          const int ga = t.gact;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4 sacc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int j = 0; j < GK_MAX; ++j) {
-              if (j < gk) {
-                const float4 w = *reinterpret_cast<const float4*>(wt + j * kpad + 4 * q);
-                sacc.x = fmaf(xr[j], w.x, sacc.x); sacc.y = fmaf(xr[j], w.y, sacc.y);
-                sacc.z = fmaf(xr[j], w.z, sacc.z); sacc.w = fmaf(xr[j], w.w, sacc.w);
-              }
-            }
-            g[q].x = dact_mul(sacc.x, va[q].x, ga); g[q].y = dact_mul(sacc.y, va[q].y, ga);
-            g[q].z = dact_mul(sacc.z, va[q].z, ga); g[q].w = dact_mul(sacc.w, va[q].w, ga);
+          for (int q = 0; q < 2; ++q) {
+            const int k = k0 + kq * 8 + 4 * q;
+            float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rowok && k < K) h = lds128(ra + (row * RAW_KC_LD + kq * 8 + 4 * q) * 4);
+            g[q].x = dact_mul(g[q].x, h.x, ga); g[q].y = dact_mul(g[q].y, h.y, ga);
+            g[q].z = dact_mul(g[q].z, h.z, ga); g[q].w = dact_mul(g[q].w, h.w, ga);
           }
         }
-        if (gstore && m0 + gr < M) {
+        if (gstore && rowok) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int k = k0 + gh * 16 + 4 * q;
-            if (k < K) *reinterpret_cast<float4*>(t.gstore + (size_t)(m0 + gr) * t.ldgs + k) = g[q];
+          for (int q = 0; q < 2; ++q) {
+            const int k = k0 + kq * 8 + 4 * q;
+            if (k < K) *reinterpret_cast<float4*>(t.gstore + (size_t)(m0 + row) * t.ldgs + k) = g[q];
           }
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int off = sw_off(gr, gh * 4 + q);
-          float4 hi, lo;
-          split4(g[q], hi, lo);
-          *reinterpret_cast<float4*>(st + off) = hi;
-          *reinterpret_cast<float4*>(st + A_T + off) = lo;
+        for (int q = 0; q < 2; ++q) { av[4 * q] = g[q].x; av[4 * q + 1] = g[q].y; av[4 * q + 2] = g[q].z; av[4 * q + 3] = g[q].w; }
+      } else if constexpr (ASRC == A_KC) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rowok && k0 + kq * 8 + 4 * q < K) v = lds128(ra + (row * RAW_KC_LD + kq * 8 + 4 * q) * 4);
+          av[4 * q] = v.x; av[4 * q + 1] = v.y; av[4 * q + 2] = v.z; av[4 * q + 3] = v.w;
         }
-      } else if (akc) {
+      } else {   // A_MC: raw [32 k][128 m]; consecutive lanes = consecutive m: conflict-free
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int c = tid + PRODUCERS * i, r = c >> 3, ck = c & 7;
-          const int off = sw_off(r, ck);
-          float4 hi, lo;
-          split4(va[i], hi, lo);
-          *reinterpret_cast<float4*>(st + off) = hi;
-          *reinterpret_cast<float4*>(st + A_T + off) = lo;
-        }
-      } else {   // transpose while storing: element (m = warp*16 + 4i + c, k = lane)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float v4[4] = {va[i].x, va[i].y, va[i].z, va[i].w};
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int m = warp * 16 + 4 * i + c;
-            const int off = sw_off(m, lane >> 2) + (lane & 3) * 4;
-            const float hi = rna_tf32(v4[c]);
-            *reinterpret_cast<float*>(st + off) = hi;
-            *reinterpret_cast<float*>(st + A_T + off) = rna_tf32(v4[c] - hi);
-            if (want_cs) cs[4 * i + c] += v4[c];
-          }
+        for (int j = 0; j < 8; ++j) {
+          const int k = kq * 8 + j;
+          av[j] = (rowok && k0 + k < K) ? lds32(ra + (k * RAW_A_MC_LD + row) * 4) : 0.f;
+          cs += av[j];
         }
       }
-      if (bkc) {
+      {
+        float hi[8], lo[8];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int c = tid + PRODUCERS * i, r = c >> 3, ck = c & 7;
-          const int off = sw_off(r, ck);
-          float4 hi, lo;
-          split4(vb[i], hi, lo);
-          *reinterpret_cast<float4*>(st + 2 * A_T + off) = hi;
-          *reinterpret_cast<float4*>(st + 2 * A_T + B_T + off) = lo;
-        }
-      } else {
+        for (int j = 0; j < 8; ++j) { hi[j] = rnd_tf32(av[j]); lo[j] = rnd_tf32(av[j] - hi[j]); }
+        const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(TM_A + so * 64 + kq * 8);
+        tmem_st8(ta, hi);
+        tmem_st8(ta + 32, lo);
+      }
+      // ---- B operand -> shared memory (SWIZZLE_128B k-major)
+      if constexpr (BKC) {
+        const int r = tid >> 3, ck = tid & 7;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n0 + r < N && k0 + ck * 4 < K) v = lds128(rb + (r * RAW_KC_LD + ck * 4) * 4);
+        const int off = sw_off(r, ck);
+        float4 hi, lo;
+        split4(v, hi, lo);
+        sts128(st + off, hi);
+        sts128(st + B_T + off, lo);
+      } else {   // raw [32 k][64 n]: warp = (n group of 8, k half)
+        const int n = (warp & 7) * 8 + m7;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const float v4[4] = {vb[i].x, vb[i].y, vb[i].z, vb[i].w};
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int n = warp * 8 + 4 * i + c;
-            const int off = sw_off(n, lane >> 2) + (lane & 3) * 4;
-            const float hi = rna_tf32(v4[c]);
-            *reinterpret_cast<float*>(st + 2 * A_T + off) = hi;
-            *reinterpret_cast<float*>(st + 2 * A_T + B_T + off) = rna_tf32(v4[c] - hi);
-          }
+        for (int kc4 = 0; kc4 < 4; ++kc4) {
+          const int kc = (warp >> 3) * 4 + kc4, k = kc * 4 + k3;
+          float v = 0.f;
+          if (n0 + n < N && k0 + k < K) v = lds32(rb + (k * RAW_B_NC_LD + n) * 4);
+          const int off = sw_off(n, kc) + k3 * 4;
+          const float hi = rnd_tf32(v);
+          sts32(st + off, hi);
+          sts32(st + B_T + off, rnd_tf32(v - hi));
         }
       }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[s]);
-    };
-    {
-      float4 a0[4], b0[2], a1[4], b1[2];
-      load(0, a0, b0);
-      for (int kt = 0; kt < nk; kt += 2) {
-        if (kt + 1 < nk) load(kt + 1, a1, b1);
-        store(kt, a0, b0);
-        if (kt + 1 < nk) {
-          if (kt + 2 < nk) load(kt + 2, a0, b0);
-          store(kt + 1, a1, b1);
-        }
+      if (lane == 0) {
+        mbar_arrive(&op_full[so]);
+        mbar_arrive(&raw_empty[sr]);
       }
+      if (kt < 8) FZ_STAMP(9 + 2 * kt);
     }
-    if (want_cs) {   // bias gradient: sum over k (= the batch) of A[m, k]; lanes hold disjoint k's
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float v = cs[i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        const int m = m0 + warp * 16 + i;
-        if (lane == 0 && m < M) t.colsum[m] = v;
+    if constexpr (ASRC == A_MC) {
+      if (want_cs) {   // bias gradient: sum over k (= the batch) of A[m, k]; the two k-halves of a row meet in shared memory
+        float* csx = cs_s;
+        csx[kq * BM + row] = cs;
+        asm volatile("bar.sync 1, %0;" ::"n"(CONV) : "memory");
+        if (kq == 0 && rowok) t.colsum[m0 + row] = ((csx[row] + csx[BM + row]) + csx[2 * BM + row]) + csx[3 * BM + row];
       }
     }
     // ------------------------------------------------ epilogue
+    FZ_STAMP(3);
     mbar_wait(&acc_bar, 0);
+    FZ_STAMP(4);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int q = warp & 3, half = warp >> 2;
-    float* tile = reinterpret_cast<float*>(smem);   // [128][TP], reuses the ring (every MMA has completed)
-#pragma unroll
-    for (int cb = 0; cb < BN / 2; cb += 16) {
-      const int col = half * (BN / 2) + cb;
+    const int q = warp & 3;
+    const uint32_t tile = rbase;   // [128][TP] floats, reuses the raw ring (every slab has been consumed)
+    {
+      const int col = (warp >> 2) * 16;   // 16 warps: lane quarter x column quarter
       uint32_t v[3][16];
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
@@ -396,16 +476,18 @@ __global__ void __launch_bounds__(THREADS, MINB) k_fz(const __grid_constant__ Fz
             : "r"(taddr));
       }
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      float* dst = tile + (q * 32 + lane) * TP + col;
+      const uint32_t dst = tile + ((q * 32 + lane) * TP + col) * 4;
       float f[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j)
         f[j] = (__uint_as_float(v[0][j]) + __uint_as_float(v[1][j])) + __uint_as_float(v[2][j]);
 #pragma unroll
-      for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+      for (int j = 0; j < 16; j += 4) sts128(dst + j * 4, make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]));
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(PRODUCERS) : "memory");
-    // phase 2: fused epilogue, coalesced stores (32 lanes = 32 consecutive columns of one row)
+    asm volatile("bar.sync 1, %0;" ::"n"(CONV) : "memory");
+    FZ_STAMP(5);
+    // phase 2: fused epilogue.  lane = (row parity, 4 consecutive columns): two rows of 64 columns per warp
+    // iteration, 16-byte accesses when every row base is 16-byte aligned (t.epi_vec), scalar otherwise
     {
       float* __restrict__ C = t.C;
       float* __restrict__ aux = t.aux;
@@ -413,81 +495,118 @@ __global__ void __launch_bounds__(THREADS, MINB) k_fz(const __grid_constant__ Fz
       const float* __restrict__ dsrc = t.dact_src;
       const int ldc = t.ldc, ldaux = t.ldaux, ldr = t.ldr, ldd = t.ld_dact, act = t.act, clampf = t.clamp, dact = t.dact;
       const float scale = t.scale, lo = t.lo, hi = t.hi;
-      const bool cst = t.c_store != 0, red = t.red != 0;
-      float bj[BN / 32];
-#pragma unroll
-      for (int j = 0; j < BN / 32; ++j) {
-        const int gj = n0 + j * 32 + lane;
-        bj[j] = (t.bias && gj < N) ? t.bias[gj] : 0.f;
+      const bool cst = t.c_store != 0, vec = t.epi_vec != 0;
+      const int c4 = (lane & 15) * 4, gj = n0 + c4;
+      float4 bj = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t.bias) {
+        if (gj < N) bj.x = t.bias[gj];
+        if (gj + 1 < N) bj.y = t.bias[gj + 1];
+        if (gj + 2 < N) bj.z = t.bias[gj + 2];
+        if (gj + 3 < N) bj.w = t.bias[gj + 3];
       }
-      for (int r = warp; r < BM; r += PRODUCERS / 32) {
-        const int gi = m0 + r;
-        if (gi >= M) break;
+      const bool plain = !aux && !resid && !clampf && scale == 1.f;
+      const bool tanh_act = act == ACT_TANH;
+      const bool relu_act = act == ACT_RELU;
+      // four rows per thread: their shared / global loads are issued before anything is stored
 #pragma unroll
-        for (int j = 0; j < BN / 32; ++j) {
-          const int gj = n0 + j * 32 + lane;
-          float v = 0.f;
-          if (gj < N) {
-            v = apply_act(tile[r * TP + j * 32 + lane] + bj[j], act);
-            if (aux) aux[(size_t)gi * ldaux + gj] = v;
-            v *= scale;
-            if (resid) v += resid[(size_t)gi * ldr + gj];
-            if (clampf) v = fminf(fmaxf(v, lo), hi);
-            if (dact) v = dact_mul(v, dsrc[(size_t)gi * ldd + gj], dact);
-            if (cst) C[(size_t)gi * ldc + gj] = v;
-          }
-          if (red) tile[r * TP + j * 32 + lane] = v;
-        }
-      }
-    }
-    // phase 3: reduce epilogue -- partial dot products of this column tile, last tile to arrive finishes the rows
-    if (t.red) {
-      asm volatile("bar.sync 1, %0;" ::"n"(PRODUCERS) : "memory");
-      const int rn = t.red_n;
-      const int r = tid >> 1, nh = tid & 1, gi = m0 + r;
-      float acc[RED_MAX];
+      for (int pass = 0; pass < 1; ++pass) {
+        float e[4][4];
+        float4 hm[4];
 #pragma unroll
-      for (int j = 0; j < RED_MAX; ++j) acc[j] = 0.f;
-      if (gi < M) {
-#pragma unroll
-        for (int c4 = 0; c4 < BN / 8; ++c4) {
-          const int col = nh * (BN / 2) + 4 * c4;
-          const float4 v = *reinterpret_cast<const float4*>(tile + r * TP + col);
-#pragma unroll
-          for (int j = 0; j < RED_MAX; ++j) {
-            if (j < rn) {
-              const float4 w = *reinterpret_cast<const float4*>(rws + j * BN + col);
-              acc[j] = fmaf(v.x, w.x, acc[j]); acc[j] = fmaf(v.y, w.y, acc[j]);
-              acc[j] = fmaf(v.z, w.z, acc[j]); acc[j] = fmaf(v.w, w.w, acc[j]);
+        for (int it = 0; it < 4; ++it) {
+          const int r = (pass * 4 + it) * 2 * (CONV / 32) + warp * 2 + (lane >> 4), gi = m0 + r;
+          const float4 v = lds128(tile + (r * TP + c4) * 4);
+          e[it][0] = v.x + bj.x; e[it][1] = v.y + bj.y; e[it][2] = v.z + bj.z; e[it][3] = v.w + bj.w;
+          hm[it] = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (dact && gi < M) {
+            if (vec && gj + 3 < N) hm[it] = *reinterpret_cast<const float4*>(dsrc + (size_t)gi * ldd + gj);
+            else {
+              if (gj < N) hm[it].x = dsrc[(size_t)gi * ldd + gj];
+              if (gj + 1 < N) hm[it].y = dsrc[(size_t)gi * ldd + gj + 1];
+              if (gj + 2 < N) hm[it].z = dsrc[(size_t)gi * ldd + gj + 2];
+              if (gj + 3 < N) hm[it].w = dsrc[(size_t)gi * ldd + gj + 3];
             }
           }
         }
-      }
-      float* __restrict__ part = t.rpart + ((size_t)(t.r_slot0 + tn) * M + (gi < M ? gi : 0)) * rn;
 #pragma unroll
-      for (int j = 0; j < RED_MAX; ++j) {
-        if (j < rn) {
-          const float o = __shfl_xor_sync(0xffffffffu, acc[j], 1);
-          const float sum = nh == 0 ? acc[j] + o : o + acc[j];   // (same value on both lanes)
-          if (nh == 0 && gi < M) part[j] = sum;
+        for (int it = 0; it < 4; ++it) {
+          const int r = (pass * 4 + it) * 2 * (CONV / 32) + warp * 2 + (lane >> 4), gi = m0 + r;
+          if (tanh_act) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) e[it][c] = tanhf(e[it][c]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) e[it][c] = relu_act ? (e[it][c] > 0.f ? e[it][c] : 0.f) : e[it][c];
+          }
+          if (!plain && gi < M) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (gj + c < N) {
+                if (aux) aux[(size_t)gi * ldaux + gj + c] = e[it][c];
+                e[it][c] *= scale;
+                if (resid) e[it][c] += resid[(size_t)gi * ldr + gj + c];
+                if (clampf) e[it][c] = fminf(fmaxf(e[it][c], lo), hi);
+              }
+            }
+          }
+          if (dact) {
+            e[it][0] = dact_mul(e[it][0], hm[it].x, dact); e[it][1] = dact_mul(e[it][1], hm[it].y, dact);
+            e[it][2] = dact_mul(e[it][2], hm[it].z, dact); e[it][3] = dact_mul(e[it][3], hm[it].w, dact);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (gj + c >= N) e[it][c] = 0.f;
+          if (cst && gi < M) {
+            if (vec && gj + 3 < N) *reinterpret_cast<float4*>(C + (size_t)gi * ldc + gj) = make_float4(e[it][0], e[it][1], e[it][2], e[it][3]);
+            else {
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                if (gj + c < N) C[(size_t)gi * ldc + gj + c] = e[it][c];
+            }
+          }
+          if constexpr (RED) sts128(tile + (r * TP + c4) * 4, make_float4(e[it][0], e[it][1], e[it][2], e[it][3]));
         }
       }
+    }
+    FZ_STAMP(6);
+    // phase 3: reduce epilogue -- partial dot products of this column tile, last tile to arrive finishes the rows
+    if constexpr (RED) {
+      asm volatile("bar.sync 1, %0;" ::"n"(CONV) : "memory");
+      const int rn = t.red_n;
+      const int r = tid >> 2, nq = tid & 3, gi = m0 + r;   // four threads per row, 16 columns each
+      float4 tv[4];
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) tv[c4] = lds128(tile + (r * TP + nq * 16 + 4 * c4) * 4);
+      float* __restrict__ part = t.rpart + ((size_t)(t.r_slot0 + tn) * M + (gi < M ? gi : 0)) * rn;
+      for (int j = 0; j < rn; ++j) {
+        const float* __restrict__ wj = rws + j * BN + nq * 16;
+        float acc = 0.f;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const float4 w = *reinterpret_cast<const float4*>(wj + 4 * c4);
+          acc = fmaf(tv[c4].x, w.x, acc); acc = fmaf(tv[c4].y, w.y, acc);
+          acc = fmaf(tv[c4].z, w.z, acc); acc = fmaf(tv[c4].w, w.w, acc);
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (nq == 0 && gi < M) part[j] = acc;
+      }
       __threadfence();
-      asm volatile("bar.sync 1, %0;" ::"n"(PRODUCERS) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(CONV) : "memory");
       if (tid == 0) {
         const unsigned prev = atomicAdd(t.rcnt + tm, 1u);
         const int last = prev == (unsigned)(t.r_slots - 1);
         if (last) t.rcnt[tm] = 0u;   // ready for the next launch / graph replay
         last_flag = last;
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(PRODUCERS) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(CONV) : "memory");
       if (last_flag) {
         __threadfence();
         const int slots = t.r_slots;
         const float* __restrict__ rp = t.rpart;
         const int ract = t.ract, rclamp = t.rclamp;
         const float rscale = t.rscale, rlo = t.rlo, rhi = t.rhi;
-        for (int e = tid; e < BM * rn; e += PRODUCERS) {
+        for (int e = tid; e < BM * rn; e += CONV) {
           const int rr = e / rn, j = e - rr * rn, g = m0 + rr;
           if (g >= M) break;
           float v = 0.f;
@@ -502,32 +621,38 @@ __global__ void __launch_bounds__(THREADS, MINB) k_fz(const __grid_constant__ Fz
         }
       }
     }
+    FZ_STAMP(7);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  } else if (lane == 0) {
+  } else if (warp == CONV / 32 && lane == 0) {
     // ------------------------------------------------ MMA issuer (one thread)
     for (int kt = 0; kt < nk; ++kt) {
-      const int s = kt % NSTAGE;
-      mbar_wait(&full_bar[s], (kt / NSTAGE) & 1);
+      const int s = kt % NOP;
+      mbar_wait(&op_full[s], (kt / NOP) & 1);
+      if (kt < 8) FZ_STAMP_MMA(32 + 2 * kt);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t sb = smem_u32(smem + (size_t)s * STAGE_BYTES);
-      const uint64_t a_hi = make_desc(sb), a_lo = make_desc(sb + A_T);
-      const uint64_t b_hi = make_desc(sb + 2 * A_T), b_lo = make_desc(sb + 2 * A_T + B_T);
+      const uint32_t sb = sbase + s * STAGE_BYTES;
+      const uint64_t b_hi = make_desc(sb), b_lo = make_desc(sb + B_T);
+      const uint32_t a_hi = tmem_base + TM_A + s * 64, a_lo = a_hi + 32;   // lane 0, one 32-bit column per k
 #pragma unroll
       for (int k8 = 0; k8 < BK / 8; ++k8) {
         const uint64_t adv = (uint64_t)((k8 * 32) >> 4);
-        mma_tf32_ss(tmem_base + 2 * BN, a_lo + adv, b_hi + adv, IDESC, (kt | k8) != 0);
-        mma_tf32_ss(tmem_base + 2 * BN, a_hi + adv, b_lo + adv, IDESC, 1);
-        mma_tf32_ss(tmem_base + (k8 & 1) * BN, a_hi + adv, b_hi + adv, IDESC, kt != 0 || k8 >= 2);
+        mma_tf32_ts(tmem_base + 2 * BN, a_lo + k8 * 8, b_hi + adv, IDESC, (kt | k8) != 0);
+        mma_tf32_ts(tmem_base + 2 * BN, a_hi + k8 * 8, b_lo + adv, IDESC, 1);
+        mma_tf32_ts(tmem_base + (k8 & 1) * BN, a_hi + k8 * 8, b_hi + adv, IDESC, kt != 0 || k8 >= 2);
       }
-      commit(&empty_bar[s]);
+      commit(&op_empty[s]);
+      if (kt < 8) FZ_STAMP_MMA(33 + 2 * kt);
     }
     commit(&acc_bar);
   }
   __syncthreads();
+  FZ_STAMP(63);
   if (warp == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
+#undef FZ_STAMP
+#undef FZ_STAMP_MMA
 }
 
 }  // namespace fz

@@ -23,7 +23,7 @@ def _cfg(meta):
     return ocdt.CDTConfig(**c)
 
 
-def _engine(meta, B, gemm="tc5"):
+def _engine(meta, B, gemm="fz"):
     import os
     from osrl_b200 import Engine
     os.environ["OSRL_GEMM"] = gemm
@@ -76,7 +76,7 @@ def test_cdt_small_golden(lib_built):
     eng.close()
 
 
-@pytest.mark.parametrize("gemm", ["ffma", "mma", "tc5"])
+@pytest.mark.parametrize("gemm", ["ffma", "mma", "tc5", "fz"])
 @pytest.mark.parametrize("case", ["cdt_small", "cdt_full"])
 def test_cdt_against_live_oracle(lib_built, case, gemm):
     z, meta = load_golden(case)

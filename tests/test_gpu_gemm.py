@@ -6,10 +6,11 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-SHAPES = [(2560, 256, 256), (5120, 400, 400), (640, 128, 64), (1024, 1024, 128), (515, 72, 100), (256, 400, 12)]
+SHAPES = [(2560, 256, 256), (5120, 400, 400), (640, 128, 64), (1024, 1024, 128), (515, 72, 100), (256, 400, 12),
+          (256, 256, 256), (16, 32, 32), (300, 70, 41)]
 
 
-@pytest.mark.parametrize("impl", ["ffma", "mma", "tc5"])
+@pytest.mark.parametrize("impl", ["ffma", "mma", "tc5", "fz"])
 def test_linear_matches_torch(lib_built, impl):
     from osrl_b200 import Engine
     eng = Engine("bc", batch_size=8, device=0, state_dim=4, action_dim=2, a_hidden_sizes=[8, 8])
@@ -48,10 +49,14 @@ LAYOUT_SHAPES = [
     (333, 16, 1000, 0, 0),
     (256, 256, 256, 1, 0),    # tiled dgrad / wgrad for comparison
     (400, 400, 256, 0, 0),
+    (256, 256, 256, 0, 0),    # (fz: batch-256 weight gradient of a 256x256 layer, colsum = bias gradient)
+    (32, 32, 16, 0, 0),
+    (130, 70, 100, 0, 1),
+    (100, 48, 300, 1, 0),
 ]
 
 
-@pytest.mark.parametrize("impl", ["ffma", "mma", "tc5"])
+@pytest.mark.parametrize("impl", ["ffma", "mma", "tc5", "fz"])
 def test_gemm_layouts_match_torch(lib_built, impl):
     from osrl_b200 import Engine
     eng = Engine("bc", batch_size=8, device=0, state_dim=4, action_dim=2, a_hidden_sizes=[8, 8])

@@ -29,10 +29,10 @@ pytestmark = pytest.mark.gpu
 BATCH_KEYS = ("observations", "next_observations", "actions", "rewards", "costs", "done")
 
 
-GEMMS = ["ffma", "mma", "tc5"]   # OSRL_GEMM: CUDA cores / 3xTF32 mma.sync / + tcgen05 for large layers (default)
+GEMMS = ["ffma", "mma", "tc5", "fz"]   # fz (default): fused tcgen05 networks, gemm_fz.cuh   # OSRL_GEMM: CUDA cores / 3xTF32 mma.sync / + tcgen05 for large layers (default)
 
 
-def _engine(meta, B, gemm="tc5"):
+def _engine(meta, B, gemm="fz"):
     import os
     from osrl_b200 import Engine
     os.environ["OSRL_GEMM"] = gemm          # read when the engine builds its step program
@@ -42,7 +42,7 @@ def _engine(meta, B, gemm="tc5"):
         os.environ.pop("OSRL_GEMM", None)
 
 
-def _compare_step(tag, eng, s32, s64, g32, g64, before, p64, gemm="tc5"):
+def _compare_step(tag, eng, s32, s64, g32, g64, before, p64, gemm="fz"):
     """Engine (already stepped) vs the fp32 reference step, tolerance scaled by conditioning.
     Gradient outliers (ReLU kinks, see module docstring): the CUDA-core GEMM reproduces the reference's
     pre-activations to ~1e-7, so a kink flip is rare (<=5 % of tensors, <=1e-2); the 3xTF32 GEMM is ~1e-6
@@ -243,7 +243,7 @@ def test_sampled_steps_match_oracle_on_dumped_batch(lib_built):
              "actions": data["actions"][idx], "rewards": data["rewards"][idx] * np.float32(0.1),
              "costs": data["costs"][idx] * np.float32(1.0), "done": done[idx]}
         s32, s64, g32, g64, before, p64 = probe_step(orc, "bcql", b, noise=nz)
-        _compare_step(f"sampled step {s}", eng, s32, s64, g32, g64, before, p64, "tc5")
+        _compare_step(f"sampled step {s}", eng, s32, s64, g32, g64, before, p64, "fz")
     eng.close()
 
 
