@@ -12,6 +12,13 @@ void emit_vae_decode(Engine& e, Program& p, const float* W, const float* dec_in,
                      float* out, int ldout, int mode, bool nograd) {
   const VaeLay& v = e.plan.vae;
   const int V = v.d1.out, ldin = v.d1.in;
+  if (fz_mlp_ok(v.d1, v.d2, v.d3) && fz_unfuse_first(rows, nograd)) {
+    flush(e, p, {task_fwd(dec_in, ldin, rows, W, v.d1, h1, V, ACT_RELU)});
+    FzTask t = fz_fwd2(h1, V, rows, W, v.d2, v.d3, ACT_RELU, nullptr, 0, out, ldout);
+    if (mode == 0) { t.ract = ACT_TANH; t.rscale = e.plan.cfg.max_action; }
+    emit_fz(e, p, {t});
+    return;
+  }
   if (fz_mlp_ok(v.d1, v.d2, v.d3)) {   // the whole decoder in one fused launch
     FzTask t = fz_fwd3(dec_in, ldin, rows, W, v.d1, v.d2, v.d3, ACT_RELU, nograd ? nullptr : h1, V, nograd ? nullptr : h2,
                        V, out, ldout);
@@ -61,9 +68,11 @@ void emit_vae_update(Engine& e, Program& p, const float* sa, float* dec_in, cons
     }
     KOP(p, e, 28.0 * B * L, (k_vae_reparam_bwd<<<(B * L + 255) / 256, 256, 0, s>>>(dz, L, 0, ml, sd, eps, B, L, beta, dml, iw)));
     emit_fz(e, p, {fz_bwd_mid(dml, 2 * L, B, e.P, v.e2, v.heads, ACT_RELU, h1, V, h2, V, dh2, V, dh1, V)});
+    p.begin_par();
     emit_fz(e, p, {fz_wgrad(dg2, V, g1, V, B, e.G, v.d2), fz_wgrad(dh2, V, h1, V, B, e.G, v.e2)});
     flush(e, p, {task_wgrad(dpre3, a, g2, V, B, e.G, v.d3), task_wgrad(dg1, V, dec_in, o + L, B, e.G, v.d1),
                  task_wgrad(dml, 2 * L, h2, V, B, e.G, v.heads), task_wgrad(dh1, V, sa, o + a, B, e.G, v.e1)});
+    p.end_par();
     const Group& g = e.plan.groups[e.plan.g_vae];
     emit_allreduce(e, p, e.G + g.begin, g.end - g.begin);
     emit_adam(e, p, e.plan.g_vae, g.begin, g.end, false);
@@ -108,6 +117,14 @@ GemmTask mlp_fwd_hidden(Engine& e, Program& p, const float* W, const MlpLay& m, 
     // fused network: nothing is launched here -- the returned task is a marker that carries the caller's last-layer
     // epilogue to emit_gemm, which completes the fused task (Engine::fz_pending) and launches it
     float *y0 = nullptr, *y1 = nullptr;
+    if (fz_unfuse_first(rows, nograd)) {
+      y0 = e.ws((size_t)rows * m.L[0].out);
+      emit_gemm(e, p, {task_fwd(X, ldx, rows, W, m.L[0], y0, m.L[0].out, hact)});
+      e.fz_pending.push_back(fz_fwd2(y0, m.L[0].out, rows, W, m.L[1], m.L[2], hact, nullptr, 0, out, ldout));
+      GemmTask mk = task_fwd(nullptr, m.L[1].out, rows, W, m.L[2], out, ldout, ACT_NONE);
+      mk.fz_pending = (int)e.fz_pending.size();
+      return mk;
+    }
     if (!nograd) {
       y0 = e.ws((size_t)rows * m.L[0].out); y1 = e.ws((size_t)rows * m.L[1].out);
       h.push_back(y0); h.push_back(y1);
@@ -140,8 +157,10 @@ void mlp_bwd(Engine& e, Program& p, const float* W, float* Gsec, const MlpLay& m
     float* d1 = e.ws((size_t)rows * H1);
     float* d0 = e.ws((size_t)rows * H0);
     emit_fz(e, p, {fz_bwd_mid(dpre, lddy, rows, W, m.L[1], m.L[2], hact, h[0], H0, h[1], H1, d1, H1, d0, H0)});
+    p.begin_par();
     emit_fz(e, p, {fz_wgrad(d1, H1, h[0], H0, rows, Gsec, m.L[1])});
     emit_gemm(e, p, {task_wgrad(dpre, lddy, h[1], H1, rows, Gsec, m.L[2]), task_wgrad(d0, H0, X, ldx, rows, Gsec, m.L[0])});
+    p.end_par();
     return;
   }
   for (int j = n - 1; j >= 0; --j) {
@@ -163,9 +182,11 @@ void mlp_bwd(Engine& e, Program& p, const float* W, float* Gsec, const MlpLay& m
 
 namespace osrl {
 void emit_stages(Engine& e, Program& p, std::vector<Stage>& st) {
-  for (auto& s : st) {
+  for (auto& s : st) {   // the launches of one stage are independent of each other
+    p.begin_par();
     emit_fz(e, p, s.fz);
     emit_gemm(e, p, s.tasks);
+    p.end_par();
   }
 }
 }  // namespace osrl

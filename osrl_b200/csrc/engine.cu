@@ -317,6 +317,27 @@ FzTask fz_fwd3(const float* X, int ldx, int rows, const float* W, const Lin& l0,
   t.rout = out; t.ldro = ldo;
   return t;
 }
+FzTask fz_fwd2(const float* H1, int ldh1, int rows, const float* W, const Lin& l1, const Lin& l2, int hact, float* h2,
+               int ldh2, float* out, int ldo) {
+  FzTask t = fz_blank();
+  t.A = H1; t.lda = ldh1; t.a_kc = 1;
+  t.B = W + l1.w; t.ldb = l1.in; t.b_kc = 1;
+  t.M = rows; t.N = l1.out; t.K = l1.in;
+  t.bias = W + l1.b; t.act = hact;
+  t.C = h2; t.ldc = ldh2; t.c_store = h2 != nullptr;
+  t.red = 1; t.red_n = l2.out; t.rw = W + l2.w; t.rs_j = l2.in; t.rs_n = 1; t.rbias = W + l2.b;
+  t.r_group = fz_new_group(); t.r_slot0 = 0; t.r_slots = (l1.out + fz::BN - 1) / fz::BN;
+  t.rout = out; t.ldro = ldo;
+  return t;
+}
+// large no-grad passes (targets on B*S rows): every column tile of a fused task regenerates the first layer, and the
+// generation is bound by broadcast shared-memory reads of the weights.  Measured on B200 (BCQ-Lag B=256): actor_old on
+// 5120 rows 57 us fused vs 15 + 41 us split; the 8 target critics 95 us fused vs 21 + 68 + 27 us -- no gain, so the
+// split is off by default (OSRL_FZ_UNFUSE=1 enables it for A/B timing).
+bool fz_unfuse_first(int rows, bool nograd) {
+  static const bool on = [] { const char* v = getenv("OSRL_FZ_UNFUSE"); return v && v[0] == '1'; }();
+  return on && nograd && rows >= 1024;
+}
 FzTask fz_bwd_mid(const float* dq, int lddq, int rows, const float* W, const Lin& l1, const Lin& l2, int hact,
                   const float* h1, int ldh1, const float* h2, int ldh2, float* d1, int ldd1, float* d0, int ldd0) {
   FzTask t = fz_blank();
@@ -682,6 +703,16 @@ void ens_fwd(std::vector<Stage>& st, const EnsLay& l, const float* W, const floa
              bool nograd) {
   const int nh = (int)l.h.size();
   OSRL_REQUIRE((int)st.size() >= nh + 1, "ens_fwd: not enough stages");
+  if (ens_fz_ok(l) && fz_unfuse_first(rows, nograd)) {   // thin first layer (one stacked task), then mid + head fused
+    st[0].tasks.push_back(task_fwd(X, ldx, rows, W, l.first, buf.h[0], l.n * l.h[0], ACT_RELU));
+    for (int i = 0; i < l.n; ++i) {
+      Lin l0, l1, l2;
+      ens_member(l, i, l0, l1, l2);
+      st[1].fz.push_back(fz_fwd2(buf.h[0] + (size_t)i * l.h[0], l.n * l.h[0], rows, W, l1, l2, ACT_RELU, nullptr, 0,
+                                 buf.q + i, l.n));
+    }
+    return;
+  }
   if (ens_fz_ok(l)) {   // one fused launch: first layer generated, middle layer on tcgen05, Q head in the reduce epilogue
     for (int i = 0; i < l.n; ++i) {
       Lin l0, l1, l2;
@@ -781,6 +812,9 @@ static void free_all(Engine* e) {
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->side_stream) cudaStreamDestroy(e->side_stream);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  for (auto& ps : e->par_streams)
+    for (cudaStream_t x : ps.second) cudaStreamDestroy(x);
+  for (cudaEvent_t ev : e->par_events) cudaEventDestroy(ev);
   for (void* p : e->allocs) cudaFree(p);
   if (e->comm2 && nccl::CommDestroy) nccl::CommDestroy(e->comm2);
   if (e->comm && nccl::CommDestroy) nccl::CommDestroy(e->comm);
@@ -902,8 +936,53 @@ static Engine* create(const osrl_config& cfg, int device) {
   return e;
 }
 
+static cudaEvent_t par_event(Engine& e) {
+  if (e.par_events_used == e.par_events.size()) {
+    cudaEvent_t ev = nullptr;
+    OSRL_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    e.par_events.push_back(ev);
+  }
+  return e.par_events[e.par_events_used++];
+}
+static cudaStream_t par_stream(Engine& e, cudaStream_t of, size_t idx) {
+  for (auto& ps : e.par_streams)
+    if (ps.first == of) {
+      while (ps.second.size() <= idx) {
+        cudaStream_t x = nullptr;
+        OSRL_CUDA(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
+        ps.second.push_back(x);
+      }
+      return ps.second[idx];
+    }
+  e.par_streams.push_back({of, {}});
+  return par_stream(e, of, idx);
+}
+// Run a program on stream s.  Consecutive ops of one par group (Program::begin_par) are independent: the first stays
+// on s, the others go to helper streams forked from / joined to s with events -- inside a capture that makes them
+// parallel branches of the graph.  OSRL_PAR=0 keeps everything serial.
 static void run_ops(Engine& e, const Program& p, cudaStream_t s) {
-  for (auto& op : p.ops) op(s);
+  static const bool par_on = [] { const char* v = getenv("OSRL_PAR"); return !(v && v[0] == '0'); }();
+  for (size_t i = 0; i < p.ops.size();) {
+    const int g = p.meta[i].par;
+    size_t j = i + 1;
+    if (g && par_on)
+      while (j < p.ops.size() && p.meta[j].par == g) ++j;
+    if (j - i == 1) { p.ops[i](s); i = j; continue; }
+    cudaEvent_t fork = par_event(e);
+    OSRL_CUDA(cudaEventRecord(fork, s));
+    std::vector<cudaEvent_t> joins;
+    for (size_t k = i + 1; k < j; ++k) {
+      cudaStream_t sk = par_stream(e, s, k - i - 1);
+      OSRL_CUDA(cudaStreamWaitEvent(sk, fork, 0));
+      p.ops[k](sk);
+      cudaEvent_t jn = par_event(e);
+      OSRL_CUDA(cudaEventRecord(jn, sk));
+      joins.push_back(jn);
+    }
+    p.ops[i](s);
+    for (cudaEvent_t jn : joins) OSRL_CUDA(cudaStreamWaitEvent(s, jn, 0));
+    i = j;
+  }
 }
 static void prologue(Engine& e, cudaStream_t s, unsigned mask = 0xffffffffu) {
   k_prologue<<<1, 32, 0, s>>>(e.ds, e.d_groups, (int)e.plan.groups.size(), mask);

@@ -101,15 +101,27 @@ struct OpMeta {
   double bytes = 0.0;   // algorithmic bytes of this launch (operands read once + results written once)
   double flops = 0.0;   // algorithmic flops of this launch
   bool kernel = true;   // one of OUR kernels (false: NCCL collective)
+  int par = 0;          // > 0: ops that share this id are independent of each other (run on forked graph branches)
 };
 struct Program {
   std::vector<Op> ops;
   std::vector<OpMeta> meta;
   int kernels = 0;
+  int par_open = 0, par_next = 0;
   void add(const std::string& name, double bytes, double flops, bool kernel, Op fn) {
     ops.push_back(std::move(fn));
-    meta.push_back({name, bytes, flops, kernel});
+    meta.push_back({name, bytes, flops, kernel, par_open});
     if (kernel) ++kernels;
+  }
+  // launches emitted between begin_par() and end_par() do not depend on each other: when the step is captured they
+  // become parallel branches of the graph (engine.cu: run_ops) instead of one serial chain
+  void begin_par() { par_open = ++par_next; }
+  void end_par() {
+    for (auto& m : meta)   // an accumulate-into-zeroed-buffer pair (split-K) must stay ordered: give the group up
+      if (m.par == par_open && m.name == "memset")
+        for (auto& m2 : meta)
+          if (m2.par == par_open) m2.par = 0;
+    par_open = 0;
   }
 };
 // elementwise / reduction kernel launch as one program op: KOP(p, e, bytes, (kernel<<<...>>>(args)))
@@ -171,6 +183,9 @@ struct Engine {
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaStream_t cap_stream = nullptr;
+  std::vector<std::pair<cudaStream_t, std::vector<cudaStream_t>>> par_streams;   // helper streams of forked launches
+  std::vector<cudaEvent_t> par_events;
+  size_t par_events_used = 0;
   float* stats = nullptr;
   std::vector<void*> allocs;
   // packed tf32 hi/lo activation images announced by producer GEMM tasks (GemmTask::pk_*), looked up by the
@@ -219,6 +234,11 @@ FzTask fz_blank();
 // (FzTask::ract / rscale / rresid / rclamp / raux) is the caller's to set.
 FzTask fz_fwd3(const float* X, int ldx, int rows, const float* W, const Lin& l0, const Lin& l1, const Lin& l2, int hact,
                float* h1, int ldh1, float* h2, int ldh2, float* out, int ldo);
+// the same without the generated first layer: H1 [rows, l1.in] (already activated) -> act(l1) -> l2 -> out.  Used for
+// the large no-grad passes, where regenerating the first layer in every column tile costs more than one thin launch.
+FzTask fz_fwd2(const float* H1, int ldh1, int rows, const float* W, const Lin& l1, const Lin& l2, int hact, float* h2,
+               int ldh2, float* out, int ldo);
+bool fz_unfuse_first(int rows, bool nograd);
 // backward through the last and middle layers: dq [rows, l2.out] -> d1 = (dq W2) * act'(h2) (stored if d1 given)
 // -> d0 = (d1 W1) * act'(h1) (stored if d0 given).  fz_add_dx() then folds the first layer's input gradient in.
 FzTask fz_bwd_mid(const float* dq, int lddq, int rows, const float* W, const Lin& l1, const Lin& l2, int hact,

@@ -297,9 +297,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_fz(const __grid_constant__ FzPac
       const int gwld = t.gw_ld;
       for (int k = tid; k < kpad; k += CONV) {      // thread = one row of W1: gk contiguous floats in, a column of W1^T out
         const float* __restrict__ src = gw + (size_t)k * gwld;
-#pragma unroll 4
-        for (int i = 0; i < gk; ++i) gen_s[i * kpad + k] = k < K ? src[i] : 0.f;
-        gen_s[gk * kpad + k] = (k < K && t.gb) ? t.gb[k] : 0.f;
+        float w[GK_MAX];
+#pragma unroll
+        for (int i = 0; i < GK_MAX; ++i) w[i] = (i < gk && k < K) ? src[i] : 0.f;   // all loads in flight at once
+        const float b = (k < K && t.gb) ? t.gb[k] : 0.f;
+#pragma unroll
+        for (int i = 0; i < GK_MAX; ++i)
+          if (i < gk) gen_s[i * kpad + k] = w[i];
+        gen_s[gk * kpad + k] = b;
       }
     } else if constexpr (ASRC == A_LASTD) { // W3 [gk][kpad]
       const float* __restrict__ gw = t.gw;
@@ -309,11 +314,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_fz(const __grid_constant__ FzPac
     }
     if constexpr (GEN) {
       xs = gen_s + (gk + 1) * kpad;
-      if (tid < BM) {
-        const bool ok = m0 + tid < M;
-        const float* __restrict__ src = t.gx + (size_t)(m0 + (ok ? tid : 0)) * t.ldgx;
-#pragma unroll 4
-        for (int i = 0; i < gk; ++i) xs[tid * XS_LD + i] = ok ? src[i] : 0.f;
+      if (tid >= CONV - BM) {   // (the last four warps: the first ones are busy with the weight table)
+        const int r = tid - (CONV - BM);
+        const bool ok = m0 + r < M;
+        const float* __restrict__ src = t.gx + (size_t)(m0 + (ok ? r : 0)) * t.ldgx;
+        float x[GK_MAX];
+#pragma unroll
+        for (int i = 0; i < GK_MAX; ++i) x[i] = (i < gk && ok) ? src[i] : 0.f;
+#pragma unroll
+        for (int i = 0; i < GK_MAX; ++i)
+          if (i < gk) xs[r * XS_LD + i] = x[i];
       }
     }
     if constexpr (RED) {
