@@ -16,7 +16,15 @@ reference : the reference's CPU implementation of the same step (the oracle port
             all host threads), rank 0 only.
 Data-parallel (N>1): one process per GPU (torchrun), per-GPU batch fixed at 256 (weak scaling), gradients
 all-reduced with NCCL before every optimiser update; `value` = N x synchronous steps/s, i.e. batch-256
-gradient-step equivalents per second over the whole job.
+gradient-step equivalents per second over the whole job (`config.synchronous_steps_per_s` is the rate of actual
+optimiser steps).  Before timing, N>1 runs a data-parallel parity check (engine under NCCL vs the single-rank oracle
+on the concatenated batch, active PID multiplier) and reports it as `dp_parity`.
+
+Extra keys of the result line: `roofline` -- step-level fraction of the measured HBM peak per SURVEY.md 8(d)
+(bytes = 24 P_train + 8 P_target + batch bytes) with the per-kernel table (timed inside a replayed CUDA graph) as
+`roofline.kernels`; `other_configs` -- short device-resident runs of BASELINE.json configs[2..4] (CPQ B=512,
+CDT B=2048 seq 10, BEAR-Lag B=512 per GPU and the strong-scaling BEAR-Lag global B=4096) with ms/step and the same
+step-level fractions; `cpu_baseline`.
 """
 from __future__ import annotations
 
@@ -131,8 +139,101 @@ def calibrate_threads(step_fn, budget_s: float = 25.0):
 
 
 def init_params():
+    """Reference arm only: the oracle port of the reference's CPU step."""
     from tests.helpers import make_oracle
     return make_oracle("bcql", CFG, 0)
+
+
+def bcql_model(device: str):
+    """Our arm: the public mirror class, initialised like the reference (seed_all, then construct; bcql.py:85-98)."""
+    from osrl_b200.algorithms import BCQL
+    from osrl_b200.common.exp_util import seed_all
+    seed_all(0)
+    return BCQL(8, 2, 1.0, CFG["a_hidden_sizes"], CFG["c_hidden_sizes"], CFG["vae_hidden_sizes"],
+                CFG["sample_action_num"], CFG["gamma"], CFG["tau"], CFG["phi"], CFG["lmbda"], CFG["beta"], CFG["PID"],
+                CFG["num_q"], CFG["num_qc"], CFG["cost_limit"], CFG["episode_len"], device=device)
+
+
+# ------------------------------------------------------------------------------------------ other BASELINE configs
+# SURVEY.md 8(d): algorithmic bytes = 24 P_train + 8 P_target + batch bytes; flops from the oracle's flop counter
+OTHER = {
+    "cpq_b512": dict(algo="cpq", batch=512, dims=(33, 8, 200), steps=200, bytes=21.47e6, flops=8.80e9,
+                     workload="CPQ OfflineAntRun-v0-shaped (obs 33, act 8) batch=512 (BASELINE.json configs[2])"),
+    "cdt_b2048": dict(algo="cdt", batch=2048, dims=(17, 6, 1000), steps=12, bytes=20.04e6, flops=305.8e9,
+                      workload="CDT OfflineHalfCheetahVelocity-v1-shaped (obs 17, act 6) seq_len=10 batch=2048, "
+                               "3 layers, E=128, dropout 0.1 (BASELINE.json configs[3])"),
+    "bearl_b512": dict(algo="bearl", batch=512, dims=(8, 2, 300), steps=200, bytes=27.91e6, flops=14.6e9,
+                       workload="BEAR-Lag OfflineCarCircle-v0-shaped batch=512 per GPU (BASELINE.json configs[4] shard)"),
+}
+
+
+def build_other(name: str, batch: int, device: str, world: int, rank: int):
+    """Model + engine + resident dataset of one of the other BASELINE configs through the public mirror classes."""
+    from oracle import synth
+    from osrl_b200.algorithms import BEARL, CDT, CPQ, BEARLTrainer, CDTTrainer, CPQTrainer
+    from osrl_b200.common.dataset import SequenceDataset
+    from osrl_b200.common.exp_util import seed_all
+    spec = OTHER[name]
+    o, a, T = spec["dims"]
+    seed_all(0)
+    if spec["algo"] == "cpq":       # examples/configs/cpq_configs.py:29-51
+        model = CPQ(o, a, 1.0, [256, 256], [256, 256], 400, 10, 0.99, 0.005, 0.5, 2, 2, 1.5, 10, T, device=device)
+        tr = CPQTrainer(model, None, None, actor_lr=1e-4, critic_lr=1e-3, alpha_lr=1e-4, vae_lr=1e-3, reward_scale=0.1,
+                        cost_scale=1.0, device=device)
+    elif spec["algo"] == "bearl":   # examples/configs/bearl_configs.py:29-56
+        model = BEARL(o, a, 1.0, [256, 256], [256, 256], 400, 10, 0.99, 0.005, 0.5, 0.75, 50, 0.05, 10,
+                      [0.1, 0.003, 0.001], "gaussian", 2, 2, 10, T, 0, device=device)
+        tr = BEARLTrainer(model, None, None, actor_lr=1e-3, critic_lr=1e-3, alpha_lr=1e-3, vae_lr=1e-3, reward_scale=0.1,
+                          cost_scale=1.0, device=device)
+    else:                           # examples/configs/cdt_configs.py:22-44,498-511
+        model = CDT(o, a, 1.0, seq_len=10, episode_len=T, embedding_dim=128, num_layers=3, num_heads=8,
+                    attention_dropout=0.1, residual_dropout=0.1, embedding_dropout=0.1, time_emb=True, use_rew=True,
+                    use_cost=True, cost_transform=True, stochastic=True, init_temperature=0.1, target_entropy=-a,
+                    device=device)
+        tr = CDTTrainer(model, None, None, learning_rate=1e-4, weight_decay=1e-4, betas=(0.9, 0.999), clip_grad=0.25,
+                        lr_warmup_steps=500, reward_scale=0.1, cost_scale=1.0, loss_cost_weight=0.02,
+                        loss_state_weight=0.0, device=device)
+    eng = model._bind(batch, tr._lrs, seed=4321, world_size=world, rank=rank)
+    if spec["algo"] == "cdt":
+        data = synth.make_dataset(o, a, T, 300, seed=200 + rank)
+        SequenceDataset(data, seq_len=10, reward_scale=0.1, cost_scale=1.0, cost_sample=True,
+                        cost_transform=lambda x: 200 - x).to_engine(eng)   # (synthetic episodes cost ~100)
+    else:
+        eng.upload_dataset(synth.make_dataset(o, a, T, max(2, 1_500_000 // T), seed=200 + rank), 0.1, 1.0)
+    return model, eng
+
+
+def run_other(name: str, batch: int, local: int, world: int, rank: int, barrier, peaks, comm_setup):
+    """Short device-resident timing of one other config: CUDA events between barriers, max over ranks."""
+    import torch.distributed as dist
+    spec = OTHER[name]
+    model, eng = build_other(name, batch, f"cuda:{local}", world, rank)
+    if world > 1:
+        comm_setup(eng)
+    K = spec["steps"]
+    eng.steps(5)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.steps(K)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    stats = eng.stats()
+    lps = eng.launches_per_step
+    eng.close()
+    sps = K / ms * 1e3
+    peak_gbs, peak_tf, _ = peaks
+    return {"workload": spec["workload"], "per_gpu_batch": batch, "global_batch": batch * world, "steps": K,
+            "ms_per_step": ms / K, "synchronous_steps_per_s": sps, "launches_per_step": lps,
+            "hbm_frac": spec["bytes"] * sps / 1e9 / peak_gbs, "tflops": spec["flops"] * sps / 1e12,
+            "tensor_frac_of_bf16_peak": spec["flops"] * sps / 1e12 / peak_tf,
+            "tensor_frac_of_3xtf32_ceiling": spec["flops"] * sps / 1e12 / (peak_tf / 6.0),
+            "finite": bool(np.isfinite(list(stats.values())).all())}
 
 
 # ------------------------------------------------------------------------------------------ reference arm
@@ -174,8 +275,8 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch.distributed as dist
-    from osrl_b200 import Engine, comm_unique_id
-    from osrl_b200.algorithms import BCQL, BCQLTrainer
+    from osrl_b200 import comm_unique_id
+    from osrl_b200.algorithms import BCQLTrainer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -184,6 +285,7 @@ def run_ours(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("--gpus N>1 must be launched with torchrun (one process per GPU)")
     torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -193,18 +295,36 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    orc = init_params()
-    eng = Engine("bcql", batch_size=BATCH, device=local, seed=1234, world_size=world, rank=rank, **CFG)
-    eng.load_params(orc.params)
-    if world > 1:
+    def comm_setup(engine):
         ids = [comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
-        eng.init_comm(ids[0])
+        engine.init_comm(ids[0])
+
+    peaks = measured_peaks()
+    peak_gbs, peak_tf, peak_src = peaks
+
+    # ---- data-parallel parity, before anything is timed (N > 1): NCCL engine vs the single-rank oracle on the
+    # concatenated batch -- the small config with an ACTIVE PID multiplier (tests/dp_worker.py) and one step of the
+    # bench configuration itself (global batch 256 N)
+    dp_parity = None
+    if world > 1:
+        from tests import dp_worker
+        small = dp_worker.run("bcql", "nccl", steps=3, Bg=32 * world, detail=True)
+        cfg_act = dict(CFG, cost_limit=0.05)
+        full = dp_worker.run("bcql", "nccl", steps=1, Bg=BATCH * world, cfg=cfg_act, detail=True)
+        dp_parity = {"ok": bool(small["ok"] and full["ok"]), "worst_ratio": max(small["worst_ratio"], full["worst_ratio"]),
+                     "small_active_pid": small, "bench_config_one_step": full}
+
+    # ---- device-resident path: the public model class bound to an engine, dataset shard resident in HBM
+    model = bcql_model(dev)
+    lrs = dict(actor_lr=CFG["actor_lr"], critic_lr=CFG["critic_lr"], vae_lr=CFG["vae_lr"])
+    eng = model._bind(BATCH, lrs, seed=1234, world_size=world, rank=rank)
+    if world > 1:
+        comm_setup(eng)
     data = make_dataset(DATASET_ROWS, seed=100 + rank)      # each rank owns its own shard (weak scaling)
     eng.upload_dataset(data, REWARD_SCALE, COST_SCALE)
 
     K, W = args.steps, max(args.warmup, 3)
-    # ---- device-resident path
     eng.steps(W)
     barrier()
     clocks = ClockSampler(local)
@@ -227,10 +347,7 @@ def run_ours(args):
     value = sync_steps_per_s * world
 
     # ---- end-to-end through the public trainer API with host minibatches
-    torch.manual_seed(0)
-    model = BCQL(8, 2, 1.0, CFG["a_hidden_sizes"], CFG["c_hidden_sizes"], CFG["vae_hidden_sizes"],
-                 CFG["sample_action_num"], CFG["gamma"], CFG["tau"], CFG["phi"], CFG["lmbda"], CFG["beta"], CFG["PID"],
-                 CFG["num_q"], CFG["num_qc"], CFG["cost_limit"], CFG["episode_len"], device=f"cuda:{local}")
+    model2 = bcql_model(dev)
 
     class _Store:
         def __init__(self):
@@ -240,14 +357,11 @@ def run_ours(args):
             self.last = kw
 
     logger = _Store()
-    trainer = BCQLTrainer(model, None, logger, actor_lr=CFG["actor_lr"], critic_lr=CFG["critic_lr"],
-                          vae_lr=CFG["vae_lr"], reward_scale=REWARD_SCALE, cost_scale=COST_SCALE,
-                          device=f"cuda:{local}", seed=99)
+    trainer = BCQLTrainer(model2, None, logger, actor_lr=CFG["actor_lr"], critic_lr=CFG["critic_lr"],
+                          vae_lr=CFG["vae_lr"], reward_scale=REWARD_SCALE, cost_scale=COST_SCALE, device=dev, seed=99)
     if world > 1:
-        model._bind(BATCH, trainer._lrs, seed=99, world_size=world, rank=rank)
-        ids = [comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        model.engine.init_comm(ids[0])
+        model2._bind(BATCH, trainer._lrs, seed=99, world_size=world, rank=rank)
+        comm_setup(model2.engine)
     KE = min(K, 1000)
     rng = np.random.default_rng(7 + rank)
     n = data["observations"].shape[0]
@@ -276,6 +390,67 @@ def run_ours(args):
     e2e_v = KE / ms_e * 1e3 * world
     d2h = 4 * len(eng.stat_names)
     assert logger.last is not None and np.isfinite(list(logger.last.values())).all()
+    model2.engine.close()
+
+    # ---- per-kernel timing inside a replayed graph (osrl_profile), rank 0 only, N == 1
+    roof = None
+    if rank == 0:
+        roof = {"bound": "hbm", "achieved": STEP_BYTES * sync_steps_per_s / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                "frac": STEP_BYTES * sync_steps_per_s / 1e9 / peak_gbs, "traffic": None,
+                "definition": "SURVEY.md 8(d): bytes per step = 24 P_train + 8 P_target + batch bytes = "
+                              f"{STEP_BYTES} B; achieved = bytes x synchronous steps/s; peak = measured HBM copy bandwidth",
+                "peak_source": peak_src,
+                "tensor": {"flops_per_step": STEP_FLOPS, "tflops": STEP_FLOPS * sync_steps_per_s / 1e12,
+                           "frac_of_bf16_peak": STEP_FLOPS * sync_steps_per_s / 1e12 / peak_tf,
+                           "frac_of_3xtf32_ceiling": STEP_FLOPS * sync_steps_per_s / 1e12 / (peak_tf / 6.0),
+                           "note": "fp32-accurate 3xTF32: three TF32 MMAs (half the bf16 rate) per product"}}
+        tp = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")   # warm-cache DRAM bytes of one step (ncu)
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            roof["traffic"] = tj.get("dram_bytes_per_step")
+            roof["traffic_source"] = tj.get("source")
+    if rank == 0 and world == 1:
+        prof = eng.profile(20)
+        in_graph = bool(eng.lib.osrl_profile_was_in_graph(eng.h))
+        agg = {}
+        for name, pms, by, fl in prof:
+            a = agg.setdefault(name, [0.0, 0.0, 0.0, 0])
+            a[0] += pms; a[1] += by; a[2] += fl; a[3] += 1
+        tot = sum(a[0] for a in agg.values())
+        kern = []
+        for k_, d in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+            tensor = k_.startswith("k_fz") or k_.startswith("k_gemm_mma") or k_.startswith("k_gemm_tc5")
+            ent = {"kernel": k_, "launches_per_step": d[3], "us_per_step": 1e3 * d[0], "share_of_step_time": d[0] / tot,
+                   "avg_launch_us": 1e3 * d[0] / d[3], "bound": "tensor" if tensor else "hbm",
+                   "algorithmic_bytes_per_step": d[1], "algorithmic_flops_per_step": d[2],
+                   "gbs": d[1] / (d[0] * 1e-3) / 1e9 if d[0] > 0 else None,
+                   "tflops": d[2] / (d[0] * 1e-3) / 1e12 if d[0] > 0 else None}
+            ent["frac"] = (ent["tflops"] / (peak_tf / 6.0)) if tensor else (ent["gbs"] / peak_gbs)
+            ent["frac_of"] = "3xTF32 ceiling (bf16 peak / 6)" if tensor else "HBM peak (operands are L2-resident)"
+            kern.append(ent)
+        roof["kernels"] = kern
+        roof["kernels_timing"] = ("per launch, inside a replayed CUDA graph with event-record nodes between launches "
+                                  "(osrl_profile)" if in_graph else "eager launches with an event pair around each")
+        roof["sequential_step_us"] = 1e3 * tot
+        roof["note"] = ("the sequential step (sum of the kernels above) is longer than ms_per_step: osrl_steps overlaps the "
+                        "VAE update of step s+1 with the critic / actor updates of step s on a second graph branch")
+
+    # ---- BASELINE.json configs[2..4] (short runs) and the strong-scaling BEAR-Lag point
+    others = {}
+    for name, spec in OTHER.items():
+        try:
+            others[name] = run_other(name, spec["batch"], local, world, rank, barrier, peaks, comm_setup)
+        except Exception as ex:   # a failure here must not take the headline number with it
+            others[name] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+    if 4096 % world == 0:
+        try:
+            r = run_other("bearl_b512", 4096 // world, local, world, rank, barrier, peaks, comm_setup)
+            r["workload"] = "BEAR-Lag OfflineCarCircle-v0-shaped GLOBAL batch=4096 sharded over the GPUs (BASELINE.json configs[4], strong scaling)"
+            r["hbm_frac"] = None if r.get("synchronous_steps_per_s") is None else \
+                (24 * 954_454 + 8 * 620_044 + (4096 // world) * 84) * r["synchronous_steps_per_s"] / 1e9 / peak_gbs
+            others["bearl_strong_b4096"] = r
+        except Exception as ex:
+            others["bearl_strong_b4096"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
 
     if rank != 0:
         if world > 1:
@@ -283,56 +458,11 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- per-kernel timing (CUDA events around every launch, this stream) -> roofline of the dominant kernel
-    peak_gbs, peak_tf, peak_src = measured_peaks()
-    roof = None
-    if world == 1:
-        prof = eng.profile(30)
-        agg = {}
-        for name, pms, by, fl in prof:
-            base = name.split("<")[0]
-            a = agg.setdefault(base, [0.0, 0.0, 0.0, 0])
-            a[0] += pms; a[1] += by; a[2] += fl; a[3] += 1
-        tot = sum(a[0] for a in agg.values())
-
-        traffic = {}
-        tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")   # dram read+write per launch, one ncu --set full capture
-        if os.path.exists(tp):
-            traffic = {k_: v["traffic_bytes_per_launch"] for k_, v in json.load(open(tp))["kernels"].items()}
-
-        def entry(k_):
-            d = agg[k_]
-            tensor = k_ in ("k_gemm_tc5", "k_gemm_mma")     # tensor-core kernels; everything else moves bytes
-            gbs = d[1] / (d[0] * 1e-3) / 1e9
-            tfs = d[2] / (d[0] * 1e-3) / 1e12
-            ent = {"bound": "tensor" if tensor else "hbm", "kernel": k_,
-                   "achieved": tfs if tensor else gbs, "peak": peak_tf if tensor else peak_gbs,
-                   "unit": "TFLOP/s" if tensor else "GB/s", "frac": (tfs / peak_tf) if tensor else (gbs / peak_gbs),
-                   "traffic": traffic.get(k_), "launches_per_step": d[3], "share_of_step_time": d[0] / tot,
-                   "avg_launch_us": 1e3 * d[0] / d[3], "algorithmic_bytes_per_step": d[1],
-                   "algorithmic_flops_per_step": d[2]}
-            if tensor:   # fp32-accurate 3xTF32: three TF32 MMAs (half the bf16 rate) per algorithmic product
-                ent["ceiling_3xtf32_tflops"] = peak_tf / 6.0
-                ent["frac_of_3xtf32_ceiling"] = tfs / (peak_tf / 6.0)
-            return ent
-
-        order = sorted(agg, key=lambda k_: -agg[k_][0])
-        roof = entry(order[0])
-        roof["peak_source"] = peak_src
-        roof["timing"] = "CUDA events around every launch of the step on the engine's stream (osrl_profile, 30 reps)"
-        roof["traffic_source"] = ("profiles/r01_ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per launch, "
-                                  "ncu --set full (cold caches under replay); algorithmic bytes per launch = "
-                                  "algorithmic_bytes_per_step / launches_per_step")
-        roof["other_kernels"] = [entry(k_) for k_ in order[1:4]]
-        roof["step_level"] = {"bytes_per_step": STEP_BYTES, "hbm_gbs": STEP_BYTES * sync_steps_per_s / 1e9,
-                              "flops_per_step": STEP_FLOPS, "tflops": STEP_FLOPS * sync_steps_per_s / 1e12}
-        roof["note"] = ("batch-256 BCQ-Lag is a chain of ~57 dependent launches over L2-resident operands (20 MB): "
-                        "every kernel is bound by launch + L2 latency, not by HBM or tensor throughput -- see DESIGN.md")
-
     # ---- CPU baseline: the oracle port of the reference step on the host cores (bounded sample)
     cpu = None
     if world == 1:
         from oracle import synth
+        orc = init_params()
         r2 = np.random.default_rng(0)
         keys = ("observations", "next_observations", "actions", "rewards", "costs", "done")
         tb = [[torch.from_numpy(b[k]) for k in keys] for b in (synth.make_batch(r2, BATCH, 8, 2) for _ in range(4))]
@@ -354,17 +484,20 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "per_gpu_batch": BATCH,
                    "parallelism": f"dp{world}", "synchronous_steps_per_s": sync_steps_per_s,
                    "value_is": "data-parallel ranks x synchronous steps/s (batch-256 step equivalents)",
-                   "dataset_rows_per_gpu": DATASET_ROWS,
+                   "dataset_rows_per_gpu": DATASET_ROWS, "init": "osrl_b200.algorithms.BCQL under seed_all(0)",
                    "l2": "inputs larger than L2: the resident dataset is 192 MB per GPU and rows are drawn at "
                          "random; parameters/optimizer state (19 MB) are reused every step by construction"},
         "clocks": clk, "gpu_launches": int(launches),
         "e2e": {"value": e2e_v, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": KE, "api": "osrl_b200.algorithms.BCQLTrainer.train_one_step (pinned host tensors) + stats read"},
+        "other_configs": others,
     }
     if roof is not None:
         out["roofline"] = roof
     if cpu is not None:
         out["cpu_baseline"] = cpu
+    if dp_parity is not None:
+        out["dp_parity"] = dp_parity
     print(json.dumps(out))
     if world > 1:
         dist.barrier()

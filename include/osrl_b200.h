@@ -240,11 +240,14 @@ int osrl_debug_gemm(osrl_engine* e, const char* impl, int M, int N, int K, const
  * (0 params, 1 targets, 2 gradients of the last step, 3 Adam m, 4 Adam v). */
 int osrl_debug_read(osrl_engine* e, int section, int64_t offset, int64_t count, float* host_out);
 
-/* Per-launch timing of one step: runs the step program eagerly `reps` times on `stream` with a CUDA
- * event pair around every launch and returns, per launch, its name, mean milliseconds and its
- * algorithmic bytes / flops.  Call with ms == NULL to query the launch count. */
+/* Per-launch timing of one step.  The step program is captured in launch order into a CUDA graph with an
+ * event-record node between consecutive launches and replayed `reps` times (so a launch is timed as it runs
+ * inside the step graph, not with the CPU launch floor of eager launches); returns, per launch, its name,
+ * mean milliseconds and its algorithmic bytes / flops.  Call with ms == NULL to query the launch count.
+ * osrl_profile_was_in_graph() tells whether the last call used the graph (1) or fell back to eager launches. */
 int osrl_profile(osrl_engine* e, int reps, int* n_ops, const char** names, double* ms, double* bytes,
                  double* flops, int cap, void* stream);
+int osrl_profile_was_in_graph(osrl_engine* e);
 
 /* Number of kernels launched by this engine so far / per step. */
 int64_t osrl_launch_count(osrl_engine* e);

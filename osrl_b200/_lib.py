@@ -111,6 +111,7 @@ SYMBOLS = [
     ("osrl_debug_read", C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p]),
     ("osrl_profile", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_char_p), C.POINTER(C.c_double),
                                C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_void_p]),
+    ("osrl_profile_was_in_graph", C.c_int, [C.c_void_p]),
     ("osrl_launch_count", C.c_int64, [C.c_void_p]),
     ("osrl_launches_per_step", C.c_int, [C.c_void_p]),
     ("osrl_comm_unique_id", C.c_int, [C.c_char * 128]),

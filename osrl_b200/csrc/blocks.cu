@@ -12,14 +12,7 @@ void emit_vae_decode(Engine& e, Program& p, const float* W, const float* dec_in,
                      float* out, int ldout, int mode, bool nograd) {
   const VaeLay& v = e.plan.vae;
   const int V = v.d1.out, ldin = v.d1.in;
-  if (fz_mlp_ok(v.d1, v.d2, v.d3) && fz_unfuse_first(rows, nograd)) {
-    flush(e, p, {task_fwd(dec_in, ldin, rows, W, v.d1, h1, V, ACT_RELU)});
-    FzTask t = fz_fwd2(h1, V, rows, W, v.d2, v.d3, ACT_RELU, nullptr, 0, out, ldout);
-    if (mode == 0) { t.ract = ACT_TANH; t.rscale = e.plan.cfg.max_action; }
-    emit_fz(e, p, {t});
-    return;
-  }
-  if (fz_mlp_ok(v.d1, v.d2, v.d3)) {   // the whole decoder in one fused launch
+  if (fz_mlp_ok(v.d1, v.d2, v.d3) && !fz_unfuse_first(rows, nograd)) {   // the whole decoder in one fused launch
     FzTask t = fz_fwd3(dec_in, ldin, rows, W, v.d1, v.d2, v.d3, ACT_RELU, nograd ? nullptr : h1, V, nograd ? nullptr : h2,
                        V, out, ldout);
     if (mode == 0) { t.ract = ACT_TANH; t.rscale = e.plan.cfg.max_action; }
@@ -113,18 +106,10 @@ GemmTask mlp_fwd_hidden(Engine& e, Program& p, const float* W, const MlpLay& m, 
   const float* cur = X;
   int ld = ldx;
   h.clear();
-  if (n == 3 && fz_mlp_ok(m.L[0], m.L[1], m.L[2])) {
+  if (n == 3 && fz_mlp_ok(m.L[0], m.L[1], m.L[2]) && !fz_unfuse_first(rows, nograd)) {
     // fused network: nothing is launched here -- the returned task is a marker that carries the caller's last-layer
     // epilogue to emit_gemm, which completes the fused task (Engine::fz_pending) and launches it
     float *y0 = nullptr, *y1 = nullptr;
-    if (fz_unfuse_first(rows, nograd)) {
-      y0 = e.ws((size_t)rows * m.L[0].out);
-      emit_gemm(e, p, {task_fwd(X, ldx, rows, W, m.L[0], y0, m.L[0].out, hact)});
-      e.fz_pending.push_back(fz_fwd2(y0, m.L[0].out, rows, W, m.L[1], m.L[2], hact, nullptr, 0, out, ldout));
-      GemmTask mk = task_fwd(nullptr, m.L[1].out, rows, W, m.L[2], out, ldout, ACT_NONE);
-      mk.fz_pending = (int)e.fz_pending.size();
-      return mk;
-    }
     if (!nograd) {
       y0 = e.ws((size_t)rows * m.L[0].out); y1 = e.ws((size_t)rows * m.L[1].out);
       h.push_back(y0); h.push_back(y1);

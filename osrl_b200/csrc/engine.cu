@@ -151,7 +151,7 @@ static int thin_kind(const GemmTask& t) {
 static bool pack_producer_ok(const GemmTask& t) {
   const char* v = getenv("OSRL_PACK");   // read at program build, like OSRL_GEMM
   const bool on = !(v && v[0] == '0');
-  return on && gemm_mode() == "tc5" && t.thin == THIN_K && t.pk_gcols >= 64 && t.pk_gcols % 4 == 0 && t.M >= 512 &&
+  return on && (gemm_mode() == "tc5" || gemm_mode() == "fz") && t.thin == THIN_K && t.pk_gcols >= 64 && t.pk_gcols % 4 == 0 && t.M >= 512 &&
          t.N % t.pk_gcols == 0 && t.C != nullptr;
 }
 static void emit_thin(Engine& e, Program& p, std::vector<GemmTask> tasks) {
@@ -286,10 +286,11 @@ FzTask fz_blank() {
   t.scale = 1.f; t.rscale = 1.f; t.a_kc = 1; t.b_kc = 1; t.c_store = 1;
   return t;
 }
-bool fz_mlp_ok(const Lin& l0, const Lin& l1, const Lin& l2) {
-  return fz_on() && l0.in <= fz::GK_MAX && l2.out <= fz::RED_MAX && l0.out == l1.in && l1.out == l2.in &&
-         l1.in % 4 == 0 && l1.out % 4 == 0;
+// middle + last layer fusable (reduce epilogue / generated last-layer dgrad); fz_mlp_ok: the first layer too
+static bool fz_mid_ok(const Lin& l0, const Lin& l1, const Lin& l2) {
+  return fz_on() && l2.out <= fz::RED_MAX && l0.out == l1.in && l1.out == l2.in && l1.in % 4 == 0 && l1.out % 4 == 0;
 }
+bool fz_mlp_ok(const Lin& l0, const Lin& l1, const Lin& l2) { return fz_mid_ok(l0, l1, l2) && l0.in <= fz::GK_MAX; }
 int fz_new_group() {
   static int next = 0;
   return ++next;
@@ -330,12 +331,14 @@ FzTask fz_fwd2(const float* H1, int ldh1, int rows, const float* W, const Lin& l
   t.rout = out; t.ldro = ldo;
   return t;
 }
-// large no-grad passes (targets on B*S rows): every column tile of a fused task regenerates the first layer, and the
-// generation is bound by broadcast shared-memory reads of the weights.  Measured on B200 (BCQ-Lag B=256): actor_old on
-// 5120 rows 57 us fused vs 15 + 41 us split; the 8 target critics 95 us fused vs 21 + 68 + 27 us -- no gain, so the
-// split is off by default (OSRL_FZ_UNFUSE=1 enables it for A/B timing).
+// large no-grad passes (targets on B*S rows): every column tile of a fused task regenerates the first layer (bound by
+// broadcast shared-memory reads of its weights) and the kernel runs one CTA per SM, so on multi-wave launches the
+// per-CTA prologue / epilogue is not hidden.  Those passes keep round 1's split -- thin first layer writing packed tf32
+// images, gemm_tc5 (two CTAs per SM, bulk-copied A) for the middle layer, thin last layer.  Measured on B200 (BCQ-Lag
+// B=256): actor_old on 5120 rows 57 us fused vs 39 us split; CPQ / BEAR-Lag at B=512 (5120-row passes twice per step)
+// 0.46 / 0.56 ms fused vs 0.33 / 0.49 ms.  OSRL_FZ_UNFUSE=0 fuses them too (A/B timing).
 bool fz_unfuse_first(int rows, bool nograd) {
-  static const bool on = [] { const char* v = getenv("OSRL_FZ_UNFUSE"); return v && v[0] == '1'; }();
+  static const bool on = [] { const char* v = getenv("OSRL_FZ_UNFUSE"); return !(v && v[0] == '0'); }();
   return on && nograd && rows >= 1024;
 }
 FzTask fz_bwd_mid(const float* dq, int lddq, int rows, const float* W, const Lin& l1, const Lin& l2, int hact,
@@ -509,13 +512,30 @@ void emit_gemm(Engine& e, Program& p, const std::vector<GemmTask>& tasks_in) {
     }
   if (fz_on()) {   // every tiled problem the fused kernel's plain mode covers goes to tcgen05
     std::vector<FzTask> fzt;
-    std::vector<GemmTask> rest;
+    std::vector<GemmTask> rest, packed;
     for (auto& t : tasks) {
+      // large no-grad passes keep round 1's split: thin first layer -> packed tf32 images -> gemm_tc5 (two CTAs per SM)
+      const Engine::PackReg* reg = nullptr;
+      for (auto& r : e.pack_regs) {
+        const ptrdiff_t off = t.A - r.C;
+        if (t.a_kc && off >= 0 && off < r.N && t.lda == r.ldc && t.M == r.M) reg = &r;
+      }
+      if (reg) {
+        OSRL_REQUIRE(tc5_eligible(t) && t.K == reg->gcols && (t.A - reg->C) % reg->gcols == 0,
+                     "a GEMM reads activations that only exist as packed images");
+        const int grp = (int)((t.A - reg->C) / reg->gcols);
+        t.a_hi = reg->hi + (size_t)grp * reg->gstride;
+        t.a_lo = reg->lo + (size_t)grp * reg->gstride;
+        t.pk_ks = reg->ks;
+        packed.push_back(t);
+        continue;
+      }
       const bool full = t.act == ACT_GELU || t.dact == ACT_GELU || t.mmask != nullptr || t.ksplit > 1;
       // (operand rows are fetched with 16-byte bulk copies: unaligned layouts, e.g. K = 41 first layers, stay on mma.sync)
       if (full || (t.colsum && t.a_kc) || !t.a_vec || !t.b_vec || t.K % 4 != 0) rest.push_back(t);
       else fzt.push_back(fz_from_gemm(t));
     }
+    if (!packed.empty()) emit_tc5(e, p, packed, true);
     emit_fz(e, p, fzt);
     if (rest.empty()) return;
     tasks = rest;
@@ -699,21 +719,28 @@ static bool ens_fz_ok(const EnsLay& l) {
   ens_member(l, 0, l0, l1, l2);
   return fz_mlp_ok(l0, l1, l2);
 }
+static bool ens_fz_mid_ok(const EnsLay& l) {   // wide first layers (CPQ: obs 33 + act 8): only the first layer stays apart
+  if (!fz_on() || l.h.size() != 2) return false;
+  Lin l0, l1, l2;
+  ens_member(l, 0, l0, l1, l2);
+  return fz_mid_ok(l0, l1, l2);
+}
 void ens_fwd(std::vector<Stage>& st, const EnsLay& l, const float* W, const float* X, int ldx, int rows, EnsBuf& buf,
              bool nograd) {
   const int nh = (int)l.h.size();
   OSRL_REQUIRE((int)st.size() >= nh + 1, "ens_fwd: not enough stages");
-  if (ens_fz_ok(l) && fz_unfuse_first(rows, nograd)) {   // thin first layer (one stacked task), then mid + head fused
+  if (!ens_fz_ok(l) && ens_fz_mid_ok(l) && !fz_unfuse_first(rows, nograd)) {
+    // first layer as one stacked GEMM, then per member: middle layer with the Q head in its reduce epilogue
     st[0].tasks.push_back(task_fwd(X, ldx, rows, W, l.first, buf.h[0], l.n * l.h[0], ACT_RELU));
     for (int i = 0; i < l.n; ++i) {
       Lin l0, l1, l2;
       ens_member(l, i, l0, l1, l2);
-      st[1].fz.push_back(fz_fwd2(buf.h[0] + (size_t)i * l.h[0], l.n * l.h[0], rows, W, l1, l2, ACT_RELU, nullptr, 0,
-                                 buf.q + i, l.n));
+      st[1].fz.push_back(fz_fwd2(buf.h[0] + (size_t)i * l.h[0], l.n * l.h[0], rows, W, l1, l2, ACT_RELU,
+                                 nograd ? nullptr : buf.h[1] + (size_t)i * l.h[1], l.n * l.h[1], buf.q + i, l.n));
     }
     return;
   }
-  if (ens_fz_ok(l)) {   // one fused launch: first layer generated, middle layer on tcgen05, Q head in the reduce epilogue
+  if (ens_fz_ok(l) && !fz_unfuse_first(rows, nograd)) {   // one fused launch: first layer generated, middle layer on tcgen05, Q head in the reduce epilogue
     for (int i = 0; i < l.n; ++i) {
       Lin l0, l1, l2;
       ens_member(l, i, l0, l1, l2);
@@ -743,7 +770,7 @@ void ens_bwd(std::vector<Stage>& st, const EnsLay& l, const float* W, float* Gse
              const EnsBuf& act, EnsBuf& grad, const float* dq, float* dX, int lddx, int xcol0, int xcols) {
   const int nh = (int)l.h.size();
   OSRL_REQUIRE((int)st.size() >= nh + 1, "ens_bwd: not enough stages");
-  if (ens_fz_ok(l) && (!dX || xcols <= fz::RED_MAX)) {
+  if (ens_fz_mid_ok(l) && (!dX || xcols <= fz::RED_MAX)) {
     // stage 0: per member, last-layer dgrad generated -> middle-layer dgrad on tcgen05 -> (input gradient summed over
     // the ensemble in the reduce epilogue); stage 1: weight gradients (middle layers on tcgen05, thin ones beside)
     const int grp = dX ? fz_new_group() : 0;
@@ -1731,25 +1758,80 @@ int osrl_profile(osrl_engine* h, int reps, int* n_ops, const char** names, doubl
   *n_ops = n;
   if (!ms) return OSRL_OK;
   OSRL_REQUIRE(cap >= n, "profile buffers too small");
-  std::vector<cudaEvent_t> ev(2 * n);
-  for (auto& x : ev) OSRL_CUDA(cudaEventCreate(&x));
+  // Time the launches INSIDE a captured graph: the step program in launch order (parallel branches serialised) with an
+  // event-record node between consecutive launches, replayed like the real step -- so a launch's time carries the
+  // graph's kernel-to-kernel edge, not the ~6 us CPU launch floor of eager timing.  OSRL_PROFILE_EAGER=1 (or a driver
+  // that refuses to time event nodes) falls back to eager launches with an event pair around each.
   std::vector<double> acc(n, 0.0);
-  for (int r = 0; r < reps; ++r) {
-    prologue(e, s);
-    for (int i = 0; i < n; ++i) {
-      OSRL_CUDA(cudaEventRecord(ev[2 * i], s));
-      e.body.ops[i](s);
-      OSRL_CUDA(cudaEventRecord(ev[2 * i + 1], s));
+  bool done = false;
+  cudaError_t why = cudaSuccess;
+  if (!getenv("OSRL_PROFILE_EAGER")) {
+    // (event-record nodes cannot be timed with cudaEventElapsedTime -- "invalid argument" -- so the graph carries
+    // one-thread timestamp kernels (%globaltimer) between the launches; stamp[0] -> stamp[1] has nothing in between
+    // and measures the cost of a stamp node itself, which is subtracted)
+    cudaStream_t cs = e.cap_stream;
+    const int64_t before = e.launches;
+    unsigned long long* stamps = (unsigned long long*)e.ws((size_t)2 * (n + 3));
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t x = nullptr;
+    bool ok = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      try {
+        prologue(e, cs);
+        k_stamp<<<1, 1, 0, cs>>>(stamps, 0);
+        for (int i = 0; i < n; ++i) {
+          k_stamp<<<1, 1, 0, cs>>>(stamps, i + 1);
+          e.body.ops[i](cs);
+        }
+        k_stamp<<<1, 1, 0, cs>>>(stamps, n + 1);
+        epilogue(e, cs);
+      } catch (...) { ok = false; }
+      const cudaError_t ce = cudaStreamEndCapture(cs, &g);
+      if (ce != cudaSuccess) { why = ce; ok = false; }
     }
-    epilogue(e, s);
-    OSRL_CUDA(cudaStreamSynchronize(s));
-    for (int i = 0; i < n; ++i) {
-      float t = 0.f;
-      OSRL_CUDA(cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]));
-      acc[i] += t;
+    e.launches = before;
+    if (ok && g) {
+      const cudaError_t ce = cudaGraphInstantiate(&x, g, 0);
+      if (ce != cudaSuccess) { why = ce; ok = false; }
+    } else ok = false;
+    if (g) cudaGraphDestroy(g);
+    std::vector<unsigned long long> hs(n + 2);
+    for (int r = 0; ok && r < reps + 2; ++r) {
+      ok = cudaGraphLaunch(x, s) == cudaSuccess && cudaStreamSynchronize(s) == cudaSuccess;
+      if (!ok || r < 2) continue;   // warm-up replays
+      ok = cudaMemcpy(hs.data(), stamps, hs.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess;
+      const double floor_ms = (double)(hs[1] - hs[0]) * 1e-6;
+      for (int i = 0; ok && i < n; ++i) acc[i] += std::max(0.0, (double)(hs[i + 2] - hs[i + 1]) * 1e-6 - floor_ms);
+    }
+    if (x) cudaGraphExecDestroy(x);
+    done = ok;
+    if (!done) {
+      fprintf(stderr, "[osrl_profile] in-graph timing unavailable (%s), falling back to eager launches\n",
+              cudaGetErrorString(why != cudaSuccess ? why : cudaGetLastError()));
+      std::fill(acc.begin(), acc.end(), 0.0);
     }
   }
-  for (auto& x : ev) cudaEventDestroy(x);
+  if (!done) {
+    std::vector<cudaEvent_t> ev2(2 * n);
+    for (auto& x : ev2) OSRL_CUDA(cudaEventCreate(&x));
+    for (int r = 0; r < reps; ++r) {
+      prologue(e, s);
+      for (int i = 0; i < n; ++i) {
+        OSRL_CUDA(cudaEventRecord(ev2[2 * i], s));
+        e.body.ops[i](s);
+        OSRL_CUDA(cudaEventRecord(ev2[2 * i + 1], s));
+      }
+      epilogue(e, s);
+      OSRL_CUDA(cudaStreamSynchronize(s));
+      for (int i = 0; i < n; ++i) {
+        float t = 0.f;
+        OSRL_CUDA(cudaEventElapsedTime(&t, ev2[2 * i], ev2[2 * i + 1]));
+        acc[i] += t;
+      }
+    }
+    for (auto& x : ev2) cudaEventDestroy(x);
+  }
+  e.profile_in_graph = done;
   for (int i = 0; i < n; ++i) {
     ms[i] = acc[i] / reps;
     if (names) names[i] = e.body.meta[i].name.c_str();
@@ -1785,6 +1867,7 @@ int osrl_debug_fz_timelines(osrl_engine* h) {
   OSRL_CATCH
 }
 
+int osrl_profile_was_in_graph(osrl_engine* h) { return h && h->e->profile_in_graph ? 1 : 0; }
 int64_t osrl_launch_count(osrl_engine* h) { return h ? h->e->launches : 0; }
 int osrl_launches_per_step(osrl_engine* h) { return h ? kernels_per_step(*h->e, true) : 0; }
 

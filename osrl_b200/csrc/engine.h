@@ -193,6 +193,7 @@ struct Engine {
   struct PackReg { const float* C; int ldc, M, N, gcols, gstride, ks, dead; float* hi; float* lo; };
   std::vector<PackReg> pack_regs;
   int64_t launches = 0;
+  bool profile_in_graph = false;
   // fused tcgen05 path (gemm_fz.cuh): networks whose last layer is still being described by the caller
   // (mlp_fwd_hidden returns a marker GemmTask, emit_gemm completes and launches the fused task)
   std::vector<FzTask> fz_pending;

@@ -106,6 +106,13 @@ static __global__ void k_epilogue(DevState* ds, int mode) {
   else ds->vae_step += 1ull;
 }
 
+// timestamp node of the in-graph profile (osrl_profile): nanoseconds of the global timer
+static __global__ void k_stamp(unsigned long long* out, int slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  out[slot] = t;
+}
+
 // ------------------------------------------------------------------ Adam (+ Polyak target) over a flat range
 // torch.optim.Adam single-tensor semantics (bias-corrected, eps after sqrt); optional decoupled
 // weight decay (AdamW) and global-norm clip factor; optional fused Polyak update of the target copy

@@ -41,9 +41,10 @@ def shard(x, rank, world):
     return x[rank * n:(rank + 1) * n]
 
 
-def run(algo: str, backend: str, steps: int = 3, Bg: int = 32):
+def run(algo: str, backend: str, steps: int = 3, Bg: int = 32, cfg=None, detail: bool = False):
+    """detail=True: return {"ok", "worst_ratio", ...} instead of the bool (bench.py prints it as `dp_parity`)."""
     rank, world = dist.get_rank(), dist.get_world_size()
-    cfg = CFGS[algo]
+    cfg = CFGS[algo] if cfg is None else cfg
     B = Bg // world
     full = make_oracle(algo, cfg, 0)              # single-rank reference on the concatenated batch
     init = {k: v.clone() for k, v in full.params.items()}
@@ -94,9 +95,18 @@ def run(algo: str, backend: str, steps: int = 3, Bg: int = 32):
     if backend == "nccl":
         ok = ok.cuda()
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-    if rank == 0:
-        print(json.dumps({"algo": algo, "backend": backend, "world": world, "worst_ratio": worst, "ok": bool(ok.item())}))
-    return bool(ok.item())
+    wt = torch.tensor([worst], dtype=torch.float64)
+    if backend == "nccl":
+        wt = wt.cuda()
+    dist.all_reduce(wt, op=dist.ReduceOp.MAX)
+    out = {"algo": algo, "backend": backend, "world": world, "global_batch": Bg, "steps": steps,
+           "worst_ratio": float(wt.item()), "ok": bool(ok.item()),
+           "bound": "final params vs the single-rank oracle on the concatenated batch: |d| <= 1e-3 |delta| + 4e-7 |p| per tensor"}
+    if backend == "nccl":
+        eng.close()
+    if rank == 0 and not detail:
+        print(json.dumps(out))
+    return out if detail else bool(ok.item())
 
 
 def run_pipelined(algo: str, steps: int = 5, Bg: int = 32):
