@@ -114,6 +114,32 @@ class EngineTrainer:
         if self.model.engine is not None:
             self.model.engine.upload_dataset(dataset, rs, cs)
 
+    # -- evaluation (bcql.py:308-340, cpq.py:315-347, bearl.py:414-446): batch-1 policy calls against a CPU environment,
+    # outside the hot path -- plain torch on the arena views, so it always sees the weights the engine just wrote
+    def evaluate(self, eval_episodes):
+        self.model.eval()
+        rets, costs, lens = [], [], []
+        for _ in range(eval_episodes):
+            r, n, c = self.rollout()
+            rets.append(r); lens.append(n); costs.append(c)
+        self.model.train()
+        return np.mean(rets) / self.reward_scale, np.mean(costs) / self.cost_scale, np.mean(lens)
+
+    @torch.no_grad()
+    def rollout(self):
+        """One episode with the current policy: (return, length, cost) in the trainer's scaled units."""
+        obs, info = self.env.reset()
+        ret, cost, n = 0.0, 0.0, 0
+        for _ in range(self.model.episode_len):
+            act, _ = self.model.act(obs)
+            obs, reward, terminated, truncated, info = self.env.step(act)
+            ret += reward
+            cost += info["cost"] * self.cost_scale
+            n += 1
+            if terminated or truncated:
+                break
+        return ret, n, cost
+
     def train_steps(self, n: int, batch_size: Optional[int] = None) -> Dict[str, float]:
         """n gradient steps without touching the host (replaces n iterations of train_bcql.py:142-148)."""
         if self._dataset is None:

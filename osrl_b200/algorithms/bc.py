@@ -44,3 +44,27 @@ class BCTrainer(EngineTrainer):
 
     def train_one_step(self, observations, actions):
         self._step({"observations": observations, "actions": actions})
+
+    def evaluate(self, eval_episodes):
+        """bc.py:111-124: unscaled episode means (BC has no reward / cost scale)."""
+        self.model.eval()
+        out = [self.rollout() for _ in range(eval_episodes)]
+        self.model.train()
+        return np.mean([o[0] for o in out]), np.mean([o[2] for o in out]), np.mean([o[1] for o in out])
+
+    @torch.no_grad()
+    def rollout(self):
+        """bc.py:126-150; "multi-task" BC conditions the policy on the cost limit appended to the observation."""
+        tag = (lambda o: np.append(o, self.cost_limit)) if self.bc_mode == "multi-task" else (lambda o: o)
+        obs, info = self.env.reset()
+        obs = tag(obs)
+        ret, cost, n = 0.0, 0.0, 0
+        for _ in range(self.model.episode_len):
+            obs_next, reward, terminated, truncated, info = self.env.step(self.model.act(obs))
+            obs = tag(obs_next)
+            ret += reward
+            n += 1
+            cost += info["cost"]
+            if terminated or truncated:
+                break
+        return ret, n, cost

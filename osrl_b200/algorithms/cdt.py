@@ -1,6 +1,8 @@
-"""CDT / CDTTrainer with the reference's signatures (osrl/algorithms/cdt.py:45-418), for the mode every
+"""CDT / CDTTrainer with the reference's signatures (osrl/algorithms/cdt.py:45-560), for the mode every
 reference task config uses: time_emb, use_rew, use_cost, cost_transform, stochastic head, 1-layer action
-head, no cost prefix / cost features.  Dropout must be 0 in this build."""
+head, no cost prefix / cost features.  Training (forward, losses, backward, AdamW, the three dropouts) runs in the
+engine; `forward` / `evaluate` / `rollout` below are the evaluation-time path (batch 1 against a CPU environment,
+outside the hot path): plain torch on the parameter views, dropout inactive as in `model.eval()`."""
 from __future__ import annotations
 
 from typing import Optional, Tuple
@@ -13,7 +15,7 @@ from ._base import EngineModel, EngineTrainer
 
 
 class _Block(nn.Module):
-    """Parameter shell of TransformerBlock (net.py:391-441)."""
+    """Parameter shell of TransformerBlock (net.py:391-441); forward = the evaluation-time block."""
 
     def __init__(self, seq_len, embedding_dim, num_heads):
         super().__init__()
@@ -24,6 +26,13 @@ class _Block(nn.Module):
                                  nn.Linear(4 * embedding_dim, embedding_dim), nn.Dropout(0.0))
         self.register_buffer("causal_mask", ~torch.tril(torch.ones(seq_len, seq_len)).to(bool))
 
+    def forward(self, x, padding_mask=None):
+        n = x.shape[1]
+        h = self.norm1(x)
+        x = x + self.attention(h, h, h, attn_mask=self.causal_mask[:n, :n], key_padding_mask=padding_mask,
+                               need_weights=False)[0]
+        return x + self.mlp(self.norm2(x))
+
 
 class _DiagGaussianActor(nn.Module):
     def __init__(self, hidden_dim, act_dim):
@@ -33,6 +42,9 @@ class _DiagGaussianActor(nn.Module):
         for m in (self.mu, self.log_std):   # net.py:521-528 (consumes RNG like the reference)
             nn.init.orthogonal_(m.weight.data)
             m.bias.data.fill_(0.0)
+
+    def forward(self, feat):
+        return torch.distributions.Normal(self.mu(feat), self.log_std(feat).exp())   # net.py:530-533
 
 
 class CDT(EngineModel):
@@ -81,6 +93,25 @@ class CDT(EngineModel):
             torch.nn.init.zeros_(module.bias)
             torch.nn.init.ones_(module.weight)
 
+    def forward(self, states, actions, returns_to_go, costs_to_go, time_steps, padding_mask=None, episode_cost=None):
+        """cdt.py:166-265 for the configured mode: tokens (rtg, ctg, state, action) per step, action distribution from
+        the state token, cost class log-probabilities and next-state prediction from the action token."""
+        B, T = states.shape[0], states.shape[1]
+        te = self.timestep_emb(time_steps)
+        tok = [self.return_emb(returns_to_go.unsqueeze(-1)) + te,
+               self.cost_emb((50 - costs_to_go.detach()).unsqueeze(-1)) + te,      # cost_transform (cdt.py:79)
+               self.state_emb(states) + te, self.action_emb(actions) + te]
+        x = torch.stack(tok, dim=1).permute(0, 2, 1, 3).reshape(B, 4 * T, self.embedding_dim)
+        if padding_mask is not None:
+            padding_mask = torch.stack([padding_mask] * 4, dim=1).permute(0, 2, 1).reshape(B, -1)
+        x = self.emb_norm(x)
+        for blk in self.blocks:
+            x = blk(x, padding_mask=padding_mask)
+        x = self.out_norm(x).reshape(B, T, 4, self.embedding_dim).permute(0, 2, 1, 3)
+        act_feat, state_feat = x[:, 3], x[:, 2]
+        return (self.action_head(state_feat), torch.log_softmax(self.cost_pred_head(act_feat), dim=-1),
+                self.state_pred_head(act_feat))
+
     def temperature(self):
         e = self.engine
         return torch.tensor(np.exp(e.scalars()["log_temperature"]) if e else self.init_temperature)
@@ -107,7 +138,7 @@ class CDTTrainer(EngineTrainer):
         self._lrs = dict(learning_rate=learning_rate, weight_decay=weight_decay, betas=tuple(betas),
                          clip_grad=0.0 if clip_grad is None else clip_grad, lr_warmup_steps=lr_warmup_steps,
                          loss_cost_weight=loss_cost_weight, loss_state_weight=loss_state_weight)
-        self.stochastic, self.max_action = model.stochastic, model.max_action
+        self.stochastic, self.max_action, self.cost_reverse = model.stochastic, model.max_action, cost_reverse
 
     def _store(self, stats):
         self.logger.store(tab="train", **stats)
@@ -127,6 +158,46 @@ class CDTTrainer(EngineTrainer):
         elif eng.batch_size != batch_size:
             raise RuntimeError(f"engine was built for batch_size={eng.batch_size}, got a batch of {batch_size}")
         return eng
+
+    def evaluate(self, num_rollouts, target_return, target_cost):
+        """cdt.py:420-435: mean return / cost / length over `num_rollouts` episodes conditioned on the targets."""
+        self.model.eval()
+        out = [self.rollout(self.model, self.env, target_return, target_cost) for _ in range(num_rollouts)]
+        self.model.train()
+        return (np.mean([o[0] for o in out]) / self.reward_scale, np.mean([o[2] for o in out]) / self.cost_scale,
+                np.mean([o[1] for o in out]))
+
+    @torch.no_grad()
+    def rollout(self, model, env, target_return: float, target_cost: float):
+        """cdt.py:437-518: autoregressive episode -- the last seq_len steps of (state, action, return-to-go,
+        cost-to-go) condition the next action; the targets are decremented by what the environment returned."""
+        dev = model.state_emb.weight.device
+        L = model.episode_len
+        states = torch.zeros(1, L + 1, model.state_dim, device=dev)
+        actions = torch.zeros(1, L, model.action_dim, device=dev)
+        rtg, ctg = torch.zeros(1, L + 1, device=dev), torch.zeros(1, L + 1, device=dev)
+        ts = torch.arange(L, dtype=torch.long, device=dev).view(1, -1)
+        obs, info = env.reset()
+        states[:, 0] = torch.as_tensor(obs, device=dev)
+        rtg[:, 0], ctg[:, 0] = float(target_return), float(target_cost)
+        epi_cost = torch.tensor([float(target_cost)], device=dev)
+        ret, cost, n = 0.0, 0.0, 0
+        for t in range(L):
+            w = slice(max(0, t + 1 - model.seq_len), t + 1)
+            dist, _, _ = model(states[:, w], actions[:, w], rtg[:, w], ctg[:, w], ts[:, w], None, epi_cost)
+            a = (dist.mean if self.stochastic else dist).clamp(-self.max_action, self.max_action)[0, -1].cpu().numpy()
+            obs, reward, terminated, truncated, info = env.step(a)
+            c = ((1.0 - info["cost"]) if self.cost_reverse else info["cost"]) * self.cost_scale
+            actions[:, t] = torch.as_tensor(a, device=dev)
+            states[:, t + 1] = torch.as_tensor(obs, device=dev)
+            rtg[:, t + 1] = rtg[:, t] - reward
+            ctg[:, t + 1] = ctg[:, t] - c
+            ret += reward
+            n += 1
+            cost += info["cost"]
+            if terminated or truncated:
+                break
+        return ret, n, cost
 
     def train_one_step(self, states, actions, returns, costs_return, time_steps, mask, episode_cost, costs):
         eng = self._engine(states.shape[0])
