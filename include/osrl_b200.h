@@ -20,13 +20,14 @@
 extern "C" {
 #endif
 
-#define OSRL_ABI_VERSION 2
+#define OSRL_ABI_VERSION 3
 
 enum { OSRL_OK = 0, OSRL_ERR_ARG = -1, OSRL_ERR_CUDA = -2, OSRL_ERR_STATE = -3, OSRL_ERR_NCCL = -4,
        OSRL_ERR_UNSUPPORTED = -5 };
 
-/* algorithm ids: osrl/algorithms/{bc,bcql,cpq,bearl,cdt}.py */
-enum { OSRL_ALGO_BC = 0, OSRL_ALGO_BCQL = 1, OSRL_ALGO_CPQ = 2, OSRL_ALGO_BEARL = 3, OSRL_ALGO_CDT = 4 };
+/* algorithm ids: osrl/algorithms/{bc,bcql,cpq,bearl,cdt,coptidice}.py */
+enum { OSRL_ALGO_BC = 0, OSRL_ALGO_BCQL = 1, OSRL_ALGO_CPQ = 2, OSRL_ALGO_BEARL = 3, OSRL_ALGO_CDT = 4,
+       OSRL_ALGO_COPTIDICE = 5 };
 
 #define OSRL_MAX_HIDDEN 4
 
@@ -36,6 +37,7 @@ enum { OSRL_ALGO_BC = 0, OSRL_ALGO_BCQL = 1, OSRL_ALGO_CPQ = 2, OSRL_ALGO_BEARL 
  *   CPQ.__init__ cpq.py:38-54,  CPQTrainer.__init__ cpq.py:272-292
  *   BEARL.__init__ bearl.py:46-68, BEARLTrainer.__init__ bearl.py:369-387
  *   CDT.__init__ cdt.py:45-70, CDTTrainer.__init__ cdt.py:291-341
+ *   COptiDICE.__init__ coptidice.py:68-123, COptiDICETrainer.__init__ coptidice.py:267-283
  * Fields an algorithm does not have are ignored. */
 typedef struct osrl_config {
   int32_t algo;
@@ -66,6 +68,13 @@ typedef struct osrl_config {
   int32_t batch_size;  /* rows per rank per step */
   uint64_t seed;       /* Philox key of the on-device sampler / noise */
   int32_t world_size, rank;
+  /* COptiDICE (ABI 3).  The two std vectors are HOST pointers, read once by osrl_engine_create. */
+  int32_t f_type;                 /* 0 chi2, 1 softchi, 2 kl (get_f_div_fn, coptidice.py:15-38) */
+  float init_state_propotion, alpha, cost_ub_epsilon;
+  int32_t num_nu, num_chi;
+  float scalar_lr;                /* Adam lr of tau and lmbda (coptidice.py:233-234) */
+  const float* observations_std;  /* [obs_dim] */
+  const float* actions_std;       /* [act_dim] */
 } osrl_config;
 
 /* One parameter tensor of model.state_dict() (names/shapes identical to the reference's,
@@ -93,6 +102,7 @@ typedef struct osrl_dataset_view {
   const uint8_t* terminals;       /* [n] or NULL */
   const uint8_t* timeouts;        /* [n] or NULL */
   float reward_scale, cost_scale;
+  const float* is_init;           /* [n] or NULL: TransitionDataset(state_init=True) (dataset.py:817-820), COptiDICE */
 } osrl_dataset_view;
 
 /* One collated transition minibatch = the positional arguments of
@@ -108,6 +118,7 @@ typedef struct osrl_batch {
   const float* rewards;
   const float* costs;
   const float* done;
+  const float* is_init;           /* COptiDICE only: 7th element of its batch (coptidice.py:126-127); else NULL */
 } osrl_batch;
 
 /* Noise replay: raw standard-normal draws in the order the reference consumes them

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, os.environ.get("OSRL_B200_LIBNAME", "libosrl_b200
 
 OSRL_MAX_HIDDEN = 4
 OSRL_MAX_NOISE = 32
-ALGO = {"bc": 0, "bcql": 1, "cpq": 2, "bearl": 3, "cdt": 4}
+ALGO = {"bc": 0, "bcql": 1, "cpq": 2, "bearl": 3, "cdt": 4, "coptidice": 5}
 
 
 class Config(C.Structure):
@@ -37,6 +37,9 @@ class Config(C.Structure):
         ("adam_beta2", C.c_float), ("clip_grad", C.c_float), ("lr_warmup_steps", C.c_int32),
         ("loss_cost_weight", C.c_float), ("loss_state_weight", C.c_float),
         ("batch_size", C.c_int32), ("seed", C.c_uint64), ("world_size", C.c_int32), ("rank", C.c_int32),
+        ("f_type", C.c_int32), ("init_state_propotion", C.c_float), ("alpha", C.c_float), ("cost_ub_epsilon", C.c_float),
+        ("num_nu", C.c_int32), ("num_chi", C.c_int32), ("scalar_lr", C.c_float),
+        ("observations_std", C.c_void_p), ("actions_std", C.c_void_p),
     ]
 
 
@@ -49,13 +52,13 @@ class DatasetView(C.Structure):
     _fields_ = [("n", C.c_int64), ("observations", C.c_void_p), ("next_observations", C.c_void_p),
                 ("actions", C.c_void_p), ("rewards", C.c_void_p), ("costs", C.c_void_p), ("done", C.c_void_p),
                 ("terminals", C.c_void_p), ("timeouts", C.c_void_p), ("reward_scale", C.c_float),
-                ("cost_scale", C.c_float)]
+                ("cost_scale", C.c_float), ("is_init", C.c_void_p)]
 
 
 class Batch(C.Structure):
     _fields_ = [("rows", C.c_int32), ("on_host", C.c_int32), ("observations", C.c_void_p),
                 ("next_observations", C.c_void_p), ("actions", C.c_void_p), ("rewards", C.c_void_p),
-                ("costs", C.c_void_p), ("done", C.c_void_p)]
+                ("costs", C.c_void_p), ("done", C.c_void_p), ("is_init", C.c_void_p)]
 
 
 class SeqBatch(C.Structure):

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, os.environ.get("OSRL_B200_LIBNAME", "libosrl_b200.so"))
-SOURCES = ["plan.cu", "engine.cu", "blocks.cu", "algo_bcql.cu", "algo_cpq_bearl.cu", "algo_cdt.cu"]
+SOURCES = ["plan.cu", "engine.cu", "blocks.cu", "algo_bcql.cu", "algo_cpq_bearl.cu", "algo_cdt.cu", "algo_coptidice.cu"]
 # every header next to the sources is a dependency of every object (a stale object is worse than a slow build)
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))) + [os.path.join("..", "..", "include", "osrl_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -7,6 +7,7 @@ arithmetic happens in libosrl_b200.so.  The ``forward`` methods here are only us
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -57,12 +58,16 @@ class SquashedGaussianMLPActor(nn.Module):
         self.log_std_layer = nn.Linear(hidden_sizes[-1], act_dim)
 
     def forward(self, obs, deterministic=False, with_logprob=True, **_):
+        """Evaluation path (net.py:170-205): tanh action and, on request, its log-density with the tanh correction."""
         h = self.net(obs)
         mu = self.mu_layer(h)
-        if deterministic:
-            return torch.tanh(mu), None
         std = torch.exp(torch.clamp(self.log_std_layer(h), -20, 2))
-        return torch.tanh(mu + std * torch.randn_like(std)), None
+        u = mu if deterministic else mu + std * torch.randn_like(std)
+        logp = None
+        if with_logprob:
+            logp = torch.distributions.Normal(mu, std).log_prob(u).sum(-1)
+            logp = logp - (2 * (np.log(2) - u - F.softplus(-2 * u))).sum(1)
+        return torch.tanh(u), logp
 
 
 class EnsembleQCritic(nn.Module):

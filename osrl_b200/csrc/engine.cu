@@ -894,6 +894,7 @@ static void build_program(Engine& e) {
     case OSRL_ALGO_CPQ: build_cpq(e); build_pipelined(e, {0}); break;
     case OSRL_ALGO_BEARL: build_bearl(e); build_pipelined(e, {0}); break;
     case OSRL_ALGO_CDT: build_cdt(e); break;
+    case OSRL_ALGO_COPTIDICE: build_coptidice(e); break;
     default: throw Err(OSRL_ERR_UNSUPPORTED, "algorithm not supported");
   }
 }
@@ -934,6 +935,17 @@ static Engine* create(const osrl_config& cfg, int device) {
     e->b_obs = e->ws((size_t)B * o); e->b_nobs = e->ws((size_t)B * o); e->b_act = e->ws((size_t)B * a);
     e->b_rew = e->ws(B); e->b_cost = e->ws(B); e->b_done = e->ws(B);
     e->b_idx = (int64_t*)e->ws((size_t)B * 2);
+    if (cfg.algo == OSRL_ALGO_COPTIDICE) {
+      OSRL_REQUIRE(cfg.observations_std && cfg.actions_std, "COptiDICE needs observations_std / actions_std");
+      e->b_init = e->ws(B);
+      e->cop_obs_std = e->upload(std::vector<float>(cfg.observations_std, cfg.observations_std + o));
+      e->cop_act_std = e->upload(std::vector<float>(cfg.actions_std, cfg.actions_std + a));
+      DevState hst;
+      memset(&hst, 0, sizeof(hst));
+      hst.cop_tau = hst.cop_lmbda = 1.f;   // torch.ones(1) (coptidice.py:104-105)
+      OSRL_CUDA(cudaMemcpy(e->ds, &hst, sizeof(hst), cudaMemcpyHostToDevice));
+      e->plan.cfg.observations_std = e->plan.cfg.actions_std = nullptr;   // (host pointers are not kept)
+    }
     if (cfg.algo == OSRL_ALGO_CDT) {
       const size_t BT = (size_t)B * cfg.seq_len;
       e->s_states = e->ws(BT * o); e->s_actions = e->ws(BT * a); e->s_returns = e->ws(BT); e->s_ctg = e->ws(BT);
@@ -1045,7 +1057,7 @@ static void sample_front(Engine& e, cudaStream_t s) {
   const int warps_per_block = 8;
   k_sample_gather<<<(e.B + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, s>>>(
       e.ds_rows, e.ds_n, e.ds_stride, c.obs_dim, c.act_dim, nullptr, c.seed, &e.ds->step, (uint32_t)e.rank, e.B, e.b_obs,
-      e.b_nobs, e.b_act, e.b_rew, e.b_cost, e.b_done, e.b_idx);
+      e.b_nobs, e.b_act, e.b_rew, e.b_cost, e.b_done, e.b_idx, e.b_init);
   e.launches++;
   if (!e.noise_buf.empty()) {
     k_noise_fill<<<dim3(64, (unsigned)e.noise_buf.size()), 256, 0, s>>>(e.d_slots_all, (int)e.noise_buf.size(), c.seed,
@@ -1320,7 +1332,9 @@ int osrl_buffer_upload(osrl_engine* h, const osrl_dataset_view* v) {
   OSRL_REQUIRE(v->done || (v->terminals && v->timeouts), "need done or terminals+timeouts");
   OSRL_CUDA(cudaSetDevice(e.device));
   const int o = e.plan.cfg.obs_dim, a = e.plan.cfg.act_dim;
-  const int stride = (2 * o + a + 3 + 3) / 4 * 4;
+  const bool cop = e.plan.cfg.algo == OSRL_ALGO_COPTIDICE;
+  if (cop) OSRL_REQUIRE(v->is_init, "COptiDICE datasets carry is_init (TransitionDataset(state_init=True))");
+  const int stride = (2 * o + a + 3 + (cop ? 1 : 0) + 3) / 4 * 4;
   std::vector<float> packed((size_t)v->n * stride, 0.f);
   const float rs = v->reward_scale, cs = v->cost_scale;
   for (int64_t i = 0; i < v->n; ++i) {
@@ -1331,6 +1345,7 @@ int osrl_buffer_upload(osrl_engine* h, const osrl_dataset_view* v) {
     r[2 * o + a] = v->rewards[i] * rs;   // dataset.py:836 (float32 * weak python float -> float32)
     r[2 * o + a + 1] = v->costs[i] * cs; // dataset.py:837
     r[2 * o + a + 2] = v->done ? v->done[i] : ((v->terminals[i] || v->timeouts[i]) ? 1.f : 0.f);  // :815-816
+    if (cop) r[2 * o + a + 3] = v->is_init[i];
   }
   void* d = nullptr;
   OSRL_CUDA(cudaMalloc(&d, packed.size() * sizeof(float)));
@@ -1496,6 +1511,10 @@ int osrl_step(osrl_engine* h, const osrl_batch* b, const osrl_noise* nz, void* s
     OSRL_CUDA(cudaMemcpyAsync(e.b_cost, b->costs, (size_t)B * sizeof(float), kind, s));
     OSRL_CUDA(cudaMemcpyAsync(e.b_done, b->done, (size_t)B * sizeof(float), kind, s));
   }
+  if (e.plan.cfg.algo == OSRL_ALGO_COPTIDICE) {
+    OSRL_REQUIRE(b->is_init, "COptiDICE batches carry is_init (coptidice.py:126-127)");
+    OSRL_CUDA(cudaMemcpyAsync(e.b_init, b->is_init, (size_t)B * sizeof(float), kind, s));
+  }
   stage_noise_impl(e, nz, s);
   if (!e.g_body) e.g_body = capture(e, false);
   OSRL_CUDA(cudaGraphLaunch(e.g_body, s));
@@ -1578,24 +1597,26 @@ int osrl_stats(osrl_engine* h, float* host_out, int cap, int* n, void* stream) {
 }
 
 static const char* kScalarNames[] = {"step", "pid_error_old", "pid_error_integral", "log_alpha", "n_train_steps",
-                                     "log_temperature", "adam_t0", "adam_t1", "adam_t2", "adam_t3"};
+                                     "log_temperature", "adam_t0", "adam_t1", "adam_t2", "adam_t3", "tau", "lmbda"};
+static const int kNumScalars = 12;
 int osrl_scalar_names(osrl_engine* h, const char** names, int cap, int* n) {
   OSRL_TRY
   OSRL_REQUIRE(h && n, "null argument");
-  *n = 10;
+  *n = kNumScalars;
   if (names)
     for (int i = 0; i < *n && i < cap; ++i) names[i] = kScalarNames[i];
   OSRL_CATCH
 }
 int osrl_scalars_get(osrl_engine* h, double* out, int cap, int* n) {
   OSRL_TRY
-  OSRL_REQUIRE(h && out && n && cap >= 10, "bad argument");
+  OSRL_REQUIRE(h && out && n && cap >= kNumScalars, "bad argument");
   Engine& e = *h->e;
   OSRL_CUDA(cudaSetDevice(e.device));
   OSRL_CUDA(cudaDeviceSynchronize());
   DevState d;
   OSRL_CUDA(cudaMemcpy(&d, e.ds, sizeof(d), cudaMemcpyDeviceToHost));
-  *n = 10;
+  *n = kNumScalars;
+  out[10] = d.cop_tau; out[11] = d.cop_lmbda;   // COptiDICE: raw tau / lmbda (coptidice.py:104-105)
   out[0] = (double)d.step; out[1] = d.pid_e_old; out[2] = d.pid_e_int; out[3] = d.log_alpha;
   out[4] = d.n_train_steps; out[5] = d.log_temperature;
   for (int i = 0; i < 4; ++i) out[6 + i] = d.adam_t[i];
@@ -1603,7 +1624,7 @@ int osrl_scalars_get(osrl_engine* h, double* out, int cap, int* n) {
 }
 int osrl_scalars_set(osrl_engine* h, const double* in, int n) {
   OSRL_TRY
-  OSRL_REQUIRE(h && in && n == 10, "bad argument");
+  OSRL_REQUIRE(h && in && (n == 10 || n == kNumScalars), "bad argument");
   Engine& e = *h->e;
   OSRL_CUDA(cudaSetDevice(e.device));
   OSRL_CUDA(cudaDeviceSynchronize());
@@ -1612,6 +1633,7 @@ int osrl_scalars_set(osrl_engine* h, const double* in, int n) {
   d.step = d.vae_step = (unsigned long long)in[0]; d.pid_e_old = (float)in[1]; d.pid_e_int = (float)in[2];
   d.log_alpha = (float)in[3]; d.n_train_steps = (int)in[4]; d.log_temperature = in[5];
   for (int i = 0; i < 4; ++i) d.adam_t[i] = (int)in[6 + i];
+  if (n == kNumScalars) { d.cop_tau = (float)in[10]; d.cop_lmbda = (float)in[11]; }
   OSRL_CUDA(cudaMemcpy(e.ds, &d, sizeof(d), cudaMemcpyHostToDevice));
   OSRL_CATCH
 }

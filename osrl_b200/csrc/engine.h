@@ -147,6 +147,7 @@ struct Engine {
   int B = 0;
   float *b_obs = nullptr, *b_nobs = nullptr, *b_act = nullptr, *b_rew = nullptr, *b_cost = nullptr, *b_done = nullptr;
   int64_t* b_idx = nullptr;
+  float *b_init = nullptr, *cop_obs_std = nullptr, *cop_act_std = nullptr;   // COptiDICE: is_init column, dataset std vectors
   // CDT sequence minibatch staging (device): [B*T, .] row-major
   float *s_states = nullptr, *s_actions = nullptr, *s_returns = nullptr, *s_ctg = nullptr, *s_mask = nullptr,
         *s_costs = nullptr;
@@ -300,5 +301,6 @@ void build_bcql(Engine& e, int phase = 0);
 void build_cpq(Engine& e, int phase = 0);
 void build_bearl(Engine& e, int phase = 0);
 void build_cdt(Engine& e);
+void build_coptidice(Engine& e);
 
 }  // namespace osrl

@@ -23,6 +23,11 @@ struct DevState {
   double log_temperature;             // CDT: float64 leaf outside state_dict (cdt.py:144)
   double temp_m, temp_v;              // Adam state of log_temperature
   float scratch[16];
+  // COptiDICE dual variables (coptidice.py:104-105): raw values (softplus applied in the step), their Adam state
+  float cop_tau, cop_lmbda;
+  float cop_m[2], cop_v[2];           // [0] tau, [1] lmbda
+  int cop_t[2];
+  float cop_lm_old;                   // softplus(lmbda) of the step's first phase, reused by the policy phase (:204-206)
 };
 
 // ------------------------------------------------------------------ Philox4x32-10
@@ -214,7 +219,7 @@ static __global__ void k_sample_gather(const float* __restrict__ ds_rows, int64_
                                 const int64_t* __restrict__ idx_in, uint64_t seed,
                                 const unsigned long long* __restrict__ step_ctr, uint32_t rank,
                                 int rows, float* obs, float* nobs, float* act, float* rew, float* cost, float* done,
-                                int64_t* idx_out) {
+                                int64_t* idx_out, float* init = nullptr) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= rows) return;
@@ -233,6 +238,7 @@ static __global__ void k_sample_gather(const float* __restrict__ ds_rows, int64_
     if (rew) rew[w] = row[2 * o + a];
     if (cost) cost[w] = row[2 * o + a + 1];
     if (done) done[w] = row[2 * o + a + 2];
+    if (init) init[w] = row[2 * o + a + 3];   // (COptiDICE rows carry is_init, dataset.py:817-820)
   }
 }
 
@@ -791,6 +797,182 @@ static __global__ void k_bear_actor_bwd(const float* __restrict__ x, const float
     dmh[(size_t)b * 2 * a + j] = (float)dmu[j];
     dmh[(size_t)b * 2 * a + a + j] = (raw >= -20.f && raw <= 2.f) ? (float)(dls[j] * (double)sd) : 0.f;
   }
+}
+
+}  // namespace osrl
+
+namespace osrl {
+
+// ====================================================================== COptiDICE (coptidice.py:125-227)
+// f-divergence pieces (get_f_div_fn, coptidice.py:15-38): f_type 0 chi2, 1 softchi, 2 kl
+__device__ __forceinline__ float cop_fprime_inv(float x, int ft) {
+  if (ft == 0) return x + 1.f;
+  if (ft == 1) return x < 0.f ? expf(fminf(x, 0.f)) : x + 1.f;
+  return expf(x - 1.f);
+}
+__device__ __forceinline__ float cop_f(float w, int ft) {
+  if (ft == 0) return 0.5f * (w - 1.f) * (w - 1.f);
+  if (ft == 1) return w < 1.f ? w * (logf(w + 1e-10f) - 1.f) + 1.f : 0.5f * (w - 1.f) * (w - 1.f);
+  return w * logf(w + 1e-10f);
+}
+__device__ __forceinline__ float cop_softplus(float x) { return x > 20.f ? x : log1pf(expf(x)); }   // F.softplus
+__device__ __forceinline__ float block_max(float v, float* sh /*[33]*/) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    float x = (l < (int)(blockDim.x >> 5)) ? sh[l] : -3.0e38f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+    if (l == 0) sh[32] = x;
+  }
+  __syncthreads();
+  return sh[32];
+}
+// one scalar Adam step with torch's constants (bias corrections in double, like k_prologue)
+__device__ __forceinline__ float cop_scalar_adam(float p, float g, float& m, float& v, int& t, float lr) {
+  t += 1;
+  m = m + 0.1f * (g - m);                       // torch: m.lerp_(g, 1 - beta1)
+  v = 0.999f * v + 0.001f * g * g;              // v.mul_(beta2).addcmul_(g, g, 1 - beta2)
+  const double bc1 = 1.0 - pow(0.9, (double)t), bc2 = 1.0 - pow(0.999, (double)t);
+  const float step = (float)((double)lr / bc1), bc2s = (float)sqrt(bc2);
+  return p - step * (m / (sqrtf(v) / bc2s + 1e-8f));
+}
+
+struct CopArgs {
+  const float *q_nu, *q_chi;     // [2B, n]: rows 0..B-1 on observations, B..2B-1 on next_observations
+  int n_nu, n_chi, B;
+  const float *rew, *cost, *done, *init;
+  float gamma, alpha, eps, p0, thres, scalar_lr;
+  int ftype;
+  float *dq_nu, *dq_chi;         // [2B, n] gradients wrt the ensemble outputs (zero except at each row's arg-min)
+  float *e_buf, *w_buf, *ell_buf;  // [B] scratch
+  float* stats;                  // chi_loss, tau_loss, D_kl, Df, td_error, nu_loss, lmbda_loss, actor_loss, tau, lmbda
+};
+__device__ __forceinline__ float cop_min(const float* __restrict__ q, int n, int& arg) {
+  float m = q[0];
+  arg = 0;
+  for (int i = 1; i < n; ++i)
+    if (q[i] < m) { m = q[i]; arg = i; }   // first minimum, like torch.min(dim) (net.py:235-238)
+  return m;
+}
+// nu / chi / tau / lambda phase: every loss, every gradient wrt the network outputs, both scalar Adam steps.
+// One CTA: the chi weights are a softmax over the BATCH (:167-168).  d(nu_loss)/de_b = w_b / B: the derivative of
+// w e - alpha f(w) through w vanishes because f'(w) = e / alpha wherever w > 0 (w = relu(f'^-1(e / alpha))).
+static __global__ void __launch_bounds__(1024) k_cop_main(CopArgs a, DevState* ds) {
+  __shared__ float sh[33];
+  const int B = a.B, tid = threadIdx.x;
+  const float lm = cop_softplus(ds->cop_lmbda), tau = cop_softplus(ds->cop_tau);
+  const float invB = 1.f / (float)B, g1 = 1.f - a.gamma;
+  float s_f = 0.f, s_e2 = 0.f, s_init = 0.f, s_main = 0.f, s_wc = 0.f;
+  for (int i = tid; i < 2 * B * a.n_nu; i += blockDim.x) a.dq_nu[i] = 0.f;
+  if (a.eps != 0.f)
+    for (int i = tid; i < 2 * B * a.n_chi; i += blockDim.x) a.dq_chi[i] = 0.f;
+  __syncthreads();
+  float lmax = -3.0e38f;
+  for (int b = tid; b < B; b += blockDim.x) {
+    int as, an;
+    const float nu_s = cop_min(a.q_nu + (size_t)b * a.n_nu, a.n_nu, as);
+    const float nu_n = cop_min(a.q_nu + (size_t)(B + b) * a.n_nu, a.n_nu, an);
+    const float nd = a.gamma * (1.f - a.done[b]);
+    const float e = (a.rew[b] - lm * a.cost[b]) + nd * nu_n - nu_s;
+    const float w = fmaxf(cop_fprime_inv(e / a.alpha, a.ftype), 0.f);
+    const float fw = cop_f(w, a.ftype), ini = a.init[b] / a.p0;
+    a.e_buf[b] = e; a.w_buf[b] = w;
+    s_f += fw; s_e2 += e * e; s_init += nu_s * ini; s_main += w * e - a.alpha * fw; s_wc += w * a.cost[b];
+    a.dq_nu[(size_t)b * a.n_nu + as] = (g1 * ini - w) * invB;
+    a.dq_nu[(size_t)(B + b) * a.n_nu + an] = w * nd * invB;
+    if (a.eps != 0.f) {
+      int cs, cn;
+      const float chi_s = cop_min(a.q_chi + (size_t)b * a.n_chi, a.n_chi, cs);
+      const float chi_n = cop_min(a.q_chi + (size_t)(B + b) * a.n_chi, a.n_chi, cn);
+      const float ell = g1 * (chi_s * ini) + w * (a.cost[b] + nd * chi_n - chi_s);
+      a.ell_buf[b] = ell;
+      lmax = fmaxf(lmax, ell / tau);
+    }
+  }
+  const float Df = block_sum(s_f, sh) * invB, td = block_sum(s_e2, sh) * invB;
+  const float nu_loss = g1 * (block_sum(s_init, sh) * invB) + block_sum(s_main, sh) * invB;
+  float weighted_c = block_sum(s_wc, sh) * invB, chi_loss = 0.f, tau_loss = 0.f, Dkl = 0.f;
+  if (a.eps != 0.f) {
+    lmax = block_max(lmax, sh);
+    float z = 0.f;
+    for (int b = tid; b < B; b += blockDim.x) z += expf(a.ell_buf[b] / tau - lmax);
+    const float Z = block_sum(z, sh), logZ = logf(Z), logB = logf((float)B);
+    float s_kl = 0.f, s_c = 0.f, s_l = 0.f, s_sl = 0.f;
+    for (int b = tid; b < B; b += blockDim.x) {
+      const float ell = a.ell_buf[b], lg = ell / tau - lmax;
+      const float sm = expf(lg) / Z, wt = sm * (float)B, lw = (lg - logZ) + logB;
+      s_kl += wt * lw - wt + 1.f; s_c += wt * a.w_buf[b] * a.cost[b]; s_l += wt * ell; s_sl += sm * ell;
+    }
+    Dkl = block_sum(s_kl, sh) * invB;
+    weighted_c = block_sum(s_c, sh) * invB;
+    chi_loss = block_sum(s_l, sh) * invB;
+    const float S_ell = block_sum(s_sl, sh);
+    for (int b = tid; b < B; b += blockDim.x) {   // d chi_loss / d ell_b = s_b + (s_b / tau)(ell_b - sum_j s_j ell_j)
+      const float ell = a.ell_buf[b], sm = expf(ell / tau - lmax) / Z;
+      const float dl = sm + (sm / tau) * (ell - S_ell);
+      const float w = a.w_buf[b], ini = a.init[b] / a.p0, nd = a.gamma * (1.f - a.done[b]);
+      int cs, cn;
+      cop_min(a.q_chi + (size_t)b * a.n_chi, a.n_chi, cs);
+      cop_min(a.q_chi + (size_t)(B + b) * a.n_chi, a.n_chi, cn);
+      a.dq_chi[(size_t)b * a.n_chi + cs] = dl * (g1 * ini - w);
+      a.dq_chi[(size_t)(B + b) * a.n_chi + cn] = dl * w * nd;
+    }
+    tau_loss = tau * (a.eps - Dkl);
+  }
+  if (tid == 0) {
+    const float lm_loss = lm * (a.thres - weighted_c);
+    a.stats[0] = chi_loss; a.stats[1] = tau_loss; a.stats[2] = Dkl; a.stats[3] = Df; a.stats[4] = td;
+    a.stats[5] = nu_loss; a.stats[6] = lm_loss; a.stats[8] = tau; a.stats[9] = lm;
+    ds->cop_lm_old = lm;
+    // d softplus(x)/dx = sigmoid(x); tau first, then lambda (coptidice.py:177-193); gradients predate both steps
+    if (a.eps != 0.f) {
+      const float g = (1.f / (1.f + expf(-ds->cop_tau))) * (a.eps - Dkl);
+      ds->cop_tau = cop_scalar_adam(ds->cop_tau, g, ds->cop_m[0], ds->cop_v[0], ds->cop_t[0], a.scalar_lr);
+    }
+    const float gl = (1.f / (1.f + expf(-ds->cop_lmbda))) * (a.thres - weighted_c);
+    ds->cop_lmbda = cop_scalar_adam(ds->cop_lmbda, gl, ds->cop_m[1], ds->cop_v[1], ds->cop_t[1], a.scalar_lr);
+  }
+}
+// noisy inputs of the policy phase (coptidice.py:201-202): x + eps * std * 0.1
+static __global__ void k_cop_noise(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ sd,
+                                   int rows, int d, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * d) out[i] = x[i] + (eps[i] * sd[i % d]) * 0.1f;
+}
+// policy extraction (coptidice.py:203-212): w from the UPDATED nu network and the step's original lambda',
+// loss = -mean(w log N(x; mu, std)) with the pre-tanh Normal; gradient wrt (mu | log_std-before-clamp)
+static __global__ void __launch_bounds__(1024) k_cop_actor_loss(const float* __restrict__ q_nu, int n_nu, int B, int adim,
+                                                                const float* __restrict__ rew, const float* __restrict__ cost,
+                                                                const float* __restrict__ done, float gamma, float alpha,
+                                                                int ftype, const float* __restrict__ mh,
+                                                                const float* __restrict__ xact, float* __restrict__ dmh,
+                                                                float* stat, const DevState* ds) {
+  __shared__ float sh[33];
+  const float lm = ds->cop_lm_old, invB = 1.f / (float)B;
+  float s = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    int dummy;
+    const float nu_s = cop_min(q_nu + (size_t)b * n_nu, n_nu, dummy);
+    const float nu_n = cop_min(q_nu + (size_t)(B + b) * n_nu, n_nu, dummy);
+    const float e = (rew[b] - lm * cost[b]) + gamma * (1.f - done[b]) * nu_n - nu_s;
+    const float w = fmaxf(cop_fprime_inv(e / alpha, ftype), 0.f);
+    float logp = 0.f;
+    for (int d = 0; d < adim; ++d) {
+      const float mu = mh[(size_t)b * 2 * adim + d], raw = mh[(size_t)b * 2 * adim + adim + d];
+      const float ls = fminf(fmaxf(raw, -20.f), 2.f), sd = expf(ls), z = (xact[(size_t)b * adim + d] - mu) / sd;
+      logp += -0.5f * z * z - ls - 0.91893853320467274f;
+      dmh[(size_t)b * 2 * adim + d] = -w * invB * (z / sd);
+      dmh[(size_t)b * 2 * adim + adim + d] = (raw >= -20.f && raw <= 2.f) ? -w * invB * (z * z - 1.f) : 0.f;
+    }
+    s += w * logp;
+  }
+  const float tot = block_sum(s, sh);
+  if (threadIdx.x == 0) *stat = -tot * invB;
 }
 
 }  // namespace osrl

@@ -146,7 +146,7 @@ Plan make_plan(const osrl_config& cfg) {
   const int o = cfg.obs_dim, a = cfg.act_dim, L = 2 * a;
   Alloc al;
   // bcql.py:109-110 / cpq.py:103-105 (python double arithmetic)
-  if (cfg.algo != OSRL_ALGO_BC && cfg.algo != OSRL_ALGO_CDT) {
+  if (cfg.algo != OSRL_ALGO_BC && cfg.algo != OSRL_ALGO_CDT) {   // (COptiDICE: coptidice.py:101-102)
     const double g = (double)cfg.gamma;
     p.q_thres = p.qc_thres =
         (double)cfg.cost_limit * (1.0 - std::pow(g, (double)cfg.episode_len)) / (1.0 - g) / (double)cfg.episode_len;
@@ -244,6 +244,32 @@ Plan make_plan(const osrl_config& cfg) {
         p.noise = {{"vae_eps", B * L},          {"pi_critic", B * a}, {"pi_cost", B * a},
                    {"ood_sample", S * B * a},   {"pi_actor", B * a}};
       }
+      break;
+    }
+    case OSRL_ALGO_COPTIDICE: {
+      // coptidice.py:106-119: actor (squashed Gaussian), nu_network / chi_network = EnsembleQCritic(state_dim, act_dim=0).
+      // tau and lmbda are plain tensors outside state_dict: they live in DevState (osrl_scalars_get / set).
+      OSRL_REQUIRE(cfg.num_nu >= 1 && cfg.num_chi >= 1 && cfg.alpha > 0.f && cfg.init_state_propotion > 0.f &&
+                       cfg.f_type >= 0 && cfg.f_type <= 2, "bad COptiDICE config");
+      OSRL_REQUIRE(cfg.world_size == 1, "COptiDICE is single-GPU: its chi weights are a softmax over the whole batch");
+      auto ah = hidden(cfg.a_hidden, cfg.n_a_hidden);
+      auto ch = hidden(cfg.c_hidden, cfg.n_c_hidden);
+      int64_t b0 = al.top;
+      p.sq_actor = alloc_sq(al, o, a, ah);
+      p.g_actor = add_group(p, "actor", b0, al.top, cfg.actor_lr, false);
+      b0 = al.top;
+      p.critic = alloc_ens(al, cfg.num_nu, o, ch);          // nu_network
+      p.g_critic = add_group(p, "nu_network", b0, al.top, cfg.critic_lr, false);
+      b0 = al.top;
+      p.cost_critic = alloc_ens(al, cfg.num_chi, o, ch);    // chi_network
+      p.g_cost = add_group(p, "chi_network", b0, al.top, cfg.critic_lr, false);
+      emit_sq(p.table, "actor", p.sq_actor, a, 0, p.g_actor);
+      emit_ens(p.table, "nu_network", {"q_nets"}, cfg.num_nu, p.critic, 0, p.g_critic);
+      emit_ens(p.table, "chi_network", {"q_nets"}, cfg.num_chi, p.cost_critic, 0, p.g_cost);
+      p.stat_names = {"loss/chi_loss", "loss/tau_loss",   "loss/D_kl",       "loss/Df",  "loss/td_error",
+                      "loss/nu_loss",  "loss/lmbda_loss", "loss/actor_loss", "loss/tau", "loss/lmbda"};
+      const int64_t B = cfg.batch_size;
+      p.noise = {{"obs_eps", B * o}, {"act_eps", B * a}};
       break;
     }
     case OSRL_ALGO_CDT: {

@@ -17,6 +17,8 @@ from . import _lib
 from ._lib import ALGO, Batch, Config, DatasetView, Noise, ParamDesc, SeqBatch, SeqDatasetView, check
 
 _BATCH_KEYS = ("observations", "next_observations", "actions", "rewards", "costs", "done")
+_STEP_KEYS = _BATCH_KEYS + ("is_init",)   # COptiDICE batches carry a 7th tensor (coptidice.py:126-127)
+_F_TYPES = {"chi2": 0, "softchi": 1, "kl": 2}
 
 
 def make_config(algo: str, *, batch_size: int, seed: int = 0, world_size: int = 1, rank: int = 0, **kw) -> Config:
@@ -42,6 +44,11 @@ def make_config(algo: str, *, batch_size: int, seed: int = 0, world_size: int = 
     if algo == "cdt":
         cfg.episode_len = 1000
         cfg.target_entropy = -float(kw.get("action_dim", 0))
+    # COptiDICE defaults (coptidice.py:68-85, 267-276)
+    cfg.f_type, cfg.init_state_propotion, cfg.alpha, cfg.cost_ub_epsilon = 1, 1.0, 0.5, 0.01
+    cfg.num_nu = cfg.num_chi = 1
+    cfg.scalar_lr = 1e-3
+    cfg._keep = []   # numpy arrays behind the host pointers of the struct
     for k, v in kw.items():
         k = ren.get(k, k)
         if k in ("a_hidden_sizes", "c_hidden_sizes"):
@@ -57,6 +64,12 @@ def make_config(algo: str, *, batch_size: int, seed: int = 0, world_size: int = 
             cfg.pid_kp, cfg.pid_ki, cfg.pid_kd = [float(x) for x in v]
         elif k == "kernel":
             cfg.mmd_kernel = {"gaussian": 0, "laplacian": 1}[v]
+        elif k == "f_type":
+            cfg.f_type = _F_TYPES[v] if isinstance(v, str) else int(v)
+        elif k in ("observations_std", "actions_std"):
+            arr = np.ascontiguousarray(np.asarray(v, dtype=np.float32).reshape(-1))
+            cfg._keep.append(arr)
+            setattr(cfg, k, arr.ctypes.data)
         elif k == "betas":
             cfg.adam_beta1, cfg.adam_beta2 = float(v[0]), float(v[1])
         elif k in ("device", "episode_len_unused"):
@@ -218,6 +231,9 @@ class Engine:
             keep["timeouts"] = np.ascontiguousarray(data["timeouts"]).astype(np.uint8)
             v.terminals, v.timeouts = keep["terminals"].ctypes.data, keep["timeouts"].ctypes.data
         v.reward_scale, v.cost_scale = float(reward_scale), float(cost_scale)
+        if "is_init" in data:
+            keep["is_init"] = np.ascontiguousarray(data["is_init"], dtype=np.float32)
+            v.is_init = keep["is_init"].ctypes.data
         check(self.lib.osrl_buffer_upload(self.h, C.byref(v)))
         self.dataset_size = int(v.n)
 
@@ -292,7 +308,7 @@ class Engine:
         b = Batch()
         b.rows = self.batch_size
         kinds = set()
-        for k in _BATCH_KEYS:
+        for k in _STEP_KEYS:
             if k not in batch or batch[k] is None:
                 continue
             t, p, on_host = _as_f32(batch[k], self.device)

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol(lib_built):
     assert declared == bound, declared ^ bound
     for name in declared:
         assert hasattr(lib_built, name)
-    assert lib_built.osrl_abi_version() == int(re.search(r"#define\s+OSRL_ABI_VERSION\s+(\d+)", hdr).group(1)) == 2
+    assert lib_built.osrl_abi_version() == int(re.search(r"#define\s+OSRL_ABI_VERSION\s+(\d+)", hdr).group(1)) == 3
 
 
 @pytest.mark.parametrize("case", ["bc_small", "bcql_small", "cpq_small", "bearl_small", "bcql_full", "cdt_small"])
