@@ -387,7 +387,24 @@ def run_ours(args):
         t = torch.tensor([ms_e], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e = float(t.item())
-    e2e_v = KE / ms_e * 1e3 * world
+    e2e_sync = KE / ms_e * 1e3 * world
+    # the same loop with lagged stats (osrl_stats_lagged: the D2H read of step s-1's stats is still inside every
+    # iteration, but nothing waits for step s): the host queues the next step while the GPU runs the current one
+    trainer.lag_stats = True
+    for i in range(W):
+        trainer.train_one_step(*host[i % nb])
+    barrier()
+    e0.record()
+    for i in range(KE):
+        trainer.train_one_step(*host[i % nb])
+    e1.record()
+    barrier()
+    ms_l = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_l], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_l = float(t.item())
+    e2e_v = KE / ms_l * 1e3 * world
     d2h = 4 * len(eng.stat_names)
     assert logger.last is not None and np.isfinite(list(logger.last.values())).all()
     model2.engine.close()
@@ -489,7 +506,9 @@ def run_ours(args):
                          "random; parameters/optimizer state (19 MB) are reused every step by construction"},
         "clocks": clk, "gpu_launches": int(launches),
         "e2e": {"value": e2e_v, "unit": "steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "steps": KE, "api": "osrl_b200.algorithms.BCQLTrainer.train_one_step (pinned host tensors) + stats read"},
+                "steps": KE, "api": "osrl_b200.algorithms.BCQLTrainer.train_one_step (pinned host tensors) + stats read",
+                "stats": "lagged by one step (trainer lag_stats=True -> osrl_stats_lagged, no stream sync)",
+                "value_with_synchronous_stats": e2e_sync},
         "other_configs": others,
     }
     if roof is not None:

@@ -251,6 +251,20 @@ int osrl_debug_gemm(osrl_engine* e, const char* impl, int M, int N, int K, const
  * (0 params, 1 targets, 2 gradients of the last step, 3 Adam m, 4 Adam v). */
 int osrl_debug_read(osrl_engine* e, int section, int64_t offset, int64_t count, float* host_out);
 
+/* Lagged, sync-free statistics (the reference syncs per scalar with .item(), bcql.py:131-207):
+ * enqueues an async copy of the CURRENT stats into an internal pinned buffer on `stream` and returns the stats of the
+ * PREVIOUS call (whose copy has long completed) without synchronising the stream.  *valid = 0 on the first call. */
+int osrl_stats_lagged(osrl_engine* e, float* host_out, int cap, int* n, int* valid, void* stream);
+
+/* Resumable checkpoint (the reference saves {"model_state": state_dict} only, train_bcql.py:108-109; optimiser
+ * moments, Polyak targets, PID / dual variables, Adam step counts and the Philox step counters are lost).
+ * osrl_state_save writes one self-describing blob (header, P | T | M | V arena sections, device state) into a host
+ * buffer of osrl_state_size bytes; osrl_state_load restores it into an engine built from the same osrl_config --
+ * training then continues bit-identically. */
+int osrl_state_size(osrl_engine* e, int64_t* bytes);
+int osrl_state_save(osrl_engine* e, void* host_buf, int64_t cap);
+int osrl_state_load(osrl_engine* e, const void* host_buf, int64_t bytes);
+
 /* Per-launch timing of one step.  The step program is captured in launch order into a CUDA graph with an
  * event-record node between consecutive launches and replayed `reps` times (so a launch is timed as it runs
  * inside the step graph, not with the CPU launch floor of eager launches); returns, per launch, its name,

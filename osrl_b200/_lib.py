@@ -112,6 +112,10 @@ SYMBOLS = [
     ("osrl_debug_gemm", C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                   C.c_void_p, C.c_void_p]),
     ("osrl_debug_read", C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p]),
+    ("osrl_stats_lagged", C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]),
+    ("osrl_state_size", C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    ("osrl_state_save", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    ("osrl_state_load", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     ("osrl_profile", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_char_p), C.POINTER(C.c_double),
                                C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_void_p]),
     ("osrl_profile_was_in_graph", C.c_int, [C.c_void_p]),

@@ -67,7 +67,7 @@ class EngineTrainer:
     lr_names = ()
 
     def __init__(self, model: EngineModel, env=None, logger=None, reward_scale: float = 1.0, cost_scale: float = 1.0,
-                 device="cuda:0", noise: str = "device", seed: int = 0, log_every: int = 1):
+                 device="cuda:0", noise: str = "device", seed: int = 0, log_every: int = 1, lag_stats: bool = False):
         self.model = model
         self.logger = logger if logger is not None else DummyLogger()
         self.env = env
@@ -77,6 +77,9 @@ class EngineTrainer:
         self.noise_mode = noise
         self.seed = seed
         self.log_every = log_every
+        # lag_stats: logger.store() receives the stats of the PREVIOUS step, read without a stream synchronisation
+        # (osrl_stats_lagged): the host queues step s+1 while the GPU still runs step s
+        self.lag_stats = lag_stats
         self._n = 0
         self._dataset = None
 
@@ -104,7 +107,29 @@ class EngineTrainer:
         eng.step(batch, noise)
         self._n += 1
         if self.log_every and self._n % self.log_every == 0:
-            self._store(eng.stats())
+            if self.lag_stats:
+                st = eng.stats_lagged()
+                if st is not None:
+                    self._store(st)
+            else:
+                self._store(eng.stats())
+
+    # -- resumable checkpoint: {"model_state": ...} stays what the reference writes (train_bcql.py:108-109); the extra
+    # key carries what it loses (optimiser moments, targets, PID / dual variables, step counters)
+    def checkpoint(self) -> dict:
+        out = {"model_state": self.model.state_dict()}
+        if self.model.engine is not None:
+            out["engine_state"] = self.model.engine.state_blob()
+            out["n_steps"] = self._n
+        return out
+
+    def load_checkpoint(self, ckpt: dict, batch_size: Optional[int] = None) -> None:
+        self.model.load_state_dict(ckpt["model_state"])
+        if "engine_state" in ckpt:
+            eng = self._engine(batch_size if batch_size is not None else (self.model.engine.batch_size
+                                                                          if self.model.engine else 256))
+            eng.load_state_blob(ckpt["engine_state"])
+            self._n = int(ckpt.get("n_steps", 0))
 
     # -- fast path: dataset resident in HBM, sampling on the device
     def set_dataset(self, dataset: dict, reward_scale: Optional[float] = None, cost_scale: Optional[float] = None):

@@ -9,7 +9,6 @@ front is a sort + scan, so the reference's `oapackage` dependency (dataset.py:9-
 """
 from __future__ import annotations
 
-import heapq
 import random
 from collections import Counter
 
@@ -231,15 +230,11 @@ class SequenceDataset(IterableDataset):
         c0 = np.array([t[3][0] for t in traj], dtype=np.float64)
         aug = []
         self.pareto_frontier = None
-        if pf_only:                       # dataset.py:509-547: per cost bin the npb best returns above rmin
+        if pf_only:
+            # dataset.py:702-707 selects the best `npb` returns per cost bin (select_optimal_trajectory, :509-547) into
+            # self.dataset -- and :725 then overwrites self.dataset with original + augmented unconditionally, so in the
+            # reference pf_only only prints its banner and suppresses augmentation.  Reproduced as is.
             print("*" * 100 + "\nUsing pareto frontier data points only!!!!!\n" + "*" * 100)
-            step = (max(c0) - min(c0)) / cost_bins
-            bins = {}
-            for i in range(n_orig):
-                if r0[i] >= rmin:
-                    bins.setdefault((c0[i] - min(c0)) // step, []).append(i)
-            chosen = [i for members in bins.values() for i in heapq.nlargest(npb, members, key=lambda j: r0[j])]
-            selected = [traj[i] for i in chosen]
         elif random_aug > 0:              # dataset.py:550-630
             num = int(random_aug * n_orig)
             tgt = np.random.uniform(low=(aug_cmin, aug_rmin), high=(aug_cmax, aug_rmax), size=(num, 2))
@@ -271,10 +266,9 @@ class SequenceDataset(IterableDataset):
                 lo, hi, r, c = traj[keep[i]]
                 aug.append((lo, hi, (r + (p[1] - r[0])).astype(r.dtype), (c + (p[0] - c[0])).astype(c.dtype)))
             self.idx, self.indices = srcs, keep
-        selected = selected if pf_only else traj
-        self._traj = selected + aug
-        self.n_original, self.n_augmented = len(selected), len(aug)
-        print(f"original data: {len(traj)}, augment data: {len(aug)}, total: {len(traj) + len(aug) if not pf_only else len(self._traj)}")
+        self._traj = traj + aug
+        self.n_original, self.n_augmented = len(traj), len(aug)
+        print(f"original data: {len(traj)}, augment data: {len(aug)}, total: {len(self._traj)}")
 
         first_c = np.array([t[3][0] for t in self._traj])          # float32, like dataset.py:452-458
         first_r = np.array([t[2][0] for t in self._traj])

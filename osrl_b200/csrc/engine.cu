@@ -839,6 +839,10 @@ static void free_all(Engine* e) {
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->side_stream) cudaStreamDestroy(e->side_stream);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (e->stats_pinned[i]) cudaFreeHost(e->stats_pinned[i]);
+    if (e->stats_ev[i]) cudaEventDestroy(e->stats_ev[i]);
+  }
   for (auto& ps : e->par_streams)
     for (cudaStream_t x : ps.second) cudaStreamDestroy(x);
   for (cudaEvent_t ev : e->par_events) cudaEventDestroy(ev);
@@ -1593,6 +1597,79 @@ int osrl_stats(osrl_engine* h, float* host_out, int cap, int* n, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   OSRL_CUDA(cudaMemcpyAsync(host_out, e.stats, *n * sizeof(float), cudaMemcpyDeviceToHost, s));
   OSRL_CUDA(cudaStreamSynchronize(s));
+  OSRL_CATCH
+}
+
+int osrl_stats_lagged(osrl_engine* h, float* host_out, int cap, int* n, int* valid, void* stream) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && host_out && n && valid, "null argument");
+  Engine& e = *h->e;
+  *n = (int)e.plan.stat_names.size();
+  OSRL_REQUIRE(cap >= *n, "stats buffer too small");
+  OSRL_CUDA(cudaSetDevice(e.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!e.stats_pinned[0])
+    for (int i = 0; i < 2; ++i) {
+      OSRL_CUDA(cudaMallocHost((void**)&e.stats_pinned[i], 16 * sizeof(float)));
+      OSRL_CUDA(cudaEventCreateWithFlags(&e.stats_ev[i], cudaEventDisableTiming));
+    }
+  const int cur = e.stats_slot, prev = cur ^ 1;
+  OSRL_CUDA(cudaMemcpyAsync(e.stats_pinned[cur], e.stats, *n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  OSRL_CUDA(cudaEventRecord(e.stats_ev[cur], s));
+  *valid = e.stats_calls > 0;
+  if (*valid) {
+    OSRL_CUDA(cudaEventSynchronize(e.stats_ev[prev]));   // (recorded one step ago: no wait in steady state)
+    memcpy(host_out, e.stats_pinned[prev], *n * sizeof(float));
+  }
+  e.stats_slot = prev;
+  e.stats_calls++;
+  OSRL_CATCH
+}
+
+// ---- resumable checkpoint blob: header | P | T | M | V | DevState
+struct StateHeader { char magic[8]; int32_t abi, algo; int64_t nP; int32_t dev_state_bytes, reserved; };
+int osrl_state_size(osrl_engine* h, int64_t* bytes) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && bytes, "null argument");
+  *bytes = (int64_t)sizeof(StateHeader) + 4 * h->e->plan.nP * (int64_t)sizeof(float) + (int64_t)sizeof(DevState);
+  OSRL_CATCH
+}
+int osrl_state_save(osrl_engine* h, void* host_buf, int64_t cap) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && host_buf, "null argument");
+  Engine& e = *h->e;
+  const int64_t sec = e.plan.nP * (int64_t)sizeof(float);
+  OSRL_REQUIRE(cap >= (int64_t)sizeof(StateHeader) + 4 * sec + (int64_t)sizeof(DevState), "state buffer too small");
+  OSRL_CUDA(cudaSetDevice(e.device));
+  OSRL_CUDA(cudaDeviceSynchronize());
+  StateHeader hd;
+  memset(&hd, 0, sizeof(hd));
+  memcpy(hd.magic, "OSRLB200", 8);
+  hd.abi = OSRL_ABI_VERSION; hd.algo = e.plan.cfg.algo; hd.nP = e.plan.nP; hd.dev_state_bytes = (int32_t)sizeof(DevState);
+  char* o = (char*)host_buf;
+  memcpy(o, &hd, sizeof(hd)); o += sizeof(hd);
+  for (float* src : {e.P, e.T, e.M, e.V}) { OSRL_CUDA(cudaMemcpy(o, src, sec, cudaMemcpyDeviceToHost)); o += sec; }
+  OSRL_CUDA(cudaMemcpy(o, e.ds, sizeof(DevState), cudaMemcpyDeviceToHost));
+  OSRL_CATCH
+}
+int osrl_state_load(osrl_engine* h, const void* host_buf, int64_t bytes) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && host_buf, "null argument");
+  Engine& e = *h->e;
+  const int64_t sec = e.plan.nP * (int64_t)sizeof(float);
+  OSRL_REQUIRE(bytes >= (int64_t)sizeof(StateHeader), "state blob truncated");
+  StateHeader hd;
+  memcpy(&hd, host_buf, sizeof(hd));
+  OSRL_REQUIRE(memcmp(hd.magic, "OSRLB200", 8) == 0, "not an osrl_b200 state blob");
+  OSRL_REQUIRE(hd.abi == OSRL_ABI_VERSION && hd.algo == e.plan.cfg.algo && hd.nP == e.plan.nP &&
+                   hd.dev_state_bytes == (int32_t)sizeof(DevState),
+               "state blob was written by a different engine configuration / ABI");
+  OSRL_REQUIRE(bytes >= (int64_t)sizeof(StateHeader) + 4 * sec + (int64_t)sizeof(DevState), "state blob truncated");
+  OSRL_CUDA(cudaSetDevice(e.device));
+  OSRL_CUDA(cudaDeviceSynchronize());
+  const char* o = (const char*)host_buf + sizeof(hd);
+  for (float* dst : {e.P, e.T, e.M, e.V}) { OSRL_CUDA(cudaMemcpy(dst, o, sec, cudaMemcpyHostToDevice)); o += sec; }
+  OSRL_CUDA(cudaMemcpy(e.ds, o, sizeof(DevState), cudaMemcpyHostToDevice));
   OSRL_CATCH
 }
 

@@ -188,6 +188,9 @@ struct Engine {
   std::vector<cudaEvent_t> par_events;
   size_t par_events_used = 0;
   float* stats = nullptr;
+  float* stats_pinned[2] = {nullptr, nullptr};   // osrl_stats_lagged double buffer
+  cudaEvent_t stats_ev[2] = {nullptr, nullptr};
+  int stats_slot = 0, stats_calls = 0;
   std::vector<void*> allocs;
   // packed tf32 hi/lo activation images announced by producer GEMM tasks (GemmTask::pk_*), looked up by the
   // consumer that reads the same activations: see emit_gemm

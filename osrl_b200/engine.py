@@ -384,6 +384,27 @@ class Engine:
         check(self.lib.osrl_stats(self.h, buf, 16, C.byref(n), C.c_void_p(self._stream())))
         return {self.stat_names[i]: float(buf[i]) for i in range(n.value)}
 
+    def stats_lagged(self) -> Optional[Dict[str, float]]:
+        """Stats of the PREVIOUS call's step, without synchronising the stream (None on the first call)."""
+        buf = (C.c_float * 16)()
+        n, valid = C.c_int(), C.c_int()
+        check(self.lib.osrl_stats_lagged(self.h, buf, 16, C.byref(n), C.byref(valid), C.c_void_p(self._stream())))
+        return {self.stat_names[i]: float(buf[i]) for i in range(n.value)} if valid.value else None
+
+    # ------------------------------------------------------------------ resumable checkpoint
+    def state_blob(self) -> torch.Tensor:
+        """Everything a bit-exact resume needs (parameters, targets, Adam moments, PID / dual variables, step counters
+        of the Philox streams) as one uint8 tensor; `load_state_blob` restores it into an engine of the same config."""
+        nb = C.c_int64()
+        check(self.lib.osrl_state_size(self.h, C.byref(nb)))
+        t = torch.empty(nb.value, dtype=torch.uint8)
+        check(self.lib.osrl_state_save(self.h, C.c_void_p(t.data_ptr()), nb.value))
+        return t
+
+    def load_state_blob(self, blob: torch.Tensor) -> None:
+        t = blob.detach().to(torch.uint8).cpu().contiguous()
+        check(self.lib.osrl_state_load(self.h, C.c_void_p(t.data_ptr()), t.numel()))
+
     def scalars(self) -> Dict[str, float]:
         names = (C.c_char_p * 16)()
         n = C.c_int()

@@ -277,3 +277,36 @@ def test_pipelined_steps_equal_sequential(lib_built, algo):
     assert np.array_equal(seq.last_indices(), pipe.last_indices())
     for eng in engs:
         eng.close()
+
+
+@pytest.mark.parametrize("algo", ["bcql", "bearl"])
+def test_state_blob_resume_is_bit_exact(lib_built, algo):
+    """SURVEY 8f rank 2: osrl_state_save / osrl_state_load carry everything the reference's {"model_state": ...}
+    checkpoint loses (Adam moments, targets, PID state, Adam step counts, Philox step counters): 3 steps + save + 4
+    steps  ==  load into a FRESH engine + the same 4 steps, bit for bit; and the lagged stats equal the synchronous ones."""
+    z, meta = load_golden(f"{algo}_pid_small")
+    cfg, B = meta["cfg"], meta["B"]
+    data = synth.make_dataset(cfg["state_dim"], cfg["action_dim"], 50, 20, seed=1)
+    orc = make_oracle(algo, cfg, 0)
+    a = _engine(meta, B)
+    a.load_params(orc.params)
+    a.upload_dataset(data, 0.1, 1.0)
+    a.steps(3)
+    blob = a.state_blob()
+    a.steps(4)
+    b = _engine(meta, B)
+    b.upload_dataset(data, 0.1, 1.0)
+    b.load_state_blob(blob)
+    b.steps(4)
+    for sec in ("param", "target", "adam_m", "adam_v"):
+        x, y = a.read_section(sec), b.read_section(sec)
+        for k in x:
+            assert torch.equal(x[k], y[k]), f"{sec} {k} differs after resume"
+    assert a.scalars() == b.scalars() and a.stats() == b.stats()
+    assert np.array_equal(a.last_indices(), b.last_indices())
+    # lagged stats: call s returns the stats of step s-1
+    assert a.stats_lagged() is None
+    prev = a.stats()
+    a.steps(1)
+    assert a.stats_lagged() == prev
+    a.close(); b.close()
