@@ -172,15 +172,15 @@ template <int D>
 static __global__ void k_attn_fwd(const float* __restrict__ qkv, const float* __restrict__ mask, int L, int H,
                                   int tok_per_step, float* __restrict__ out, float* __restrict__ lse,
                                   const float* __restrict__ pdrop) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int E = H * D, b = blockIdx.x, T = L / tok_per_step;
   float* Ks = sm;              // [L][E]
   float* Vs = sm + L * E;      // [L][E]
   const float* base = qkv + (size_t)b * L * 3 * E;
-  for (int e = threadIdx.x; e < L * E; e += blockDim.x) {
-    const int j = e / E, c = e % E;
-    Ks[e] = base[(size_t)j * 3 * E + E + c];
-    Vs[e] = base[(size_t)j * 3 * E + 2 * E + c];
+  for (int e4 = threadIdx.x; e4 < L * E / 4; e4 += blockDim.x) {
+    const int e = e4 * 4, j = e / E, c = e % E;
+    *reinterpret_cast<float4*>(Ks + e) = *reinterpret_cast<const float4*>(base + (size_t)j * 3 * E + E + c);
+    *reinterpret_cast<float4*>(Vs + e) = *reinterpret_cast<const float4*>(base + (size_t)j * 3 * E + 2 * E + c);
   }
   __syncthreads();
   const int h = threadIdx.x / L, i = threadIdx.x % L;
@@ -193,16 +193,27 @@ static __global__ void k_attn_fwd(const float* __restrict__ qkv, const float* __
   float m = -INFINITY, l = 0.f;
   for (int j = 0; j <= i; ++j) {
     if (mask[(size_t)b * T + j / tok_per_step] <= 0.f) continue;
+    float kj[D], vj[D];
+    {
+      const float4* __restrict__ kp = reinterpret_cast<const float4*>(Ks + j * E + h * D);
+      const float4* __restrict__ vp = reinterpret_cast<const float4*>(Vs + j * E + h * D);
+#pragma unroll
+      for (int q4 = 0; q4 < D / 4; ++q4) {
+        const float4 a = kp[q4], v = vp[q4];
+        kj[4 * q4] = a.x; kj[4 * q4 + 1] = a.y; kj[4 * q4 + 2] = a.z; kj[4 * q4 + 3] = a.w;
+        vj[4 * q4] = v.x; vj[4 * q4 + 1] = v.y; vj[4 * q4 + 2] = v.z; vj[4 * q4 + 3] = v.w;
+      }
+    }
     float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < D; ++c) s = fmaf(q[c], Ks[j * E + h * D + c], s);
+    for (int c = 0; c < D; ++c) s = fmaf(q[c], kj[c], s);
     s *= scale;
     const float mn = fmaxf(m, s);
     const float corr = expf(m - mn), p = expf(s - mn);
     l = l * corr + p;
     const float pv = drow ? p * drow[j] : p;
 #pragma unroll
-    for (int c = 0; c < D; ++c) acc[c] = acc[c] * corr + pv * Vs[j * E + h * D + c];
+    for (int c = 0; c < D; ++c) acc[c] = acc[c] * corr + pv * vj[c];
     m = mn;
   }
   const float inv = 1.f / l;
@@ -211,12 +222,23 @@ static __global__ void k_attn_fwd(const float* __restrict__ qkv, const float* __
   lse[((size_t)b * H + h) * L + i] = m + logf(l);
 }
 
+// row r, head h of a [L][E] shared tile as D/4 float4 (16-byte shared loads: a quarter of the LDS instructions of
+// the scalar form, which bound this kernel -- every FMA operand of the inner loops comes from shared memory)
+template <int D>
+__device__ __forceinline__ void ld_row(const float* __restrict__ tile, int r, int E, int h, float (&v)[D]) {
+  const float4* __restrict__ p = reinterpret_cast<const float4*>(tile + r * E + h * D);
+#pragma unroll
+  for (int q = 0; q < D / 4; ++q) {
+    const float4 x = p[q];
+    v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+  }
+}
 template <int D>
 static __global__ void k_attn_bwd(const float* __restrict__ qkv, const float* __restrict__ mask, int L, int H,
                                   int tok_per_step, const float* __restrict__ out, const float* __restrict__ dout,
                                   const float* __restrict__ lse, float* __restrict__ dqkv,
                                   const float* __restrict__ pdrop) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int E = H * D, b = blockIdx.x, T = L / tok_per_step;
   float* Qs = sm;
   float* Ks = sm + L * E;
@@ -225,12 +247,12 @@ static __global__ void k_attn_bwd(const float* __restrict__ qkv, const float* __
   float* Ls = sm + 4 * L * E;      // [H*L] log-sum-exp
   float* Ds = Ls + H * L;          // [H*L] rowsum(dO * O)
   const float* base = qkv + (size_t)b * L * 3 * E;
-  for (int e = threadIdx.x; e < L * E; e += blockDim.x) {
-    const int j = e / E, c = e % E;
-    Qs[e] = base[(size_t)j * 3 * E + c];
-    Ks[e] = base[(size_t)j * 3 * E + E + c];
-    Vs[e] = base[(size_t)j * 3 * E + 2 * E + c];
-    dOs[e] = dout[((size_t)b * L + j) * E + c];
+  for (int e4 = threadIdx.x; e4 < L * E / 4; e4 += blockDim.x) {   // 16-byte global loads / shared stores
+    const int e = e4 * 4, j = e / E, c = e % E;
+    *reinterpret_cast<float4*>(Qs + e) = *reinterpret_cast<const float4*>(base + (size_t)j * 3 * E + c);
+    *reinterpret_cast<float4*>(Ks + e) = *reinterpret_cast<const float4*>(base + (size_t)j * 3 * E + E + c);
+    *reinterpret_cast<float4*>(Vs + e) = *reinterpret_cast<const float4*>(base + (size_t)j * 3 * E + 2 * E + c);
+    *reinterpret_cast<float4*>(dOs + e) = *reinterpret_cast<const float4*>(dout + ((size_t)b * L + j) * E + c);
   }
   const int h = threadIdx.x / L, i = threadIdx.x % L;
   const bool active = h < H;
@@ -246,6 +268,11 @@ static __global__ void k_attn_bwd(const float* __restrict__ qkv, const float* __
   __syncthreads();
   float* dbase = dqkv + (size_t)b * L * 3 * E;
   if (active) {
+    float qi[D], doi[D], ki[D], vi[D];
+    ld_row<D>(Qs, i, E, h, qi);
+    ld_row<D>(dOs, i, E, h, doi);
+    ld_row<D>(Ks, i, E, h, ki);
+    ld_row<D>(Vs, i, E, h, vi);
     // ---- dq for query row i
     float dq[D];
 #pragma unroll
@@ -254,20 +281,24 @@ static __global__ void k_attn_bwd(const float* __restrict__ qkv, const float* __
     const float* __restrict__ dmat = pdrop ? pdrop + ((size_t)b * H + h) * L * L : nullptr;   // [L][L] of this head
     for (int j = 0; j <= i; ++j) {
       if (mask[(size_t)b * T + j / tok_per_step] <= 0.f) continue;
+      float kj[D], vj[D];
+      ld_row<D>(Ks, j, E, h, kj);
+      ld_row<D>(Vs, j, E, h, vj);
       float s = 0.f, dp = 0.f;
 #pragma unroll
       for (int c = 0; c < D; ++c) {
-        s = fmaf(Qs[i * E + h * D + c], Ks[j * E + h * D + c], s);
-        dp = fmaf(dOs[i * E + h * D + c], Vs[j * E + h * D + c], dp);
+        s = fmaf(qi[c], kj[c], s);
+        dp = fmaf(doi[c], vj[c], dp);
       }
       const float p = expf(s * scale - li);
       if (dmat) dp *= dmat[i * L + j];   // d softmax = (dO V^T) * dropout multiplier; rowsum(dP * P) is still dO.O
       const float ds = p * (dp - di) * scale;
 #pragma unroll
-      for (int c = 0; c < D; ++c) dq[c] = fmaf(ds, Ks[j * E + h * D + c], dq[c]);
+      for (int c = 0; c < D; ++c) dq[c] = fmaf(ds, kj[c], dq[c]);
     }
 #pragma unroll
-    for (int c = 0; c < D; ++c) dbase[(size_t)i * 3 * E + h * D + c] = dq[c];
+    for (int c = 0; c < D; c += 4)
+      *reinterpret_cast<float4*>(dbase + (size_t)i * 3 * E + h * D + c) = make_float4(dq[c], dq[c + 1], dq[c + 2], dq[c + 3]);
     // ---- dk, dv for key row j = i
     const int j = i;
     float dk[D], dv[D];
@@ -275,11 +306,14 @@ static __global__ void k_attn_bwd(const float* __restrict__ qkv, const float* __
     for (int c = 0; c < D; ++c) { dk[c] = 0.f; dv[c] = 0.f; }
     if (mask[(size_t)b * T + j / tok_per_step] > 0.f) {
       for (int r = j; r < L; ++r) {
+        float qr[D], dor[D];
+        ld_row<D>(Qs, r, E, h, qr);
+        ld_row<D>(dOs, r, E, h, dor);
         float s = 0.f, dp = 0.f;
 #pragma unroll
         for (int c = 0; c < D; ++c) {
-          s = fmaf(Qs[r * E + h * D + c], Ks[j * E + h * D + c], s);
-          dp = fmaf(dOs[r * E + h * D + c], Vs[j * E + h * D + c], dp);
+          s = fmaf(qr[c], ki[c], s);
+          dp = fmaf(dor[c], vi[c], dp);
         }
         const float p = expf(s * scale - Ls[h * L + r]);
         const float mrj = dmat ? dmat[r * L + j] : 1.f;
@@ -287,15 +321,15 @@ static __global__ void k_attn_bwd(const float* __restrict__ qkv, const float* __
         const float pv = p * mrj;
 #pragma unroll
         for (int c = 0; c < D; ++c) {
-          dk[c] = fmaf(ds, Qs[r * E + h * D + c], dk[c]);
-          dv[c] = fmaf(pv, dOs[r * E + h * D + c], dv[c]);
+          dk[c] = fmaf(ds, qr[c], dk[c]);
+          dv[c] = fmaf(pv, dor[c], dv[c]);
         }
       }
     }
 #pragma unroll
-    for (int c = 0; c < D; ++c) {
-      dbase[(size_t)j * 3 * E + E + h * D + c] = dk[c];
-      dbase[(size_t)j * 3 * E + 2 * E + h * D + c] = dv[c];
+    for (int c = 0; c < D; c += 4) {
+      *reinterpret_cast<float4*>(dbase + (size_t)j * 3 * E + E + h * D + c) = make_float4(dk[c], dk[c + 1], dk[c + 2], dk[c + 3]);
+      *reinterpret_cast<float4*>(dbase + (size_t)j * 3 * E + 2 * E + h * D + c) = make_float4(dv[c], dv[c + 1], dv[c + 2], dv[c + 3]);
     }
   }
 }

@@ -302,6 +302,8 @@ FzTask fz_from_gemm(const GemmTask& g) {
   t.bias = g.bias; t.resid = g.resid; t.dact_src = g.dact_src; t.aux = g.aux;
   t.ldr = g.ldr; t.ld_dact = g.ld_dact; t.ldaux = g.ldaux; t.act = g.act; t.clamp = g.clamp; t.dact = g.dact;
   t.scale = g.scale; t.lo = g.lo; t.hi = g.hi; t.colsum = g.colsum;
+  t.ksplit = g.ksplit > 1 ? g.ksplit : 1; t.klen = g.klen;
+  t.mmask = g.mmask; t.ldmm = g.ldmm;
   return t;
 }
 FzTask fz_fwd3(const float* X, int ldx, int rows, const float* W, const Lin& l0, const Lin& l1, const Lin& l2, int hact,
@@ -392,8 +394,12 @@ void emit_fz(Engine& e, Program& p, std::vector<FzTask> tasks) {
   for (auto& t : tasks) {
     OSRL_REQUIRE(t.M > 0 && t.N > 0 && t.K > 0, "empty fused gemm task");
     const int tm = (t.M + fz::BM - 1) / fz::BM, tn = (t.N + fz::BN - 1) / fz::BN;
-    t.tile0 = tot; t.tiles_n = tn;
-    tot += tm * tn;
+    t.tile0 = tot; t.tiles_n = tn; t.tiles_mn = tm * tn;
+    if (t.ksplit < 1) t.ksplit = 1;
+    if (t.ksplit > 1)
+      OSRL_REQUIRE(t.klen % fz::BK == 0 && !t.red && t.a_gen == GEN_NONE && !t.bias && !t.dact && t.act == ACT_NONE,
+                   "split-K needs a plain epilogue");
+    tot += tm * tn * t.ksplit;
     if (t.a_gen == GEN_NONE) {
       OSRL_REQUIRE(t.A != nullptr, "fused gemm task without an A operand");
       t.a_vec = ((uintptr_t)t.A % 16 == 0) && (t.lda % 4 == 0) && ((t.a_kc ? t.K : t.M) % 4 == 0);
@@ -491,8 +497,9 @@ void emit_gemm(Engine& e, Program& p, const std::vector<GemmTask>& tasks_in) {
     t.klen = (t.K + 63) / 64 * 64;
     const bool plain = !t.bias && !t.resid && !t.dact && !t.aux && !t.clamp && t.act == ACT_NONE && t.scale == 1.f;
     if (plain && t.K >= 8192 && t.ldc == t.N) {
-      const int tiles = ((t.M + 63) / 64) * ((t.N + 63) / 64);
-      int want = std::max(1, 444 / std::max(1, tiles));
+      // (fused tcgen05 kernel: 128 x 64 tiles, one CTA per SM -> two waves' worth of splits)
+      const int tiles = fz_on() ? ((t.M + 127) / 128) * ((t.N + 63) / 64) : ((t.M + 63) / 64) * ((t.N + 63) / 64);
+      int want = std::max(1, (fz_on() ? 296 : 444) / std::max(1, tiles));
       want = std::min(want, t.K / 1024);
       if (want > 1) {
         t.klen = ((t.K + want - 1) / want + 63) / 64 * 64;
@@ -530,13 +537,18 @@ void emit_gemm(Engine& e, Program& p, const std::vector<GemmTask>& tasks_in) {
         packed.push_back(t);
         continue;
       }
-      const bool full = t.act == ACT_GELU || t.dact == ACT_GELU || t.mmask != nullptr || t.ksplit > 1;
-      // (operand rows are fetched with 16-byte bulk copies: unaligned layouts, e.g. K = 41 first layers, stay on mma.sync)
-      if (full || (t.colsum && t.a_kc) || !t.a_vec || !t.b_vec || t.K % 4 != 0) rest.push_back(t);
+      // (operand rows are fetched with 16-byte copies: unaligned layouts, e.g. K = 41 first layers, stay on mma.sync)
+      if ((t.colsum && t.a_kc) || !t.a_vec || !t.b_vec || t.K % 4 != 0) rest.push_back(t);
       else fzt.push_back(fz_from_gemm(t));
     }
     if (!packed.empty()) emit_tc5(e, p, packed, true);
     emit_fz(e, p, fzt);
+    {   // GELU-forward / dropout-multiplier epilogues (CDT): round 1's tcgen05 kernel; only unaligned leftovers see mma.sync
+      std::vector<GemmTask> big, small;
+      for (auto& t : rest) (tc5_eligible(t) ? big : small).push_back(t);
+      if (!big.empty()) emit_tc5(e, p, big, false);
+      rest = small;
+    }
     if (rest.empty()) return;
     tasks = rest;
   } else if (gemm_mode() == "tc5") {   // large forward layers -> tcgen05 kernel, the rest stays on mma.sync

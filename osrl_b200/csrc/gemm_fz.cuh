@@ -63,6 +63,10 @@ struct FzTask {
   float* raux; int ldraux;
   float* rout; int ldro;
   int tile0, tiles_n;
+  // split-K (weight gradients over many rows, CDT: K = 81,920 tokens): split s of a tile covers k in [s*klen, (s+1)*klen)
+  // and atomically adds its partial into a pre-zeroed C / colsum (plain epilogue only)
+  int ksplit, klen, tiles_mn;
+  const float* mmask; int ldmm;   // optional multiplier after act*scale, before the residual add (CDT dropout sites)
 };
 constexpr int FZ_PACK = 16;
 struct FzPack {
@@ -117,7 +121,9 @@ __device__ __forceinline__ int find_task(const FzPack& P, int ntasks, int tile) 
     if (i < ntasks && P.tile0[i] <= tile) ti = i;
   return ti;
 }
-__device__ __forceinline__ float dact_mul(float v, float h, int kind) {   // v * act'(.) from the stored activation
+// v * act'(.) from the stored activation (GELU: from the stored PRE-activation, exact erf form -- CDT's fc2 dgrad)
+__device__ __forceinline__ float dact_mul(float v, float h, int kind) {
+  if (kind == ACT_GELU) return v * gelu_bwd(h);
   return kind == ACT_RELU ? (h > 0.f ? v : 0.f) : (kind == ACT_TANH ? v * (1.f - h * h) : v);
 }
 // k-major SWIZZLE_128B tile: byte offset of 16-byte chunk ck (0..7) of row r
@@ -227,11 +233,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_fz(const __grid_constant__ FzPac
   const uint32_t tmem_base = tmem_base_s;
   FZ_STAMP(1);
   const FzTask& t = P.t[find_task(P, ntasks, blockIdx.x)];
-  const int lt = blockIdx.x - t.tile0;
+  int lt = blockIdx.x - t.tile0;
+  const int M = t.M, N = t.N;
+  int kbeg = 0, K = t.K;                      // K = END of this CTA's k range
+  if (t.ksplit > 1) {
+    kbeg = (lt / t.tiles_mn) * t.klen;
+    lt %= t.tiles_mn;
+    K = min(t.K, kbeg + t.klen);
+  }
   const int tm = lt / t.tiles_n, tn = lt % t.tiles_n;
   const int m0 = tm * BM, n0 = tn * BN;
-  const int M = t.M, N = t.N, K = t.K;
-  const int nk = (K + BK - 1) / BK, kpad = nk * BK;
+  const int nk = (K - kbeg + BK - 1) / BK, kpad = nk * BK;
+  const bool split = t.ksplit > 1;
 
   if (warp > CONV / 32) {
     // ------------------------------------------------ loaders: 16-byte cp.async pieces, NRAW slabs in flight; a slab's
@@ -246,7 +259,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_fz(const __grid_constant__ FzPac
     const int a_r = ASRC == A_MC ? (lt_ >> 5) : (lt_ >> 3), a_c = ASRC == A_MC ? (lt_ & 31) : (lt_ & 7);
     const int b_r = BKC ? (lt_ >> 3) : (lt_ >> 4), b_c = BKC ? (lt_ & 7) : (lt_ & 15);
     for (int kt = 0; kt < nk; ++kt) {
-      const int s = kt % NRAW, k0 = kt * BK;
+      const int s = kt % NRAW, k0 = kbeg + kt * BK;
       if (kt >= NRAW) mbar_wait(&raw_empty[s], ((kt / NRAW) - 1) & 1);
       const uint32_t ra = rbase + s * RAW_STAGE, rb = ra + RAW_A_BYTES;
       if constexpr (RAW_A) {
@@ -345,7 +358,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_fz(const __grid_constant__ FzPac
     const bool rowok = m0 + row < M;
 
     for (int kt = 0; kt < nk; ++kt) {
-      const int so = kt % NOP, sr = kt % NRAW, k0 = kt * BK;
+      const int so = kt % NOP, sr = kt % NRAW, k0 = kbeg + kt * BK;
       mbar_wait(&raw_full[sr], (kt / NRAW) & 1);
       if (kt >= NOP) {
         mbar_wait(&op_empty[so], ((kt / NOP) - 1) & 1);
@@ -462,7 +475,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_fz(const __grid_constant__ FzPac
         float* csx = cs_s;
         csx[kq * BM + row] = cs;
         asm volatile("bar.sync 1, %0;" ::"n"(CONV) : "memory");
-        if (kq == 0 && rowok) t.colsum[m0 + row] = ((csx[row] + csx[BM + row]) + csx[2 * BM + row]) + csx[3 * BM + row];
+        if (kq == 0 && rowok) {
+          const float tot = ((csx[row] + csx[BM + row]) + csx[2 * BM + row]) + csx[3 * BM + row];
+          if (split) atomicAdd(&t.colsum[m0 + row], tot);
+          else t.colsum[m0 + row] = tot;
+        }
       }
     }
     // ------------------------------------------------ epilogue
@@ -514,8 +531,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_fz(const __grid_constant__ FzPac
         if (gj + 2 < N) bj.z = t.bias[gj + 2];
         if (gj + 3 < N) bj.w = t.bias[gj + 3];
       }
-      const bool plain = !aux && !resid && !clampf && scale == 1.f;
-      const bool tanh_act = act == ACT_TANH;
+      const float* __restrict__ mm = t.mmask;
+      const int ldmm = t.ldmm;
+      const bool plain = !aux && !resid && !clampf && scale == 1.f && !mm;
+      const bool tanh_act = act == ACT_TANH, gelu_act = act == ACT_GELU;
       const bool relu_act = act == ACT_RELU;
       // four rows per thread: their shared / global loads are issued before anything is stored
 #pragma unroll
@@ -541,7 +560,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_fz(const __grid_constant__ FzPac
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
           const int r = (pass * 4 + it) * 2 * (CONV / 32) + warp * 2 + (lane >> 4), gi = m0 + r;
-          if (tanh_act) {
+          if (gelu_act) {   // exact-erf GELU (CDT fc1): aux keeps the PRE-activation for the backward pass
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (aux && gi < M && gj + c < N) aux[(size_t)gi * ldaux + gj + c] = e[it][c];
+              e[it][c] = gelu_fwd(e[it][c]);
+            }
+          } else if (tanh_act) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) e[it][c] = tanhf(e[it][c]);
           } else {
@@ -552,8 +577,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_fz(const __grid_constant__ FzPac
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               if (gj + c < N) {
-                if (aux) aux[(size_t)gi * ldaux + gj + c] = e[it][c];
+                if (aux && !gelu_act) aux[(size_t)gi * ldaux + gj + c] = e[it][c];
                 e[it][c] *= scale;
+                if (mm) e[it][c] *= mm[(size_t)gi * ldmm + gj + c];
                 if (resid) e[it][c] += resid[(size_t)gi * ldr + gj + c];
                 if (clampf) e[it][c] = fminf(fmaxf(e[it][c], lo), hi);
               }
@@ -566,7 +592,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_fz(const __grid_constant__ FzPac
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             if (gj + c >= N) e[it][c] = 0.f;
-          if (cst && gi < M) {
+          if (cst && gi < M && split) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (gj + c < N) atomicAdd(&C[(size_t)gi * ldc + gj + c], e[it][c]);
+          } else if (cst && gi < M) {
             if (vec && gj + 3 < N) *reinterpret_cast<float4*>(C + (size_t)gi * ldc + gj) = make_float4(e[it][0], e[it][1], e[it][2], e[it][3]);
             else {
 #pragma unroll
