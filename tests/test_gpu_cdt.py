@@ -12,7 +12,7 @@ import torch
 from oracle import algos
 from oracle import cdt as ocdt
 from oracle.make_golden import CDT_KEYS, make_seq_batch
-from tests.helpers import RTOL, l2rel, load_golden, maxrel
+from tests.helpers import RTOL, l2rel, load_golden, maxrel, record_margin
 
 pytestmark = pytest.mark.gpu
 
@@ -118,9 +118,11 @@ def test_cdt_against_live_oracle(lib_built, case, gemm):
             tol = max(2 * RTOL, 10 * cond)
             total += 1; strict += tol == 2 * RTOL
             err = maxrel(G[k], g)
+            record_margin(f"cdt_vs_oracle/{gemm}", "grad (max-rel, all tensors)", err, tol)
             if err > tol:
                 bad.append((k, err, cond))
                 assert err <= cap, f"{case}/{gemm} step {s} grad {k}: {err:.2e} (cond {cond:.1e})"
+        record_margin(f"cdt_vs_oracle/{gemm}", "grad outlier tensors (count)", len(bad), max(1, int(max_frac * len(orc.last_grads))))
         assert len(bad) <= max(1, int(max_frac * len(orc.last_grads))), bad[:6]
         if s == 0:
             P = eng.read_params()

@@ -14,9 +14,10 @@ fp32-vs-fp64 gap (`cond`) for that quantity and requires
 and separately requires that the overwhelming majority of quantities are well conditioned, i.e.
 are held to the plain bound.  Losses (the quantity north_star names) use 1e-5; raw gradients, which
 north_star does not name, use 2e-5 of the tensor's largest entry (3xTF32 tensor-core products keep
-~21 mantissa bits per operand; measured 1e-7..1.3e-5), and because a ReLU kink can also separate the
-engine from BOTH reference evaluations, at most 5 % of the gradient tensors of a step may exceed that
-bound, and then by no more than 1e-2.  Parameter deltas (named by north_star) are checked norm-wise at 2e-5.
+~21 mantissa bits per operand; measured 1e-7..2.7e-5), and because a ReLU kink can also separate the
+engine from BOTH reference evaluations, at most 8 % of the gradient tensors of a step may exceed that
+bound, and then by no more than 5e-4 (measured worst case 2.7e-5, <= 2 tensors per step: the recorded margins are
+in profiles/r02_parity_margins.json).  Parameter deltas (named by north_star) are checked norm-wise at 2e-5.
 """
 import numpy as np
 import pytest
@@ -47,7 +48,10 @@ def _compare_step(tag, eng, s32, s64, g32, g64, before, p64, gemm="fz"):
     Gradient outliers (ReLU kinks, see module docstring): the CUDA-core GEMM reproduces the reference's
     pre-activations to ~1e-7, so a kink flip is rare (<=5 % of tensors, <=1e-2); the 3xTF32 GEMM is ~1e-6
     off, a few of the ~1.5M ReLU units flip per step, each moving one or two tensors by O(1/batch)."""
-    max_frac, cap = (0.05, 1e-2) if gemm == "ffma" else (0.2, 2e-1)
+    # Budget = what was measured on B200 (profiles/r02_parity_margins.json) with a small factor: over 2056 gradient-tensor
+    # comparisons of the fused tcgen05 path the worst max-rel error was 2.3e-5 (tc5: 2.7e-5, mma: 8.2e-6, ffma:
+    # 7.1e-6) and no step had more than 2 of its ~65 tensors above 2e-5.  (Round 1 allowed 20 % of the tensors up to 0.2.)
+    max_frac, cap = (0.03, 1e-4) if gemm == "ffma" else (0.08, 5e-4)
     strict = total = 0
     got = eng.stats()
     for k, w in s32.items():
