@@ -217,6 +217,16 @@ int osrl_step_seq(osrl_engine* e, const osrl_seq_batch* batch, const osrl_noise*
  * the state after the call is bit-identical to k calls with k = 1 (tests/test_gpu_parity.py).  OSRL_PIPELINE=0
  * disables it. */
 int osrl_steps(osrl_engine* e, int k, void* stream);
+/* k steps on k explicit HOST minibatches: the batched form of osrl_step for a caller that keeps its own data loader
+ * (the loop body train_bcql.py:142-148 with the reference's DataLoader left in place, k iterations per call).
+ * `stacked` holds the k batches back to back per field (observations = [k][rows][obs_dim] floats, rewards = [k][rows],
+ * ...; rows = batch_size, on_host = 1; pageable or pinned).  The library packs each batch into a pinned ring that
+ * the step graph reads in place over PCIe (mapped memory), so the transfer of batch j+1 overlaps the compute of batch
+ * j and no copy sits on the stream between steps; noise is Philox on the device (as osrl_step with a NULL noise);
+ * the VAE algorithms are pipelined as in osrl_steps.  `stats_out` = [k][n_stats] floats (order of osrl_stat_names):
+ * the call then returns after the k-th step has finished; NULL = return as soon as everything is queued (the caller's
+ * buffers are already consumed).  State after the call is bit-identical to k x osrl_step (tests/test_gpu_parity.py). */
+int osrl_steps_host(osrl_engine* e, const osrl_batch* stacked, int k, float* stats_out, void* stream);
 
 /* Stats of the most recent step, in the order of osrl_stat_names (logger.store keys,
  * bcql.py:131,154,178,205-207).  Synchronises the stream. */

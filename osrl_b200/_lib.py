@@ -98,6 +98,7 @@ SYMBOLS = [
     ("osrl_seq_alias_table", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     ("osrl_last_sequences", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     ("osrl_steps", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    ("osrl_steps_host", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_int, C.c_void_p, C.c_void_p]),
     ("osrl_stat_names", C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_int)]),
     ("osrl_stats", C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_int), C.c_void_p]),
     ("osrl_scalar_names", C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_int)]),

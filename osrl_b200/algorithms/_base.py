@@ -165,6 +165,28 @@ class EngineTrainer:
                 break
         return ret, n, cost
 
+    # -- batched host path: k iterations of the loop body train_bcql.py:142-148 per call, the caller keeps its DataLoader
+    batch_keys = ("observations", "next_observations", "actions", "rewards", "costs", "done")
+
+    def train_batches(self, batches, store: bool = True):
+        """`train_one_step` on each of k host minibatches, queued in one call (osrl_steps_host): the transfer of batch
+        j+1 overlaps the compute of batch j and the host synchronises once.  `batches`: a list of what the reference's
+        loader yields (tuples in train_one_step's argument order, or dicts), or one dict of stacked [k, B, ...] tensors.
+        Noise is Philox on the device.  Returns the per-step stats; every step's stats go to the logger (store=True)."""
+        if isinstance(batches, (list, tuple)) and len(batches) and not isinstance(batches[0], dict):
+            batches = [dict(zip(self.batch_keys, b)) for b in batches]
+        first = batches[0] if isinstance(batches, (list, tuple)) else batches
+        B = first["observations"].shape[-2]
+        eng = self._engine(B)
+        if self.noise_mode == "torch":
+            raise RuntimeError('train_batches draws its noise on the device; noise="torch" needs train_one_step')
+        out = eng.steps_host(batches)
+        for st in out:
+            self._n += 1
+            if store and self.log_every and self._n % self.log_every == 0:
+                self._store(st)
+        return out
+
     def train_steps(self, n: int, batch_size: Optional[int] = None) -> Dict[str, float]:
         """n gradient steps without touching the host (replaces n iterations of train_bcql.py:142-148)."""
         if self._dataset is None:

@@ -32,6 +32,8 @@ class BC(EngineModel):
 
 
 class BCTrainer(EngineTrainer):
+    batch_keys = ("observations", "actions")
+
     def __init__(self, model: BC, env=None, logger=None, actor_lr: float = 1e-4, bc_mode: str = "all",
                  cost_limit: int = 10, device="cuda:0", **kw):
         super().__init__(model, env, logger, device=device, **kw)

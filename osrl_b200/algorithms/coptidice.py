@@ -68,6 +68,8 @@ class COptiDICE(EngineModel):
 
 
 class COptiDICETrainer(EngineTrainer):
+    batch_keys = ("observations", "next_observations", "actions", "rewards", "costs", "done", "is_init")
+
     def __init__(self, model: COptiDICE, env=None, logger=None, actor_lr: float = 1e-3, critic_lr: float = 1e-3,
                  scalar_lr: float = 1e-3, reward_scale: float = 1.0, cost_scale: float = 1.0, device="cuda:0", **kw):
         super().__init__(model, env, logger, reward_scale, cost_scale, device, **kw)

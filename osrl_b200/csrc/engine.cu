@@ -841,7 +841,7 @@ static float slot_drop_p(const osrl_config& c, const std::string& name) {
   return 0.f;
 }
 static void drop_sampled_graphs(Engine& e) {   // they bake the dataset pointers
-  for (cudaGraphExec_t* g : {&e.g_sampled, &e.g_pro, &e.g_mid, &e.g_last})
+  for (cudaGraphExec_t* g : {&e.g_sampled, &e.g_pro, &e.g_mid, &e.g_last, &e.g_xbody, &e.g_xpro, &e.g_xmid, &e.g_xlast})
     if (*g) { cudaGraphExecDestroy(*g); *g = nullptr; }
 }
 static void free_all(Engine* e) {
@@ -851,6 +851,8 @@ static void free_all(Engine* e) {
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->side_stream) cudaStreamDestroy(e->side_stream);
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  for (float* hp : {e->x_ring, e->x_st_side, e->x_st_main})
+    if (hp) cudaFreeHost(hp);
   for (int i = 0; i < 2; ++i) {
     if (e->stats_pinned[i]) cudaFreeHost(e->stats_pinned[i]);
     if (e->stats_ev[i]) cudaEventDestroy(e->stats_ev[i]);
@@ -895,6 +897,7 @@ static void build_pipelined(Engine& e, const std::vector<int>& vae_slots) {
     default: return;
   }
   e.pipelined = true;
+  e.side_stat_mask = 1u;   // "loss/loss_vae" (stat 0 of BCQ-Lag, CPQ and BEAR-Lag) is the VAE branch's
 }
 static void build_program(Engine& e) {
   switch (e.plan.cfg.algo) {
@@ -1043,9 +1046,29 @@ static void prologue(Engine& e, cudaStream_t s, unsigned mask = 0xffffffffu) {
   k_prologue<<<1, 32, 0, s>>>(e.ds, e.d_groups, (int)e.plan.groups.size(), mask);
   e.launches++;
 }
-static void epilogue(Engine& e, cudaStream_t s, int mode = 0) {
-  k_epilogue<<<1, 32, 0, s>>>(e.ds, mode);
+static void epilogue(Engine& e, cudaStream_t s, int mode = 0, bool hostq = false) {
+  if (hostq) k_epilogue<<<1, 32, 0, s>>>(e.ds, mode, e.xq, e.stats, (int)e.plan.stat_names.size());
+  else k_epilogue<<<1, 32, 0, s>>>(e.ds, mode);
   e.launches++;
+}
+// front of a step fed from the host-batch queue (osrl_steps_host): which = 1 reads the VAE branch's batch into the
+// "next" buffers, 0 the main branch's (or the whole step's) into the current ones
+static void unpack_front(Engine& e, cudaStream_t s, int which, const NoiseSlot* slots, const unsigned long long* counter) {
+  const osrl_config& c = e.plan.cfg;
+  const bool bc = c.algo == OSRL_ALGO_BC;
+  if (which)
+    k_unpack_batch<<<24, 256, 0, s>>>(e.xq, 1, e.B, c.obs_dim, c.act_dim, e.nb_obs, e.nb_nobs, e.nb_act, e.nb_rew, e.nb_cost,
+                                      e.nb_done, nullptr);
+  else
+    k_unpack_batch<<<24, 256, 0, s>>>(e.xq, 0, e.B, c.obs_dim, c.act_dim, e.b_obs, bc ? nullptr : e.b_nobs, e.b_act,
+                                      bc ? nullptr : e.b_rew, bc ? nullptr : e.b_cost, bc ? nullptr : e.b_done,
+                                      c.algo == OSRL_ALGO_COPTIDICE ? e.b_init : nullptr);
+  e.launches++;
+  if (!e.noise_buf.empty()) {
+    k_noise_fill<<<dim3(64, (unsigned)e.noise_buf.size()), 256, 0, s>>>(slots, (int)e.noise_buf.size(), c.seed, counter,
+                                                                         (uint32_t)e.rank);
+    e.launches++;
+  }
 }
 static void launch_seq_gather(Engine& e, cudaStream_t s, const int* traj_in, const int* start_in, int rows,
                               float* states, float* actions, float* returns, float* ctg, long long* ts, float* mask,
@@ -1082,16 +1105,17 @@ static void sample_front(Engine& e, cudaStream_t s) {
   }
 }
 
-static cudaGraphExec_t capture(Engine& e, bool sampled) {
+static cudaGraphExec_t capture(Engine& e, bool sampled, bool hostq = false) {
   cudaStream_t s = e.cap_stream;
   const int64_t before = e.launches;
   OSRL_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
   cudaGraph_t g = nullptr;
   try {
-    if (sampled) sample_front(e, s);
+    if (hostq) unpack_front(e, s, 0, e.d_slots_all, &e.ds->step);
+    else if (sampled) sample_front(e, s);
     prologue(e, s);
     run_ops(e, e.body, s);
-    epilogue(e, s);
+    epilogue(e, s, 0, hostq);
   } catch (...) {
     cudaStreamEndCapture(s, &g);
     if (g) cudaGraphDestroy(g);
@@ -1108,29 +1132,37 @@ static cudaGraphExec_t capture(Engine& e, bool sampled) {
 }
 // ---- pipelined graphs.  side = VAE update of the step whose index is ds->vae_step, on the NEXT minibatch;
 // main = the rest of step ds->step on the current minibatch, VAE weights from the snapshot taken before the fork.
-static void side_ops(Engine& e, cudaStream_t s) {
+static void side_ops(Engine& e, cudaStream_t s, bool hostq = false) {
   const osrl_config& c = e.plan.cfg;
-  k_sample_gather<<<(e.B + 7) / 8, 256, 0, s>>>(e.ds_rows, e.ds_n, e.ds_stride, c.obs_dim, c.act_dim, nullptr, c.seed,
-                                               &e.ds->vae_step, (uint32_t)e.rank, e.B, e.nb_obs, e.nb_nobs, e.nb_act,
-                                               e.nb_rew, e.nb_cost, e.nb_done, e.nb_idx);
-  k_noise_fill<<<dim3(64, (unsigned)e.noise_buf.size()), 256, 0, s>>>(e.d_slots_vae, (int)e.noise_buf.size(), c.seed,
-                                                                       &e.ds->vae_step, (uint32_t)e.rank);
-  e.launches += 2;
+  if (hostq) {
+    unpack_front(e, s, 1, e.d_slots_vae, &e.ds->vae_step);
+  } else {
+    k_sample_gather<<<(e.B + 7) / 8, 256, 0, s>>>(e.ds_rows, e.ds_n, e.ds_stride, c.obs_dim, c.act_dim, nullptr, c.seed,
+                                                 &e.ds->vae_step, (uint32_t)e.rank, e.B, e.nb_obs, e.nb_nobs, e.nb_act,
+                                                 e.nb_rew, e.nb_cost, e.nb_done, e.nb_idx);
+    k_noise_fill<<<dim3(64, (unsigned)e.noise_buf.size()), 256, 0, s>>>(e.d_slots_vae, (int)e.noise_buf.size(), c.seed,
+                                                                         &e.ds->vae_step, (uint32_t)e.rank);
+    e.launches += 2;
+  }
   prologue(e, s, 1u << e.plan.g_vae);
   run_ops(e, e.pa, s);
-  epilogue(e, s, 2);
+  epilogue(e, s, 2, hostq);
 }
-static void main_ops(Engine& e, cudaStream_t s) {
+static void main_ops(Engine& e, cudaStream_t s, bool hostq = false) {
   const osrl_config& c = e.plan.cfg;
-  k_sample_gather<<<(e.B + 7) / 8, 256, 0, s>>>(e.ds_rows, e.ds_n, e.ds_stride, c.obs_dim, c.act_dim, nullptr, c.seed,
-                                               &e.ds->step, (uint32_t)e.rank, e.B, e.b_obs, e.b_nobs, e.b_act, e.b_rew,
-                                               e.b_cost, e.b_done, e.b_idx);
-  k_noise_fill<<<dim3(64, (unsigned)e.noise_buf.size()), 256, 0, s>>>(e.d_slots_rest, (int)e.noise_buf.size(), c.seed,
-                                                                       &e.ds->step, (uint32_t)e.rank);
-  e.launches += 2;
+  if (hostq) {
+    unpack_front(e, s, 0, e.d_slots_rest, &e.ds->step);
+  } else {
+    k_sample_gather<<<(e.B + 7) / 8, 256, 0, s>>>(e.ds_rows, e.ds_n, e.ds_stride, c.obs_dim, c.act_dim, nullptr, c.seed,
+                                                 &e.ds->step, (uint32_t)e.rank, e.B, e.b_obs, e.b_nobs, e.b_act, e.b_rew,
+                                                 e.b_cost, e.b_done, e.b_idx);
+    k_noise_fill<<<dim3(64, (unsigned)e.noise_buf.size()), 256, 0, s>>>(e.d_slots_rest, (int)e.noise_buf.size(), c.seed,
+                                                                         &e.ds->step, (uint32_t)e.rank);
+    e.launches += 2;
+  }
   prologue(e, s, ~(1u << e.plan.g_vae));
   run_ops(e, e.pm, s);
-  epilogue(e, s, 1);
+  epilogue(e, s, 1, hostq);
 }
 static void snapshot_vae(Engine& e, cudaStream_t s) {
   const Group& g = e.plan.groups[e.plan.g_vae];
@@ -1140,23 +1172,23 @@ static void snapshot_vae(Engine& e, cudaStream_t s) {
     OSRL_CUDA(cudaMemcpyAsync(hd.cur, hd.next, hd.bytes, cudaMemcpyDeviceToDevice, s));
 }
 // which: 0 = first VAE update alone, 1 = steady state (fork / join), 2 = last step's remainder alone
-static cudaGraphExec_t capture_pipelined(Engine& e, int which) {
+static cudaGraphExec_t capture_pipelined(Engine& e, int which, bool hostq = false) {
   cudaStream_t s = e.cap_stream, s2 = e.side_stream;
   const int64_t before = e.launches;
   OSRL_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
   cudaGraph_t g = nullptr;
   try {
     if (which == 0) {
-      side_ops(e, s);
+      side_ops(e, s, hostq);
     } else {
       snapshot_vae(e, s);
       if (which == 1) {
         OSRL_CUDA(cudaEventRecord(e.ev_fork, s));
         OSRL_CUDA(cudaStreamWaitEvent(s2, e.ev_fork, 0));
-        side_ops(e, s2);
+        side_ops(e, s2, hostq);
         OSRL_CUDA(cudaEventRecord(e.ev_join, s2));
       }
-      main_ops(e, s);
+      main_ops(e, s, hostq);
       if (which == 1) OSRL_CUDA(cudaStreamWaitEvent(s, e.ev_join, 0));
     }
   } catch (...) {
@@ -1587,6 +1619,92 @@ int osrl_steps(osrl_engine* h, int k, void* stream) {
     if (!e.g_sampled) e.g_sampled = capture(e, true);
     for (int i = 0; i < k; ++i) OSRL_CUDA(cudaGraphLaunch(e.g_sampled, s));
     e.launches += (int64_t)k * kernels_per_step(e, true);
+  }
+  OSRL_CATCH
+}
+
+// k steps on k explicit HOST minibatches (stacked [k][B][...] arrays), the batched form of osrl_step: the batches are
+// packed into a pinned ring the step graphs read directly (mapped memory: one PCIe read per step, no copy-engine
+// round trip on the stream), the per-step stats come back the same way, and for the VAE algorithms the steps are
+// pipelined exactly like osrl_steps().  Bit-identical to k x osrl_step(batch_j, NULL noise).
+int osrl_steps_host(osrl_engine* h, const osrl_batch* stk, int k, float* stats_out, void* stream) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && stk && k >= 0, "bad argument");
+  Engine& e = *h->e;
+  const osrl_config& c = e.plan.cfg;
+  OSRL_REQUIRE(c.algo != OSRL_ALGO_CDT, "CDT steps take sequence batches: use osrl_step_seq");
+  OSRL_REQUIRE(stk->rows == e.B, "batch rows != engine batch_size");
+  OSRL_REQUIRE(stk->on_host, "osrl_steps_host takes host batches (device batches: osrl_step)");
+  OSRL_REQUIRE(stk->observations && stk->actions, "observations/actions required");
+  const bool bc = c.algo == OSRL_ALGO_BC, cop = c.algo == OSRL_ALGO_COPTIDICE;
+  if (!bc) OSRL_REQUIRE(stk->next_observations && stk->rewards && stk->costs && stk->done, "incomplete transition batch");
+  if (cop) OSRL_REQUIRE(stk->is_init, "COptiDICE batches carry is_init (coptidice.py:126-127)");
+  if (k == 0) return OSRL_OK;
+  OSRL_CUDA(cudaSetDevice(e.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int o = c.obs_dim, a = c.act_dim, B = e.B, ns = (int)e.plan.stat_names.size();
+  OSRL_REQUIRE(ns <= HQ_STAT_LD, "too many stats");
+  const size_t slot = (size_t)B * (2 * o + a + 4);
+  if (e.x_pending) { OSRL_CUDA(cudaStreamSynchronize(s)); e.x_pending = false; }
+  if (k > e.x_cap) {
+    OSRL_CUDA(cudaDeviceSynchronize());
+    for (float** hp : {&e.x_ring, &e.x_st_side, &e.x_st_main})
+      if (*hp) { cudaFreeHost(*hp); *hp = nullptr; }
+    e.x_cap = 0;
+    const int cap = std::max(k, 64);
+    OSRL_CUDA(cudaHostAlloc((void**)&e.x_ring, cap * slot * sizeof(float), cudaHostAllocMapped));
+    OSRL_CUDA(cudaHostAlloc((void**)&e.x_st_side, (size_t)cap * HQ_STAT_LD * sizeof(float), cudaHostAllocMapped));
+    OSRL_CUDA(cudaHostAlloc((void**)&e.x_st_main, (size_t)cap * HQ_STAT_LD * sizeof(float), cudaHostAllocMapped));
+    e.x_cap = cap;
+  }
+  if (!e.xq) { OSRL_CUDA(cudaMalloc((void**)&e.xq, sizeof(HostQueue))); e.allocs.push_back(e.xq); }
+  HostQueue hq;
+  memset(&hq, 0, sizeof(hq));
+  OSRL_CUDA(cudaHostGetDevicePointer((void**)&hq.ring, e.x_ring, 0));
+  OSRL_CUDA(cudaHostGetDevicePointer((void**)&hq.st_side, e.x_st_side, 0));
+  OSRL_CUDA(cudaHostGetDevicePointer((void**)&hq.st_main, e.x_st_main, 0));
+  hq.slot_floats = (long long)slot;
+  OSRL_CUDA(cudaMemcpyAsync(e.xq, &hq, sizeof(hq), cudaMemcpyHostToDevice, s));   // pageable source: staged before return
+  auto pack = [&](int j) {
+    float* d = e.x_ring + (size_t)j * slot;
+    auto put = [&](const float* src, size_t per) {
+      if (src) memcpy(d, src + (size_t)j * per, per * sizeof(float));
+      d += per;
+    };
+    put(stk->observations, (size_t)B * o); put(stk->next_observations, (size_t)B * o); put(stk->actions, (size_t)B * a);
+    put(stk->rewards, B); put(stk->costs, B); put(stk->done, B); put(stk->is_init, B);
+  };
+  const bool pipe = e.pipelined && k >= 2 && (e.world == 1 || e.comm2);
+  if (pipe) {
+    if (!e.g_xpro) e.g_xpro = capture_pipelined(e, 0, true);
+    if (!e.g_xmid) e.g_xmid = capture_pipelined(e, 1, true);
+    if (!e.g_xlast) e.g_xlast = capture_pipelined(e, 2, true);
+    pack(0);
+    OSRL_CUDA(cudaGraphLaunch(e.g_xpro, s));
+    for (int j = 1; j < k; ++j) {
+      pack(j);   // the GPU is at most at batch j-1: the host packs ahead of it
+      OSRL_CUDA(cudaGraphLaunch(e.g_xmid, s));
+    }
+    OSRL_CUDA(cudaGraphLaunch(e.g_xlast, s));
+    e.launches += (int64_t)k * (e.pa.kernels + e.pm.kernels + 8);
+  } else {
+    if (!e.g_xbody) e.g_xbody = capture(e, false, true);
+    for (int j = 0; j < k; ++j) {
+      pack(j);
+      OSRL_CUDA(cudaGraphLaunch(e.g_xbody, s));
+    }
+    e.launches += (int64_t)k * kernels_per_step(e, true);
+  }
+  e.x_last_k = k;
+  e.x_last_pipelined = pipe;
+  e.x_pending = true;
+  if (stats_out) {
+    OSRL_CUDA(cudaStreamSynchronize(s));
+    e.x_pending = false;
+    for (int j = 0; j < k; ++j)
+      for (int i = 0; i < ns; ++i)
+        stats_out[(size_t)j * ns + i] = (pipe && (e.side_stat_mask >> i & 1u)) ? e.x_st_side[(size_t)j * HQ_STAT_LD + i]
+                                                                               : e.x_st_main[(size_t)j * HQ_STAT_LD + i];
   }
   OSRL_CATCH
 }

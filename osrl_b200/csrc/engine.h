@@ -181,6 +181,14 @@ struct Engine {
   bool decode_side = false;   // BCQ-Lag: the step's VAE decodes run on the VAE branch too (OSRL_PIPELINE_DECODE)
   NoiseSlot *d_slots_vae = nullptr, *d_slots_rest = nullptr;
   cudaGraphExec_t g_pro = nullptr, g_mid = nullptr, g_last = nullptr;
+  // osrl_steps_host: the same graphs with the device draw replaced by a read of the host-batch queue
+  cudaGraphExec_t g_xbody = nullptr, g_xpro = nullptr, g_xmid = nullptr, g_xlast = nullptr;
+  HostQueue* xq = nullptr;                       // device copy of the queue descriptor
+  float *x_ring = nullptr, *x_st_side = nullptr, *x_st_main = nullptr;   // pinned, mapped
+  int x_cap = 0;                                 // batches the ring holds
+  bool x_pending = false;                        // an asynchronous osrl_steps_host call may still read the ring
+  int x_last_k = 0, x_last_pipelined = 0;
+  uint32_t side_stat_mask = 0;                   // stats written by the pipelined VAE branch
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaStream_t cap_stream = nullptr;

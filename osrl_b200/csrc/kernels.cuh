@@ -104,11 +104,56 @@ static __global__ void k_prologue(DevState* ds, const AdamGroupCfg* g, int ngrou
   }
 }
 // mode 0: a whole step finished (both counters); 1: everything but the VAE update; 2: the VAE update only
-static __global__ void k_epilogue(DevState* ds, int mode) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// Host-batch queue of osrl_steps_host: `ring` holds the call's k packed minibatches and `st_*` its per-step stat
+// rows, all in pinned host memory mapped into the device address space; `side` / `main` = how many batches the VAE
+// branch / the rest of the step have consumed in this call.
+struct HostQueue {
+  unsigned side, main, pad0, pad1;
+  const float* ring;
+  float* st_side;
+  float* st_main;
+  long long slot_floats;
+};
+constexpr int HQ_STAT_LD = 16;
+
+// mode 0: a whole step ended; 1: the main branch of a pipelined step; 2: its VAE branch.  With a host queue the
+// branch also posts its stat row to the host (zero-copy store) and advances its queue position.
+static __global__ void k_epilogue(DevState* ds, int mode, HostQueue* q = nullptr, const float* stats = nullptr, int nstats = 0) {
+  if (blockIdx.x != 0) return;
+  if (q) {
+    float* row = mode == 2 ? q->st_side + (size_t)q->side * HQ_STAT_LD : q->st_main + (size_t)q->main * HQ_STAT_LD;
+    if ((int)threadIdx.x < nstats) row[threadIdx.x] = stats[threadIdx.x];
+    __syncwarp();
+  }
+  if (threadIdx.x != 0) return;
   if (mode == 0) { ds->step += 1ull; ds->vae_step = ds->step; }
   else if (mode == 1) ds->step += 1ull;
   else ds->vae_step += 1ull;
+  if (q) {
+    if (mode != 2) q->main += 1u;
+    if (mode != 1) q->side += 1u;
+  }
+}
+
+// Minibatch `q->side` (which = 1) or `q->main` (which = 0) of the host queue -> the step's input buffers.  The slot is
+// [obs B*o | next_obs B*o | act B*a | rew B | cost B | done B | is_init B]; the loads go over PCIe (mapped pinned
+// memory), 22 KB for a CarCircle batch of 256.
+static __global__ void k_unpack_batch(const HostQueue* q, int which, int B, int o, int a, float* obs, float* nobs, float* act,
+                                      float* rew, float* cost, float* done, float* init) {
+  const long long n = q->slot_floats;
+  const float* src = q->ring + (size_t)(which ? q->side : q->main) * n;
+  const long long e0 = (long long)B * o, e1 = 2 * e0, e2 = e1 + (long long)B * a, e3 = e2 + B, e4 = e3 + B, e5 = e4 + B;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float* d; long long j;
+    if (i < e0) { d = obs; j = i; }
+    else if (i < e1) { d = nobs; j = i - e0; }
+    else if (i < e2) { d = act; j = i - e1; }
+    else if (i < e3) { d = rew; j = i - e2; }
+    else if (i < e4) { d = cost; j = i - e3; }
+    else if (i < e5) { d = done; j = i - e4; }
+    else { d = init; j = i - e5; }
+    if (d) d[j] = src[i];
+  }
 }
 
 // timestamp node of the in-graph profile (osrl_profile): nanoseconds of the global timer

@@ -374,6 +374,37 @@ class Engine:
                                      C.c_void_p(self._stream())))
         self._keep = keep
 
+    def steps_host(self, batches, want_stats: bool = True):
+        """k steps on k explicit host minibatches in ONE call (osrl_steps_host): `batches` is a list of batch dicts or
+        one dict of stacked [k, B, ...] tensors.  Returns the k per-step stat dicts (or None with want_stats=False, in
+        which case the call does not wait for the GPU)."""
+        if isinstance(batches, (list, tuple)):
+            keys = [k_ for k_ in _STEP_KEYS if k_ in batches[0] and batches[0][k_] is not None]
+            batches = {k_: torch.stack([torch.as_tensor(b[k_], dtype=torch.float32).reshape(self.batch_size, -1)
+                                        for b in batches]) for k_ in keys}
+        k = int(batches["observations"].shape[0])
+        dims = {"observations": self.cfg.obs_dim, "next_observations": self.cfg.obs_dim, "actions": self.cfg.act_dim}
+        b = Batch()
+        b.rows, b.on_host = self.batch_size, 1
+        keep = []
+        for name in _STEP_KEYS:
+            if name not in batches or batches[name] is None:
+                continue
+            t, p, on_host = _as_f32(batches[name], self.device)
+            if not on_host:
+                raise ValueError("steps_host takes host tensors (device batches: step())")
+            want = k * self.batch_size * dims.get(name, 1)
+            if t.numel() != want:
+                raise ValueError(f"{name}: expected {want} floats ([{k}, {self.batch_size}, ...]), got {t.numel()}")
+            keep.append(t)
+            setattr(b, name, p)
+        out = (C.c_float * (k * len(self.stat_names)))() if want_stats else None
+        check(self.lib.osrl_steps_host(self.h, C.byref(b), k, out, C.c_void_p(self._stream())))
+        if out is None:
+            return None
+        n = len(self.stat_names)
+        return [{self.stat_names[i]: float(out[j * n + i]) for i in range(n)} for j in range(k)]
+
     def steps(self, k: int) -> None:
         """k steps sampled on the device from the resident dataset."""
         check(self.lib.osrl_steps(self.h, int(k), C.c_void_p(self._stream())))

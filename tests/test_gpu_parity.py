@@ -314,3 +314,37 @@ def test_state_blob_resume_is_bit_exact(lib_built, algo):
     a.steps(1)
     assert a.stats_lagged() == prev
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("algo", ["bc", "bcql", "cpq", "bearl"])
+def test_steps_host_equals_step_loop(lib_built, algo):
+    """osrl_steps_host (k host minibatches per call: pinned ring read in place by the step graphs, stats posted back the
+    same way, VAE algorithms pipelined) against k calls of osrl_step on the same batches with device noise: state AND the
+    per-step stats must be bit-identical, across a second call (ring reuse, counters) and a k = 1 call."""
+    z, meta = load_golden(f"{algo}_full")
+    cfg, B = meta["cfg"], meta["B"]
+    orc = make_oracle(algo, cfg, 0)
+    rng = np.random.default_rng(5)
+    batches = [synth.make_batch(rng, B, cfg["state_dim"], cfg["action_dim"]) for _ in range(8)]
+    if algo == "bc":
+        batches = [{k: b[k] for k in ("observations", "actions")} for b in batches]
+    loop, host = _engine(meta, B), _engine(meta, B)
+    for eng in (loop, host):
+        eng.load_params(orc.params)
+    want = []
+    for b in batches:
+        loop.step(b)
+        want.append(loop.stats())
+    got = host.steps_host(batches[:5])                                  # list of dicts
+    stacked = {k: torch.stack([torch.as_tensor(b[k]).reshape(B, -1) for b in batches[5:7]]) for k in batches[0]}
+    got += host.steps_host(stacked)                                     # stacked [k, B, ...] tensors
+    got += host.steps_host(batches[7:])                                 # k = 1: sequential graph
+    assert got == want
+    for sec in ("param", "target", "grad", "adam_m", "adam_v"):
+        a, b = loop.read_section(sec), host.read_section(sec)
+        for k in a:
+            assert torch.equal(a[k], b[k]), f"{sec} {k}: host-queue run differs (max |d| {float((a[k] - b[k]).abs().max()):.3e})"
+    assert loop.scalars() == host.scalars()
+    with pytest.raises(ValueError):
+        host.steps_host({k: v[:, :-1] for k, v in stacked.items()})     # wrong row count
+    loop.close(); host.close()
