@@ -321,6 +321,7 @@ def run_ours(args):
     eng = model._bind(BATCH, lrs, seed=1234, world_size=world, rank=rank)
     if world > 1:
         comm_setup(eng)
+    dp_mode = eng.dp_mode
     data = make_dataset(DATASET_ROWS, seed=100 + rank)      # each rank owns its own shard (weak scaling)
     eng.upload_dataset(data, REWARD_SCALE, COST_SCALE)
 
@@ -524,6 +525,9 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "per_gpu_batch": BATCH,
                    "parallelism": f"dp{world}", "synchronous_steps_per_s": sync_steps_per_s,
+                   "gradient_exchange": {"single": "none (1 GPU)", "nccl": "ncclAllReduce nodes in the step graph",
+                                         "peer": "ordered sum out of NVLink peer memory inside the Adam kernel "
+                                                 "(k_dp_adam), no NCCL on the step's path"}[dp_mode],
                    "value_is": "data-parallel ranks x synchronous steps/s (batch-256 step equivalents)",
                    "dataset_rows_per_gpu": DATASET_ROWS, "init": "osrl_b200.algorithms.BCQL under seed_all(0)",
                    "l2": "inputs larger than L2: the resident dataset is 192 MB per GPU and rows are drawn at "

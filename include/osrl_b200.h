@@ -288,10 +288,16 @@ int osrl_profile_was_in_graph(osrl_engine* e);
 int64_t osrl_launch_count(osrl_engine* e);
 int osrl_launches_per_step(osrl_engine* e);
 
-/* Data-parallel: one engine per rank; gradients are all-reduced (NCCL, fp32 sum, /world)
- * before each optimiser update.  id is an ncclUniqueId made by rank 0. */
+/* Data-parallel: one engine per rank (one process per GPU); each optimiser update uses the gradient summed over the
+ * ranks (losses are pre-scaled by 1/world), so N ranks x B rows equal one step on the concatenated batch.  id is an
+ * ncclUniqueId made by rank 0.  osrl_comm_init creates the NCCL communicator(s) and then tries to map every peer's
+ * gradient section over NVLink (cudaIpc): if every rank succeeds, BC / BCQ-Lag / CPQ / BEAR-Lag steps exchange
+ * gradients through peer memory inside the Adam kernel (ordered sum: bit-identical replicas) and NCCL is no longer on
+ * the step's path; otherwise (or with OSRL_DP=nccl, and always for CDT) the step graph holds ncclAllReduce nodes.
+ * osrl_dp_mode: 0 = single GPU, 1 = NCCL collectives, 2 = peer memory. */
 int osrl_comm_unique_id(char out[128]);
 int osrl_comm_init(osrl_engine* e, const char id[128], int world_size, int rank);
+int osrl_dp_mode(osrl_engine* e);
 
 #ifdef __cplusplus
 }

@@ -124,6 +124,7 @@ SYMBOLS = [
     ("osrl_launches_per_step", C.c_int, [C.c_void_p]),
     ("osrl_comm_unique_id", C.c_int, [C.c_char * 128]),
     ("osrl_comm_init", C.c_int, [C.c_void_p, C.c_char * 128, C.c_int, C.c_int]),
+    ("osrl_dp_mode", C.c_int, [C.c_void_p]),
 ]
 
 _lib = None

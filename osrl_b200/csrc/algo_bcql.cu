@@ -24,7 +24,7 @@ void build_bc(Engine& e) {
   KOP(p, e, 0.0, (k_bc_loss<<<1, 1024, 0, s>>>(u, act, B * a, lim, dpre, stat, iw)));
   mlp_bwd(e, p, e.P, e.G, m, e.b_obs, o, B, ACT_RELU, h, dpre);
   const Group& g = e.plan.groups[e.plan.g_actor];
-  emit_allreduce(e, p, e.G + g.begin, g.end - g.begin);
+  emit_allreduce(e, p, e.G + g.begin, g.end - g.begin, false, DP_GRAD);
   emit_adam(e, p, e.plan.g_actor, g.begin, g.end, false);
 }
 
@@ -161,7 +161,7 @@ void build_bcql(Engine& e, int phase) {
     const Group& g1 = pl.groups[pl.g_critic];
     const Group& g2 = pl.groups[pl.g_cost];
     OSRL_REQUIRE(g1.end == g2.begin, "critic groups must be adjacent");
-    emit_allreduce(e, p, e.G + g1.begin, g2.end - g1.begin);
+    emit_allreduce(e, p, e.G + g1.begin, g2.end - g1.begin, false, DP_GRAD);
     // same lr and step count for both groups -> one fused Adam+Polyak launch over the union
     emit_adam(e, p, pl.g_critic, g1.begin, g2.end, true);
   }
@@ -199,7 +199,7 @@ void build_bcql(Engine& e, int phase) {
     if (e.world > 1) {  // PID error is a mean over the GLOBAL batch (net.py:380): 4-byte all-reduce before the backward
       float* part = e.ws(4);
       KOP(p, e, 0.0, (k_rowmin_mean<<<1, 1024, 0, s>>>(pqcv, nqc, B, thres, iw, part)));
-      emit_allreduce(e, p, part, 1);
+      emit_allreduce(e, p, part, 1, false, DP_SCALAR);
       gmean = part;
     }
     KOP(p, e, 0.0, (k_bcql_actor_loss<<<1, 1024, 0, s>>>(pqv, nq, pqcv, nqc, B, thres, kp, ki, kd, ds, dpq, dpqc, st3, iw,
@@ -221,7 +221,7 @@ void build_bcql(Engine& e, int phase) {
   mlp_bwd(e, p, e.P, e.G, act, p_ain, in, B, ACT_TANH, pah, dpre);
   {
     const Group& g = pl.groups[pl.g_actor];
-    emit_allreduce(e, p, e.G + g.begin, g.end - g.begin);
+    emit_allreduce(e, p, e.G + g.begin, g.end - g.begin, false, DP_GRAD);
     emit_adam(e, p, pl.g_actor, g.begin, g.end, true);
   }
 }

@@ -127,7 +127,7 @@ void build_cpq(Engine& e, int phase) {
     const Group& g1 = pl.groups[pl.g_critic];
     const Group& g2 = pl.groups[pl.g_cost];
     OSRL_REQUIRE(g1.end == g2.begin, "critic groups must be adjacent");
-    emit_allreduce(e, p, e.G + g1.begin, g2.end - g1.begin);
+    emit_allreduce(e, p, e.G + g1.begin, g2.end - g1.begin, false, DP_GRAD);
     emit_adam(e, p, pl.g_critic, g1.begin, g2.end, true);
   }
 
@@ -163,7 +163,7 @@ void build_cpq(Engine& e, int phase) {
   mlp_bwd(e, p, e.P, e.G, actor, e.b_obs, o, B, ACT_RELU, ah, dmh);
   {
     const Group& g = pl.groups[pl.g_actor];
-    emit_allreduce(e, p, e.G + g.begin, g.end - g.begin);
+    emit_allreduce(e, p, e.G + g.begin, g.end - g.begin, false, DP_GRAD);
     emit_adam(e, p, pl.g_actor, g.begin, g.end, true);
   }
 }
@@ -252,7 +252,7 @@ void build_bearl(Engine& e, int phase) {
     const Group& g1 = pl.groups[pl.g_critic];
     const Group& g2 = pl.groups[pl.g_cost];
     OSRL_REQUIRE(g1.end == g2.begin, "critic groups must be adjacent");
-    emit_allreduce(e, p, e.G + g1.begin, g2.end - g1.begin);
+    emit_allreduce(e, p, e.G + g1.begin, g2.end - g1.begin, false, DP_GRAD);
     emit_adam(e, p, pl.g_critic, g1.begin, g2.end, true);
   }
 
@@ -295,7 +295,7 @@ void build_bearl(Engine& e, int phase) {
       float* part = e.ws(4);
       KOP(p, e, 0.0, (k_rowmin_mean<<<1, 1024, 0, s>>>(pqcv, nqc, B, thres, iw, part)));
       KOP(p, e, 0.0, (k_mean_sub<<<1, 1024, 0, s>>>(mmdv, B, mth, iw, part + 1)));
-      emit_allreduce(e, p, part, 2);
+      emit_allreduce(e, p, part, 2, false, DP_SCALAR);
       gmean = part;
     }
     KOP(p, e, 0.0, (k_bear_actor_loss<<<1, 1024, 0, s>>>(pqv, nq, pqcv, nqc, mmdv, B, thres, kp, ki, kd, mth, alr, start, ds,
@@ -315,7 +315,7 @@ void build_bearl(Engine& e, int phase) {
   mlp_bwd(e, p, e.P, e.G, actor, e.b_obs, o, B, ACT_RELU, ah, dmh);
   {
     const Group& g = pl.groups[pl.g_actor];
-    emit_allreduce(e, p, e.G + g.begin, g.end - g.begin);
+    emit_allreduce(e, p, e.G + g.begin, g.end - g.begin, false, DP_GRAD);
     emit_adam(e, p, pl.g_actor, g.begin, g.end, true);
   }
 }

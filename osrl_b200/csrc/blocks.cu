@@ -67,7 +67,7 @@ void emit_vae_update(Engine& e, Program& p, const float* sa, float* dec_in, cons
                  task_wgrad(dml, 2 * L, h2, V, B, e.G, v.heads), task_wgrad(dh1, V, sa, o + a, B, e.G, v.e1)});
     p.end_par();
     const Group& g = e.plan.groups[e.plan.g_vae];
-    emit_allreduce(e, p, e.G + g.begin, g.end - g.begin);
+    emit_allreduce(e, p, e.G + g.begin, g.end - g.begin, false, DP_GRAD);
     emit_adam(e, p, e.plan.g_vae, g.begin, g.end, false);
     return;
   }
@@ -93,7 +93,7 @@ void emit_vae_update(Engine& e, Program& p, const float* sa, float* dec_in, cons
   flush(e, p, {task_wgrad(dh2, V, h1, V, B, e.G, v.e2), task_dgrad(dh2, V, B, e.P, v.e2, dh1, V, h1, V, ACT_RELU)});
   flush(e, p, {task_wgrad(dh1, V, sa, o + a, B, e.G, v.e1)});
   const Group& g = e.plan.groups[e.plan.g_vae];
-  emit_allreduce(e, p, e.G + g.begin, g.end - g.begin);
+  emit_allreduce(e, p, e.G + g.begin, g.end - g.begin, false, DP_GRAD);
   emit_adam(e, p, e.plan.g_vae, g.begin, g.end, false);
 }
 

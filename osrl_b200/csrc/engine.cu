@@ -655,10 +655,25 @@ void emit_adam(Engine& e, Program& p, int group, int64_t begin, int64_t end, boo
   const float tau = e.plan.cfg.tau;
   // read p,g,m,v + write p,m,v = 28 B/param; Polyak adds read+write of the target = 8 B/param
   const double bytes = (double)(end - begin) * (polyak ? 36.0 : 28.0);
+  // data parallel, peer mode: the all-reduce of this range (the DP_GRAD emit_allreduce just before) happens here
+  int slot = -1;
+  if (e.world > 1 && !clip_coef) {
+    slot = (int)e.dp_slot_group.size();
+    OSRL_REQUIRE(slot < DP_MAX_SLOT, "too many data-parallel reduce sites");
+    e.dp_slot_group.push_back(group);
+  }
   p.add(polyak ? "k_adam+polyak" : "k_adam", bytes, 0.0, true, [=](cudaStream_t s) {
-    k_adam<<<blocks, 256, 0, s>>>(ep->P + begin, ep->G + begin, ep->M + begin, ep->V + begin, ep->T + begin, n4, ep->ds,
-                                  group, (float)g.beta1, (float)g.beta2, (float)(1.0 - g.beta1), (float)(1.0 - g.beta2),
-                                  g.eps, g.wd, tau, polyak ? 1 : 0, 1.f, clip_coef);
+    if (ep->peer_on && slot >= 0)
+      // <= 148 blocks: with the two graph branches' reduce kernels both resident no waiting block can keep a
+      // signalling block off the machine
+      k_dp_adam<<<std::min(blocks, 148), 256, 0, s>>>(ep->peers, slot, begin, ep->P + begin, ep->M + begin, ep->V + begin,
+                                                      ep->T + begin, n4, ep->ds, group, (float)g.beta1, (float)g.beta2,
+                                                      (float)(1.0 - g.beta1), (float)(1.0 - g.beta2), g.eps, g.wd, tau,
+                                                      polyak ? 1 : 0);
+    else
+      k_adam<<<blocks, 256, 0, s>>>(ep->P + begin, ep->G + begin, ep->M + begin, ep->V + begin, ep->T + begin, n4, ep->ds,
+                                    group, (float)g.beta1, (float)g.beta2, (float)(1.0 - g.beta1), (float)(1.0 - g.beta2),
+                                    g.eps, g.wd, tau, polyak ? 1 : 0, 1.f, clip_coef);
     ep->launches++;
   });
 }
@@ -676,6 +691,7 @@ static AllReduce_t AllReduce = nullptr;
 static CommDestroy_t CommDestroy = nullptr;
 static GetErrorString_t GetErrorString = nullptr;
 static int (*CommSplit)(void*, int, int, void**, void*) = nullptr;   // optional (NCCL >= 2.18)
+static int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;   // optional: peer-memory setup
 static void load() {
   if (lib) return;
   const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
@@ -687,6 +703,7 @@ static void load() {
   CommDestroy = (CommDestroy_t)dlsym(lib, "ncclCommDestroy");
   GetErrorString = (GetErrorString_t)dlsym(lib, "ncclGetErrorString");
   CommSplit = (int (*)(void*, int, int, void**, void*))dlsym(lib, "ncclCommSplit");
+  AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(lib, "ncclAllGather");
   if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) throw Err(OSRL_ERR_NCCL, "libnccl lacks required symbols");
 }
 static void check(int r, const char* what) {
@@ -694,12 +711,23 @@ static void check(int r, const char* what) {
 }
 }  // namespace nccl
 
-void emit_allreduce(Engine& e, Program& p, float* buf, int64_t count, bool f64) {
+void emit_allreduce(Engine& e, Program& p, float* buf, int64_t count, bool f64, int kind) {
   if (e.world <= 1) return;
   Engine* ep = &e;
   const bool side = (&p == &e.pa);   // the pipelined VAE branch reduces on its own communicator: the two branches'
                                      // collectives may then be in flight at the same time
-  p.add("ncclAllReduce", 4.0 * (double)count, 0.0, false, [=](cudaStream_t s) {
+  int sslot = -1;
+  if (kind == DP_SCALAR) {
+    OSRL_REQUIRE(!f64 && count <= DP_SCAL_N && e.dp_scal_slots < DP_MAX_SLOT, "scalar exchange: at most 8 fp32 values, 32 sites");
+    sslot = e.dp_scal_slots++;
+  }
+  p.add("allreduce", 4.0 * (double)count, 0.0, false, [=](cudaStream_t s) {
+    if (ep->peer_on && kind == DP_GRAD) return;   // fused into the Adam launch that follows
+    if (ep->peer_on && kind == DP_SCALAR) {
+      k_dp_scalar<<<1, 32, 0, s>>>(ep->peers, sslot, buf, (int)count);
+      ep->launches++;
+      return;
+    }
     void* comm = side ? ep->comm2 : ep->comm;
     if (!comm) throw Err(OSRL_ERR_STATE, "world_size > 1 but osrl_comm_init was not called");
     nccl::check(nccl::AllReduce(buf, buf, (size_t)count, f64 ? /*ncclFloat64*/ 8 : /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm, s),
@@ -845,6 +873,10 @@ static void drop_sampled_graphs(Engine& e) {   // they bake the dataset pointers
     if (*g) { cudaGraphExecDestroy(*g); *g = nullptr; }
 }
 static void free_all(Engine* e) {
+  if (e->peer_on) {   // peers may still be summing this rank's last gradients out of its memory
+    k_dp_drain<<<1, 32>>>(e->d_peers);
+    cudaDeviceSynchronize();
+  }
   if (e->g_body) cudaGraphExecDestroy(e->g_body);
   drop_sampled_graphs(*e);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
@@ -853,6 +885,7 @@ static void free_all(Engine* e) {
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   for (float* hp : {e->x_ring, e->x_st_side, e->x_st_main})
     if (hp) cudaFreeHost(hp);
+  for (void* q : e->ipc_open) cudaIpcCloseMemHandle(q);
   for (int i = 0; i < 2; ++i) {
     if (e->stats_pinned[i]) cudaFreeHost(e->stats_pinned[i]);
     if (e->stats_ev[i]) cudaEventDestroy(e->stats_ev[i]);
@@ -1043,7 +1076,11 @@ static void run_ops(Engine& e, const Program& p, cudaStream_t s) {
   }
 }
 static void prologue(Engine& e, cudaStream_t s, unsigned mask = 0xffffffffu) {
-  k_prologue<<<1, 32, 0, s>>>(e.ds, e.d_groups, (int)e.plan.groups.size(), mask);
+  unsigned slots = 0;
+  if (e.peer_on)
+    for (size_t i = 0; i < e.dp_slot_group.size(); ++i)
+      if ((mask >> e.dp_slot_group[i]) & 1u) slots |= 1u << i;
+  k_prologue<<<1, 32, 0, s>>>(e.ds, e.d_groups, (int)e.plan.groups.size(), mask, e.peer_on ? e.d_peers : nullptr, slots);
   e.launches++;
 }
 static void epilogue(Engine& e, cudaStream_t s, int mode = 0, bool hostq = false) {
@@ -1727,6 +1764,11 @@ int osrl_stats(osrl_engine* h, float* host_out, int cap, int* n, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   OSRL_CUDA(cudaMemcpyAsync(host_out, e.stats, *n * sizeof(float), cudaMemcpyDeviceToHost, s));
   OSRL_CUDA(cudaStreamSynchronize(s));
+  if (e.peer_on) {   // a peer that never arrived (crashed rank, diverged control flow): fail loudly instead of training on
+    unsigned to = 0;
+    OSRL_CUDA(cudaMemcpy(&to, &e.dp_flags->timeout, sizeof(to), cudaMemcpyDeviceToHost));
+    if (to) throw Err(OSRL_ERR_NCCL, "data-parallel peer exchange timed out waiting for another rank");
+  }
   OSRL_CATCH
 }
 
@@ -2109,6 +2151,98 @@ int osrl_comm_unique_id(char out[128]) {
   memcpy(out, id.internal, 128);
   OSRL_CATCH
 }
+// Map every peer's gradient section and flag block (dp_peer.cuh).  The cudaIpc handles travel over the communicator
+// that was just created; peer mode is switched on only if EVERY rank mapped every peer (a rank that cannot -- no P2P
+// path, IPC disabled -- votes it down for all, and the step keeps its NCCL collectives).  OSRL_DP=nccl skips it.
+static void peer_setup(Engine& e) {
+  const char* v = getenv("OSRL_DP");
+  const bool want = !(v && strcmp(v, "nccl") == 0) && e.plan.cfg.algo != OSRL_ALGO_CDT && e.world <= DP_MAX_WORLD &&
+                    nccl::AllGather != nullptr;
+  struct Rec { cudaIpcMemHandle_t g, f; int ok, pad[3]; };
+  const int W = e.world;
+  Rec mine;
+  memset(&mine, 0, sizeof(mine));
+  mine.ok = want ? 1 : 0;
+  if (want) {
+    void* fl = nullptr;
+    if (cudaMalloc(&fl, sizeof(DpFlags)) == cudaSuccess) {
+      e.allocs.push_back(fl);
+      e.dp_flags = (DpFlags*)fl;
+      OSRL_CUDA(cudaMemset(fl, 0, sizeof(DpFlags)));
+    } else mine.ok = 0;
+    if (mine.ok && (cudaIpcGetMemHandle(&mine.g, e.G) != cudaSuccess || cudaIpcGetMemHandle(&mine.f, e.dp_flags) != cudaSuccess))
+      mine.ok = 0;
+    cudaGetLastError();
+  }
+  // marks the peers must find through their mappings (a handle that resolves to the wrong base would otherwise go
+  // unnoticed): the flag block's magic word and, until set-up ends, the first gradient word
+  uint32_t g0_saved = 0;
+  const uint32_t mark = 0xD9000000u | (uint32_t)e.rank;
+  if (mine.ok) {
+    OSRL_CUDA(cudaMemcpy(&g0_saved, e.G, 4, cudaMemcpyDeviceToHost));
+    OSRL_CUDA(cudaMemcpy(e.G, &mark, 4, cudaMemcpyHostToDevice));
+    OSRL_CUDA(cudaMemcpy(&e.dp_flags->magic, &mark, 4, cudaMemcpyHostToDevice));
+  }
+  const bool marked = mine.ok != 0;
+  if (!nccl::AllGather) return;   // every rank loads the same library: the same decision everywhere
+  Rec* d = nullptr;
+  OSRL_CUDA(cudaMalloc((void**)&d, sizeof(Rec) * (W + 1)));
+  OSRL_CUDA(cudaMemcpy(d + W, &mine, sizeof(Rec), cudaMemcpyHostToDevice));
+  std::vector<Rec> all(W);
+  auto gather = [&]() {
+    nccl::check(nccl::AllGather(d + W, d, sizeof(Rec), /*ncclInt8*/ 0, e.comm, (cudaStream_t)0), "ncclAllGather");
+    OSRL_CUDA(cudaStreamSynchronize(0));
+    OSRL_CUDA(cudaMemcpy(all.data(), d, sizeof(Rec) * W, cudaMemcpyDeviceToHost));
+  };
+  gather();
+  bool ok = true;
+  for (auto& r : all) ok = ok && r.ok;
+  DpPeers pr;
+  memset(&pr, 0, sizeof(pr));
+  pr.world = W; pr.rank = e.rank;
+  if (ok) {
+    for (int r = 0; r < W && ok; ++r) {
+      if (r == e.rank) { pr.G[r] = e.G; pr.flags[r] = e.dp_flags; continue; }
+      void *pg = nullptr, *pf = nullptr;
+      if (cudaIpcOpenMemHandle(&pg, all[r].g, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+      e.ipc_open.push_back(pg);
+      if (cudaIpcOpenMemHandle(&pf, all[r].f, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+      e.ipc_open.push_back(pf);
+      pr.G[r] = (const float*)pg; pr.flags[r] = (DpFlags*)pf;
+      uint32_t seen_g = 0, seen_f = 0;
+      if (cudaMemcpy(&seen_g, pg, 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+          cudaMemcpy(&seen_f, &((DpFlags*)pf)->magic, 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+          seen_g != (0xD9000000u | (uint32_t)r) || seen_f != (0xD9000000u | (uint32_t)r))
+        ok = false;
+    }
+    cudaGetLastError();
+  }
+  // second round: did every rank manage to map everybody?
+  mine.ok = ok ? 1 : 0;
+  OSRL_CUDA(cudaMemcpy(d + W, &mine, sizeof(Rec), cudaMemcpyHostToDevice));
+  gather();
+  for (auto& r : all) ok = ok && r.ok;
+  cudaFree(d);
+  if (marked) OSRL_CUDA(cudaMemcpy(e.G, &g0_saved, 4, cudaMemcpyHostToDevice));   // (after every rank has looked)
+  if (!ok) {
+    for (void* q : e.ipc_open) cudaIpcCloseMemHandle(q);
+    e.ipc_open.clear();
+    cudaGetLastError();
+    if (want && e.rank == 0) fprintf(stderr, "osrl_b200: peer-memory data parallelism unavailable, using NCCL collectives\n");
+    return;
+  }
+  e.peers = pr;
+  OSRL_CUDA(cudaMalloc((void**)&e.d_peers, sizeof(DpPeers)));
+  e.allocs.push_back(e.d_peers);
+  OSRL_CUDA(cudaMemcpy(e.d_peers, &pr, sizeof(pr), cudaMemcpyHostToDevice));
+  e.peer_on = true;
+}
+
+int osrl_dp_mode(osrl_engine* h) {
+  if (!h || h->e->world <= 1) return 0;
+  return h->e->peer_on ? 2 : (h->e->comm ? 1 : 0);
+}
+
 int osrl_comm_init(osrl_engine* h, const char id[128], int world_size, int rank) {
   OSRL_TRY
   OSRL_REQUIRE(h && id, "null argument");
@@ -2121,6 +2255,7 @@ int osrl_comm_init(osrl_engine* h, const char id[128], int world_size, int rank)
   nccl::check(nccl::CommInitRank(&e.comm, world_size, u, rank), "ncclCommInitRank");
   if (e.pipelined && nccl::CommSplit)   // communicator of the pipelined VAE branch (absent: osrl_steps stays sequential)
     nccl::check(nccl::CommSplit(e.comm, 0, rank, &e.comm2, nullptr), "ncclCommSplit");
+  peer_setup(e);
   OSRL_CATCH
 }
 

@@ -218,6 +218,15 @@ struct Engine {
   // data parallel
   void* comm = nullptr;
   void* comm2 = nullptr;   // pipelined VAE branch
+  // data parallel over NVLink peer memory (dp_peer.cuh): set up by osrl_comm_init when every rank could map every
+  // peer (OSRL_DP=nccl keeps the NCCL collectives)
+  bool peer_on = false;
+  DpPeers peers{};
+  DpPeers* d_peers = nullptr;
+  DpFlags* dp_flags = nullptr;
+  std::vector<void*> ipc_open;
+  std::vector<int> dp_slot_group;   // fused reduce+Adam sites: slot -> optimiser group
+  int dp_scal_slots = 0;
   int world = 1, rank = 0;
 
   float* ws(size_t n);  // zero-initialised device workspace
@@ -272,7 +281,11 @@ void emit_gemm(Engine& e, Program& p, const std::vector<GemmTask>& tasks);
 void emit_copy(Engine& e, Program& p, const std::vector<CopyTask>& tasks);
 void emit_adam(Engine& e, Program& p, int group, int64_t begin, int64_t end, bool polyak,
                const float* clip_coef = nullptr);
-void emit_allreduce(Engine& e, Program& p, float* buf, int64_t count, bool f64 = false);
+// kind: DP_PLAIN = a collective whose result is used as is (NCCL); DP_GRAD = the gradients of the optimiser group the
+// next emit_adam steps (peer mode: skipped, emit_adam reduces and steps in one kernel); DP_SCALAR = <= 8 fp32
+// cross-batch scalars (peer mode: k_dp_scalar)
+enum { DP_PLAIN = 0, DP_GRAD = 1, DP_SCALAR = 2 };
+void emit_allreduce(Engine& e, Program& p, float* buf, int64_t count, bool f64 = false, int kind = DP_PLAIN);
 CopyTask copy_cols(float* dst, int ldd, int dcol0, const float* src, int lds, int scol0, int rows, int cols,
                    int row_div = 1, int row_mod = 1 << 30);
 

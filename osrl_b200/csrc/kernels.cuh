@@ -83,12 +83,15 @@ struct AdamGroupCfg {
   double lr, beta1, beta2;
   int warmup;  // >0: lr * min((t)/warmup, 1) with t = step count after increment (LambdaLR, cdt.py:327-330)
 };
-static __global__ void k_prologue(DevState* ds, const AdamGroupCfg* g, int ngroups, unsigned mask) {
+}  // namespace osrl
+#include "dp_peer.cuh"
+namespace osrl {
+
+static __global__ void k_prologue(DevState* ds, const AdamGroupCfg* g, int ngroups, unsigned mask, const DpPeers* dp = nullptr,
+                                  unsigned dp_slot_mask = 0u) {
   if (blockIdx.x != 0) return;
-  {
-    const int i = threadIdx.x;           // one thread per optimiser group (the double-precision pow()s are ~1.5 us each)
-    if (i >= ngroups) return;
-    if (!((mask >> i) & 1u)) return;     // pipelined graphs advance the VAE group and the others separately
+  const int i = threadIdx.x;           // one thread per optimiser group (the double-precision pow()s are ~1.5 us each)
+  if (i < ngroups && ((mask >> i) & 1u)) {   // pipelined graphs advance the VAE group and the others separately
     const int t = ds->adam_t[i] + 1;
     ds->adam_t[i] = t;
     double lr = (double)g[i].lr;
@@ -102,6 +105,8 @@ static __global__ void k_prologue(DevState* ds, const AdamGroupCfg* g, int ngrou
     ds->adam_step_size[i] = (float)(lr / bc1);
     ds->adam_bc2_sqrt[i] = (float)sqrt(bc2);
   }
+  // data parallel over peer memory: the step is about to overwrite gradient ranges the peers summed last step
+  if (dp && dp->world > 1) dp_wait_done(*dp, dp_slot_mask);
 }
 // mode 0: a whole step finished (both counters); 1: everything but the VAE update; 2: the VAE update only
 // Host-batch queue of osrl_steps_host: `ring` holds the call's k packed minibatches and `st_*` its per-step stat

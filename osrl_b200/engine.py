@@ -486,6 +486,12 @@ class Engine:
         buf = (C.c_char * 128).from_buffer_copy(unique_id)
         check(self.lib.osrl_comm_init(self.h, buf, self.cfg.world_size, self.cfg.rank))
 
+    @property
+    def dp_mode(self) -> str:
+        """How the gradients travel between the ranks: "single", "nccl" (collectives in the step graph) or "peer"
+        (summed out of NVLink peer memory inside the Adam kernel)."""
+        return ("single", "nccl", "peer")[self.lib.osrl_dp_mode(self.h)]
+
 
 def comm_unique_id() -> bytes:
     buf = (C.c_char * 128)()

@@ -91,7 +91,17 @@ def run(algo: str, backend: str, steps: int = 3, Bg: int = 32, cfg=None, detail:
             err = float((got[k] - ref).norm())
             bound = 1e-3 * float((ref - init[k]).norm()) + 4e-7 * float(ref.norm()) + 1e-9
             worst = max(worst, err / bound)
-    ok = torch.tensor([1.0 if worst <= 1.0 else 0.0])
+    same = True
+    mode = backend
+    if backend == "nccl":   # replicas must be bit-identical (every rank applies the same summed gradient)
+        mode = eng.dp_mode
+        flat = torch.cat([got[k].reshape(-1).float().cuda() for k in sorted(got)])
+        ref0 = flat.clone()
+        dist.broadcast(ref0, src=0)
+        same = bool(torch.equal(flat, ref0))
+        if os.environ.get("OSRL_EXPECT_DP"):
+            assert mode == os.environ["OSRL_EXPECT_DP"], f"dp mode {mode}, expected {os.environ['OSRL_EXPECT_DP']}"
+    ok = torch.tensor([1.0 if worst <= 1.0 and same else 0.0])
     if backend == "nccl":
         ok = ok.cuda()
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
@@ -99,7 +109,8 @@ def run(algo: str, backend: str, steps: int = 3, Bg: int = 32, cfg=None, detail:
     if backend == "nccl":
         wt = wt.cuda()
     dist.all_reduce(wt, op=dist.ReduceOp.MAX)
-    out = {"algo": algo, "backend": backend, "world": world, "global_batch": Bg, "steps": steps,
+    out = {"algo": algo, "backend": backend, "dp_mode": mode, "replicas_identical": same, "world": world, "global_batch": Bg,
+           "steps": steps,
            "worst_ratio": float(wt.item()), "ok": bool(ok.item()),
            "bound": "final params vs the single-rank oracle on the concatenated batch: |d| <= 1e-3 |delta| + 4e-7 |p| per tensor"}
     if backend == "nccl":
