@@ -29,6 +29,8 @@ def make_config(algo: str, *, batch_size: int, seed: int = 0, world_size: int = 
     ren = {"state_dim": "obs_dim", "action_dim": "act_dim", "vae_hidden_sizes": "vae_hidden"}
     # defaults of fields the reference defaults too
     cfg.max_action, cfg.gamma, cfg.tau, cfg.phi, cfg.lmbda, cfg.beta = 1.0, 0.99, 0.005, 0.05, 0.75, 0.5
+    if algo == "cpq":
+        cfg.beta = 1.5   # cpq.py:48 (BCQ-Lag / BEAR-Lag default to 0.5: bcql.py:56, bearl.py:56)
     cfg.pid_kp, cfg.pid_ki, cfg.pid_kd = 0.1, 0.003, 0.001
     cfg.num_q = cfg.num_qc = 1
     cfg.cost_limit, cfg.episode_len, cfg.sample_action_num = 10, 300, 10

@@ -90,6 +90,8 @@ def run(algo: str, backend: str, steps: int = 3, Bg: int = 32, cfg=None, detail:
             ref = ref.detach()
             err = float((got[k] - ref).norm())
             bound = 1e-3 * float((ref - init[k]).norm()) + 4e-7 * float(ref.norm()) + 1e-9
+            if err > bound and rank == 0:
+                print(f"[dp {algo}] step {s} param {k}: err {err:.3e} bound {bound:.3e}", flush=True)
             worst = max(worst, err / bound)
     same = True
     mode = backend
