@@ -868,6 +868,14 @@ static float slot_drop_p(const osrl_config& c, const std::string& name) {
   if (name.rfind("drop_res", 0) == 0) return c.residual_dropout;
   return 0.f;
 }
+// a re-upload (curriculum, re-scaled rewards) replaces the resident copy: drop the old one instead of keeping it until
+// osrl_engine_destroy.  Called after a device synchronisation.
+static void release_alloc(Engine& e, void* p) {
+  if (!p) return;
+  auto it = std::find(e.allocs.begin(), e.allocs.end(), p);
+  if (it != e.allocs.end()) e.allocs.erase(it);
+  cudaFree(p);
+}
 static void drop_sampled_graphs(Engine& e) {   // they bake the dataset pointers
   for (cudaGraphExec_t* g : {&e.g_sampled, &e.g_pro, &e.g_mid, &e.g_last, &e.g_xbody, &e.g_xpro, &e.g_xmid, &e.g_xlast})
     if (*g) { cudaGraphExecDestroy(*g); *g = nullptr; }
@@ -1432,6 +1440,12 @@ int osrl_buffer_upload(osrl_engine* h, const osrl_dataset_view* v) {
     r[2 * o + a + 2] = v->done ? v->done[i] : ((v->terminals[i] || v->timeouts[i]) ? 1.f : 0.f);  // :815-816
     if (cop) r[2 * o + a + 3] = v->is_init[i];
   }
+  if (e.ds_rows) {
+    OSRL_CUDA(cudaDeviceSynchronize());
+    drop_sampled_graphs(e);
+    release_alloc(e, e.ds_rows);
+    e.ds_rows = nullptr;
+  }
   void* d = nullptr;
   OSRL_CUDA(cudaMalloc(&d, packed.size() * sizeof(float)));
   e.allocs.push_back(d);
@@ -1476,6 +1490,12 @@ int osrl_seq_buffer_upload(osrl_engine* h, const osrl_seq_dataset_view* v) {
   std::vector<int> alias;
   build_alias(p, prob, alias);
   std::vector<long long> off(v->traj_offsets, v->traj_offsets + v->n_traj + 1);
+  if (e.sq_rows) {
+    OSRL_CUDA(cudaDeviceSynchronize());
+    drop_sampled_graphs(e);
+    for (void* q : {(void*)e.sq_rows, (void*)e.sq_off, (void*)e.sq_prob, (void*)e.sq_alias}) release_alloc(e, q);
+    e.sq_rows = nullptr;
+  }
   e.sq_rows = e.upload(packed);
   e.sq_off = e.upload(off);
   e.sq_prob = e.upload(prob);

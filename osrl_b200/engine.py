@@ -310,10 +310,13 @@ class Engine:
         b = Batch()
         b.rows = self.batch_size
         kinds = set()
+        dims = {"observations": self.cfg.obs_dim, "next_observations": self.cfg.obs_dim, "actions": self.cfg.act_dim}
         for k in _STEP_KEYS:
             if k not in batch or batch[k] is None:
                 continue
             t, p, on_host = _as_f32(batch[k], self.device)
+            if t.numel() != self.batch_size * dims.get(k, 1):   # the C side reads batch_size * dim floats per tensor
+                raise ValueError(f"{k}: expected {self.batch_size * dims.get(k, 1)} floats, got {t.numel()}")
             keep.append(t)
             kinds.add(on_host)
             setattr(b, k, p)
@@ -353,6 +356,13 @@ class Engine:
         if isinstance(ts, np.ndarray):
             ts = torch.from_numpy(np.ascontiguousarray(ts))
         ts = ts.to(torch.int64).contiguous()
+        if not ts.is_cuda and ts.numel():
+            # the reference's nn.Embedding(episode_len + seq_len, E) raises on an index outside the table (cdt.py:75);
+            # the kernels clamp, so bad host data is refused here (device tensors are not read back: that would
+            # synchronise every step)
+            lim = self.cfg.episode_len + self.cfg.seq_len
+            if int(ts.min()) < 0 or int(ts.max()) >= lim:
+                raise IndexError(f"time_steps outside the timestep embedding table [0, {lim})")
         keep.append(ts); kinds.add(0 if ts.is_cuda else 1)
         b.time_steps = ts.data_ptr()
         if len(kinds) != 1:
