@@ -236,6 +236,45 @@ def run_other(name: str, batch: int, local: int, world: int, rank: int, barrier,
             "finite": bool(np.isfinite(list(stats.values())).all())}
 
 
+def run_preprocess(local: int, rows: int = 1_000_000, ep_len: int = 1000):
+    """One-time trajectory preprocessing of a 1M-transition DSRL-shaped dataset (HalfCheetah dims): episode split +
+    reward / cost to go + packed buffer.  device_ms includes the host->device copy of the raw arrays (74 MB)."""
+    import time
+    from oracle import cdt as ocdt
+    from osrl_b200 import Engine
+    from osrl_b200.common.dataset import SequenceDataset
+    o, a = 17, 6
+    rng = np.random.default_rng(0)
+    data = {"observations": rng.standard_normal((rows, o)).astype(np.float32),
+            "actions": rng.uniform(-1, 1, (rows, a)).astype(np.float32),
+            "rewards": rng.standard_normal(rows).astype(np.float32),
+            "costs": (rng.random(rows) < 0.1).astype(np.float32), "terminals": np.zeros(rows, bool),
+            "timeouts": (np.arange(rows) % ep_len) == ep_len - 1}
+    eng = Engine("cdt", batch_size=64, device=local, seed=0, state_dim=o, action_dim=a, max_action=1.0, seq_len=10,
+                 episode_len=ep_len, embedding_dim=128, num_layers=3, num_heads=8, use_rew=1, use_cost=1, cost_transform=1,
+                 stochastic=1, target_entropy=-float(a), learning_rate=1e-4, lr_warmup_steps=500)
+    eng.preprocess_seq_dataset(data, 0.1, 1.0)          # warm-up (allocator, first touch of the host pages)
+    t0 = time.perf_counter()
+    info = eng.preprocess_seq_dataset(data, 0.1, 1.0)
+    dev_ms = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    ds = SequenceDataset(data, seq_len=10, reward_scale=0.1, cost_scale=1.0)
+    host_ms = (time.perf_counter() - t0) * 1e3
+    sample = 100_000                                      # the reference's per-transition Python loop, bounded sample
+    sub = {k: v[:sample] for k, v in data.items()}
+    t0 = time.perf_counter()
+    trajs = ocdt.split_trajectories(sub)
+    loop_ms = (time.perf_counter() - t0) * 1e3
+    ok = bool(np.array_equal(info["returns"][:len(trajs)], np.array([t["returns"][0] for t in trajs], np.float32)))
+    eng.close()
+    return {"workload": f"process_sequence_dataset on {rows} transitions ({rows // ep_len} episodes of {ep_len}), obs 17, act 6",
+            "device_ms": dev_ms, "rows_per_s_device": rows / dev_ms * 1e3, "h2d_bytes": int(rows * (o + a + 2) * 4 + 2 * rows),
+            "host_numpy_mirror_ms": host_ms,
+            "reference_loop_port": {"sample_rows": sample, "ms": loop_ms, "rows_per_s": sample / loop_ms * 1e3,
+                                    "what": "oracle/cdt.py split_trajectories: dataset.py:137-183 restated, per-transition loop"},
+            "first_returns_equal_oracle": ok, "episodes": int(eng.n_traj)}
+
+
 # ------------------------------------------------------------------------------------------ reference arm
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -493,6 +532,13 @@ def run_ours(args):
             others["bearl_strong_b4096"] = r
         except Exception as ex:
             others["bearl_strong_b4096"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+
+    # ---- process_sequence_dataset on the device (rank 0, N == 1), next to the host restatements
+    if rank == 0 and world == 1:
+        try:
+            others["seq_preprocess_1m"] = run_preprocess(local)
+        except Exception as ex:
+            others["seq_preprocess_1m"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
 
     if rank != 0:
         if world > 1:

@@ -201,6 +201,21 @@ int osrl_seq_buffer_upload(osrl_engine* e, const osrl_seq_dataset_view* view);
 int osrl_seq_gather(osrl_engine* e, const int32_t* traj_idx, const int32_t* start_idx, int n, osrl_seq_batch* out,
                     void* stream);
 int osrl_seq_alias_table(osrl_engine* e, float* prob_out, int32_t* alias_out, int cap);
+/* Replaces process_sequence_dataset (dataset.py:137-183: a Python loop over every transition) and its two
+ * discounted_cumsum calls (dataset.py:19-27, gamma = 1) on the device: `flat` is the raw DSRL dictionary (observations,
+ * actions, rewards, costs, terminals and/or timeouts; next_observations / done / is_init ignored).  Episodes end where
+ * terminals | timeouts is set, a trailing unfinished episode is dropped (as the reference does); reward-to-go and
+ * cost-to-go are summed per episode backwards with one fp32 add per step -- the reference's order, bit-identical --
+ * and the packed trajectory buffer osrl_seq_gather / osrl_steps read is left resident with a uniform episode
+ * distribution.  cost_reverse: costs become 1 - cost (dataset.py:164-165).  reward_scale / cost_scale of the view are
+ * applied to the stored returns as osrl_seq_buffer_upload does (dataset.py:762-763).
+ * osrl_seq_episode_info: per-episode UNSCALED first return / cost return and the episode offsets [n_traj + 1] -- what
+ * the caller needs for cost_sample / pf_sample (dataset.py:439-459, 390-430); any pointer may be NULL.
+ * osrl_seq_set_sample_prob: Categorical over the episodes (normalised here; NULL = uniform). */
+int osrl_seq_preprocess(osrl_engine* e, const osrl_dataset_view* flat, int cost_reverse, int64_t* n_traj_out,
+                        int64_t* n_used_out);
+int osrl_seq_episode_info(osrl_engine* e, float* first_return, float* first_cost_return, int64_t* offsets, int cap);
+int osrl_seq_set_sample_prob(osrl_engine* e, const double* prob, int n);
 int osrl_last_sequences(osrl_engine* e, int32_t* traj_out, int32_t* start_out, int cap);
 
 /* Replaces <Algo>Trainer.train_one_step (bc.py:103-109, bcql.py:283-306, cpq.py:294-313,

@@ -287,15 +287,17 @@ def discounted_cumsum(x: np.ndarray, gamma: float) -> np.ndarray:
     return out
 
 
-def split_trajectories(dataset: dict):
-    """process_sequence_dataset (dataset.py:137-183) without cost_reverse: list of per-episode dicts with
-    returns / cost_returns (undiscounted suffix sums)."""
+def split_trajectories(dataset: dict, cost_reverse: bool = False):
+    """process_sequence_dataset (dataset.py:137-183): list of per-episode dicts with returns / cost_returns
+    (undiscounted suffix sums); cost_reverse: costs become 1.0 - cost (:164-165)."""
     trajs, start = [], 0
     n = dataset["rewards"].shape[0]
     for i in range(n):
         if dataset["terminals"][i] or dataset["timeouts"][i]:   # a trailing unfinished episode is dropped (:160)
             sl = slice(start, i + 1)
             ep = {k: np.asarray(dataset[k][sl], dtype=np.float32) for k in ("observations", "actions", "rewards", "costs")}
+            if cost_reverse:
+                ep["costs"] = np.array([1.0 - c for c in dataset["costs"][sl]], dtype=np.float32)
             ep["returns"] = discounted_cumsum(ep["rewards"], 1.0)
             ep["cost_returns"] = discounted_cumsum(ep["costs"], 1.0)
             trajs.append(ep)

@@ -96,6 +96,9 @@ SYMBOLS = [
     ("osrl_seq_buffer_upload", C.c_int, [C.c_void_p, C.POINTER(SeqDatasetView)]),
     ("osrl_seq_gather", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(SeqBatch), C.c_void_p]),
     ("osrl_seq_alias_table", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    ("osrl_seq_preprocess", C.c_int, [C.c_void_p, C.POINTER(DatasetView), C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    ("osrl_seq_episode_info", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    ("osrl_seq_set_sample_prob", C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     ("osrl_last_sequences", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     ("osrl_steps", C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     ("osrl_steps_host", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_int, C.c_void_p, C.c_void_p]),

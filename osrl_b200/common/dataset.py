@@ -316,6 +316,21 @@ class SequenceDataset(IterableDataset):
                 "costs": cat([self._cost[lo:hi] for lo, hi, _, _ in self._traj]),
                 "returns": cat([r for _, _, r, _ in self._traj]), "cost_returns": cat([c for _, _, _, c in self._traj])}
 
+    @staticmethod
+    def device_resident(engine, dataset: dict, reward_scale: float = 1.0, cost_scale: float = 1.0,
+                        cost_reverse: bool = False, cost_sample: bool = False, cost_transform=lambda x: 50 - x) -> dict:
+        """The un-augmented SequenceDataset built entirely on the GPU (osrl_seq_preprocess): the episode split and the
+        two discounted_cumsum passes of process_sequence_dataset (dataset.py:137-183) run as kernels on the raw DSRL
+        arrays and leave the packed trajectory buffer resident; only the per-episode first returns come back, for the
+        cost-based episode distribution (dataset.py:452-459).  Augmentation / Pareto sampling need the host class."""
+        info = engine.preprocess_seq_dataset(dataset, reward_scale, cost_scale, cost_reverse)
+        if cost_sample:
+            p = np.array([cost_transform(c) for c in info["cost_returns"]])
+            p[p < 0] = 0
+            engine.set_seq_sample_prob(p / np.sum(p))
+            info["sample_prob"] = p / np.sum(p)
+        return info
+
     def to_engine(self, engine) -> None:
         """Pack into HBM once (osrl_seq_buffer_upload); windows are then drawn on the device."""
         if self.start_sampling:

@@ -5,6 +5,7 @@
 #include "gemm_thin.cuh"
 #include "gemm_fz.cuh"
 #include "cdt_kernels.cuh"
+#include "preproc_kernels.cuh"
 
 #include <dlfcn.h>
 
@@ -1493,8 +1494,10 @@ int osrl_seq_buffer_upload(osrl_engine* h, const osrl_seq_dataset_view* v) {
   if (e.sq_rows) {
     OSRL_CUDA(cudaDeviceSynchronize());
     drop_sampled_graphs(e);
-    for (void* q : {(void*)e.sq_rows, (void*)e.sq_off, (void*)e.sq_prob, (void*)e.sq_alias}) release_alloc(e, q);
-    e.sq_rows = nullptr;
+    for (void* q : {(void*)e.sq_rows, (void*)e.sq_off, (void*)e.sq_prob, (void*)e.sq_alias, (void*)e.sq_first_ret,
+                    (void*)e.sq_first_cret})
+      release_alloc(e, q);
+    e.sq_rows = nullptr; e.sq_first_ret = e.sq_first_cret = nullptr;
   }
   e.sq_rows = e.upload(packed);
   e.sq_off = e.upload(off);
@@ -1504,6 +1507,132 @@ int osrl_seq_buffer_upload(osrl_engine* h, const osrl_seq_dataset_view* v) {
   e.sq_stride = stride;
   e.ds_rows = e.sq_rows;  // marks "a resident dataset exists" for osrl_steps
   drop_sampled_graphs(e);
+  OSRL_CATCH
+}
+
+// ---- trajectory preprocessing on the device (preproc_kernels.cuh)
+static void seq_install_prob(Engine& e, const double* prob, int n) {
+  std::vector<double> p(n, 1.0 / n);
+  if (prob) {
+    double tot = 0;
+    for (int i = 0; i < n; ++i) { OSRL_REQUIRE(prob[i] >= 0, "negative sample_prob"); tot += prob[i]; }
+    OSRL_REQUIRE(tot > 0, "sample_prob sums to zero");
+    for (int i = 0; i < n; ++i) p[i] = prob[i] / tot;
+  }
+  std::vector<float> pr;
+  std::vector<int> alias;
+  build_alias(p, pr, alias);
+  if (e.sq_prob) { release_alloc(e, e.sq_prob); release_alloc(e, e.sq_alias); }
+  e.sq_prob = e.upload(pr);
+  e.sq_alias = e.upload(alias);
+}
+
+int osrl_seq_preprocess(osrl_engine* h, const osrl_dataset_view* v, int cost_reverse, int64_t* n_traj_out,
+                        int64_t* n_used_out) {
+  OSRL_TRY
+  OSRL_REQUIRE(h && v && n_traj_out, "null argument");
+  Engine& e = *h->e;
+  OSRL_REQUIRE(e.plan.cfg.algo == OSRL_ALGO_CDT, "trajectory buffers belong to CDT engines");
+  OSRL_REQUIRE(v->n > 0 && v->observations && v->actions && v->rewards && v->costs && (v->terminals || v->timeouts),
+               "flat dataset view incomplete (observations, actions, rewards, costs, terminals / timeouts)");
+  OSRL_CUDA(cudaSetDevice(e.device));
+  OSRL_CUDA(cudaDeviceSynchronize());
+  const int o = e.plan.cfg.obs_dim, a = e.plan.cfg.act_dim;
+  const int stride = (o + a + 3 + 3) / 4 * 4;
+  const long long n = v->n;
+  // staging copies of the flat arrays (freed before returning)
+  std::vector<void*> tmp;
+  auto stage = [&](const void* src, size_t bytes) -> void* {
+    if (!src) return nullptr;
+    void* d = nullptr;
+    OSRL_CUDA(cudaMalloc(&d, bytes));
+    tmp.push_back(d);
+    OSRL_CUDA(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+    return d;
+  };
+  struct Cleanup { std::vector<void*>& t; ~Cleanup() { for (void* q : t) cudaFree(q); } } cleanup{tmp};
+  const float* d_obs = (const float*)stage(v->observations, (size_t)n * o * sizeof(float));
+  const float* d_act = (const float*)stage(v->actions, (size_t)n * a * sizeof(float));
+  const float* d_rew = (const float*)stage(v->rewards, (size_t)n * sizeof(float));
+  const float* d_cost = (const float*)stage(v->costs, (size_t)n * sizeof(float));
+  const uint8_t* d_term = (const uint8_t*)stage(v->terminals, (size_t)n);
+  const uint8_t* d_tout = (const uint8_t*)stage(v->timeouts, (size_t)n);
+  long long* d_off = nullptr;
+  OSRL_CUDA(cudaMalloc((void**)&d_off, (size_t)(n + 1) * sizeof(long long)));
+  tmp.push_back(d_off);
+  EpisodeCount* d_cnt = nullptr;
+  OSRL_CUDA(cudaMalloc((void**)&d_cnt, sizeof(EpisodeCount)));
+  tmp.push_back(d_cnt);
+  k_episode_offsets<<<1, 1024>>>(d_term, d_tout, n, d_off, d_cnt);
+  k_episode_finish<<<1, 1>>>(d_off, d_cnt);
+  e.launches += 2;
+  EpisodeCount cnt;
+  OSRL_CUDA(cudaMemcpy(&cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost));
+  OSRL_REQUIRE(cnt.n_traj > 0, "no finished episode in the dataset (terminals | timeouts never set)");
+  OSRL_REQUIRE(cnt.n_traj < (1ll << 31), "too many episodes");
+  // the resident buffer
+  if (e.sq_rows) {
+    drop_sampled_graphs(e);
+    for (void* q : {(void*)e.sq_rows, (void*)e.sq_off, (void*)e.sq_prob, (void*)e.sq_alias, (void*)e.sq_first_ret,
+                    (void*)e.sq_first_cret})
+      release_alloc(e, q);
+    e.sq_rows = nullptr; e.sq_prob = nullptr; e.sq_alias = nullptr; e.sq_first_ret = e.sq_first_cret = nullptr;
+  }
+  void* rows = nullptr;
+  OSRL_CUDA(cudaMalloc(&rows, (size_t)cnt.n_used * stride * sizeof(float)));
+  e.allocs.push_back(rows);
+  void* off = nullptr;
+  OSRL_CUDA(cudaMalloc(&off, (size_t)(cnt.n_traj + 1) * sizeof(long long)));
+  e.allocs.push_back(off);
+  OSRL_CUDA(cudaMemcpy(off, d_off, (size_t)(cnt.n_traj + 1) * sizeof(long long), cudaMemcpyDeviceToDevice));
+  e.sq_first_ret = e.ws((size_t)cnt.n_traj);
+  e.sq_first_cret = e.ws((size_t)cnt.n_traj);
+  k_seq_pack<<<148 * 8, 256>>>(d_obs, d_act, d_cost, cnt.n_used, o, a, stride, cost_reverse ? 1 : 0, (float*)rows);
+  k_episode_suffix<<<(unsigned)((cnt.n_traj + 127) / 128), 128>>>(d_rew, (const long long*)off, cnt.n_traj, o, a, stride,
+                                                                  v->reward_scale, v->cost_scale, (float*)rows,
+                                                                  e.sq_first_ret, e.sq_first_cret);
+  e.launches += 2;
+  OSRL_CUDA(cudaGetLastError());
+  OSRL_CUDA(cudaDeviceSynchronize());
+  e.sq_rows = (float*)rows;
+  e.sq_off = (long long*)off;
+  e.sq_ntraj = (int)cnt.n_traj;
+  e.sq_stride = stride;
+  seq_install_prob(e, nullptr, e.sq_ntraj);   // uniform until osrl_seq_set_sample_prob
+  e.ds_rows = e.sq_rows;
+  drop_sampled_graphs(e);
+  *n_traj_out = cnt.n_traj;
+  if (n_used_out) *n_used_out = cnt.n_used;
+  OSRL_CATCH
+}
+
+int osrl_seq_episode_info(osrl_engine* h, float* first_return, float* first_cost_return, int64_t* offsets, int cap) {
+  OSRL_TRY
+  OSRL_REQUIRE(h, "null argument");
+  Engine& e = *h->e;
+  OSRL_REQUIRE(e.sq_rows && e.sq_first_ret, "no preprocessed trajectory buffer (osrl_seq_preprocess)");
+  OSRL_REQUIRE(cap >= e.sq_ntraj, "buffers too small");
+  OSRL_CUDA(cudaSetDevice(e.device));
+  if (first_return) OSRL_CUDA(cudaMemcpy(first_return, e.sq_first_ret, e.sq_ntraj * sizeof(float), cudaMemcpyDeviceToHost));
+  if (first_cost_return)
+    OSRL_CUDA(cudaMemcpy(first_cost_return, e.sq_first_cret, e.sq_ntraj * sizeof(float), cudaMemcpyDeviceToHost));
+  if (offsets) {
+    static_assert(sizeof(long long) == sizeof(int64_t), "offset width");
+    OSRL_CUDA(cudaMemcpy(offsets, e.sq_off, (size_t)(e.sq_ntraj + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  }
+  OSRL_CATCH
+}
+
+int osrl_seq_set_sample_prob(osrl_engine* h, const double* prob, int n) {
+  OSRL_TRY
+  OSRL_REQUIRE(h, "null argument");
+  Engine& e = *h->e;
+  OSRL_REQUIRE(e.sq_rows, "no trajectory buffer");
+  OSRL_REQUIRE(!prob || n == e.sq_ntraj, "sample_prob length != number of trajectories");
+  OSRL_CUDA(cudaSetDevice(e.device));
+  OSRL_CUDA(cudaDeviceSynchronize());
+  drop_sampled_graphs(e);
+  seq_install_prob(e, prob, e.sq_ntraj);
   OSRL_CATCH
 }
 

@@ -158,6 +158,7 @@ struct Engine {
   float* sq_prob = nullptr;
   int* sq_alias = nullptr;
   int sq_ntraj = 0, sq_stride = 0;
+  float *sq_first_ret = nullptr, *sq_first_cret = nullptr;   // osrl_seq_preprocess: unscaled return / cost return of each episode
   int *s_traj = nullptr, *s_start = nullptr;
   // noise slots
   std::vector<float*> noise_buf;

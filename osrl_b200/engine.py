@@ -256,6 +256,35 @@ class Engine:
         check(self.lib.osrl_seq_buffer_upload(self.h, C.byref(v)))
         self.n_traj = int(v.n_traj)
 
+    def preprocess_seq_dataset(self, data: dict, reward_scale: float = 1.0, cost_scale: float = 1.0,
+                               cost_reverse: bool = False) -> Dict[str, np.ndarray]:
+        """process_sequence_dataset (dataset.py:137-183) on the device -> the resident trajectory buffer
+        (osrl_seq_preprocess).  `data` is the raw DSRL dictionary.  Returns the per-episode info the sampling options
+        need: {"returns", "cost_returns"} = unscaled first return / cost return of each episode, "traj_offsets"."""
+        keep = {k: np.ascontiguousarray(data[k], dtype=np.float32) for k in ("observations", "actions", "rewards", "costs")}
+        keep["terminals"] = np.ascontiguousarray(data["terminals"]).astype(np.uint8)
+        keep["timeouts"] = np.ascontiguousarray(data["timeouts"]).astype(np.uint8)
+        v = DatasetView()
+        v.n = keep["observations"].shape[0]
+        for k, a in keep.items():
+            setattr(v, k, a.ctypes.data)
+        v.reward_scale, v.cost_scale = float(reward_scale), float(cost_scale)
+        nt, nu = C.c_int64(), C.c_int64()
+        check(self.lib.osrl_seq_preprocess(self.h, C.byref(v), int(bool(cost_reverse)), C.byref(nt), C.byref(nu)))
+        self.n_traj = int(nt.value)
+        r, c = np.empty(self.n_traj, np.float32), np.empty(self.n_traj, np.float32)
+        off = np.empty(self.n_traj + 1, np.int64)
+        check(self.lib.osrl_seq_episode_info(self.h, r.ctypes.data, c.ctypes.data, off.ctypes.data, self.n_traj))
+        return {"returns": r, "cost_returns": c, "traj_offsets": off, "n_used": int(nu.value)}
+
+    def set_seq_sample_prob(self, prob) -> None:
+        """Categorical over the resident episodes (cost_sample / pf_sample, dataset.py:439-459); None = uniform."""
+        if prob is None:
+            check(self.lib.osrl_seq_set_sample_prob(self.h, None, 0))
+            return
+        p = np.ascontiguousarray(prob, dtype=np.float64)
+        check(self.lib.osrl_seq_set_sample_prob(self.h, p.ctypes.data, p.shape[0]))
+
     def seq_gather(self, traj_idx, start_idx) -> Dict[str, torch.Tensor]:
         """[n, T, .] windows for explicit (trajectory, start) pairs -> CUDA tensors (bit-exact copies)."""
         ti = np.ascontiguousarray(traj_idx, dtype=np.int32)

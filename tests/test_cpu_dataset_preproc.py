@@ -106,3 +106,21 @@ def test_sequence_dataset_modes(ref_dataset, case):
     for x, y in zip(ra, ma):
         for u, v in zip(x, y):
             assert np.asarray(u).dtype == np.asarray(v).dtype and np.allclose(u, v, rtol=2e-6, atol=1e-5), case
+
+
+@pytest.mark.parametrize("cost_reverse", [False, True])
+def test_oracle_split_trajectories_is_the_reference(ref_dataset, cost_reverse):
+    """oracle/cdt.py: split_trajectories -- the checker of the device preprocessing (tests/test_gpu_preproc.py) --
+    against the unmodified process_sequence_dataset (dataset.py:137-183), bit for bit, with fractional costs, a
+    trailing unfinished episode and both end flags."""
+    from oracle import cdt as ocdt
+    d = _data(seed=9, eps=40, T=23)
+    rng = np.random.default_rng(2)
+    d["costs"] = np.where(rng.random(d["costs"].shape) < 0.5, d["costs"], rng.random(d["costs"].shape)).astype(np.float32)
+    d["terminals"][40] = True
+    want, _ = ref_dataset.process_sequence_dataset({k: v.copy() for k, v in d.items()}, cost_reverse)
+    got = ocdt.split_trajectories(d, cost_reverse)
+    assert len(want) == len(got)
+    for w, g in zip(want, got):
+        for k in ("observations", "actions", "rewards", "costs", "returns", "cost_returns"):
+            assert w[k].dtype == g[k].dtype and np.array_equal(w[k], g[k]), k
