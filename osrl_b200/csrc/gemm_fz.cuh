@@ -305,6 +305,28 @@ __global__ void __launch_bounds__(THREADS, 1) k_fz(const __grid_constant__ FzPac
     const int gk = t.gk;
     float* xs = gen_s;
     // ------------------------------------------------ tables: generation weights, reduce weights
+    // The input rows and the reduce weights are requested first and stored last, so that their L2 round trips overlap
+    // the weight table's instead of following it (three dependent global latencies were 4-7k cycles before slab 0).
+    float xpre[GK_MAX];
+    float rpre[(RED_MAX * BN + CONV - 1) / CONV];
+    if constexpr (GEN) {
+      if (tid >= CONV - BM) {   // (the last four warps: the first ones are busy with the weight table)
+        const int r = tid - (CONV - BM);
+        const bool ok = m0 + r < M;
+        const float* __restrict__ src = t.gx + (size_t)(m0 + (ok ? r : 0)) * t.ldgx;
+#pragma unroll
+        for (int i = 0; i < GK_MAX; ++i) xpre[i] = (i < gk && ok) ? src[i] : 0.f;
+      }
+    }
+    if constexpr (RED) {
+      const float* __restrict__ rw = t.rw;
+#pragma unroll
+      for (int u = 0; u < (RED_MAX * BN + CONV - 1) / CONV; ++u) {
+        const int e = tid + u * CONV;
+        const int j = e / BN, n = e - j * BN;
+        rpre[u] = (e < t.red_n * BN && n0 + n < N) ? rw[(size_t)j * t.rs_j + (size_t)(n0 + n) * t.rs_n] : 0.f;
+      }
+    }
     if constexpr (ASRC == A_FIRST) {        // W1^T [gk][kpad] then b1 [kpad], zero padded
       const float* __restrict__ gw = t.gw;
       const int gwld = t.gw_ld;
@@ -327,23 +349,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_fz(const __grid_constant__ FzPac
     }
     if constexpr (GEN) {
       xs = gen_s + (gk + 1) * kpad;
-      if (tid >= CONV - BM) {   // (the last four warps: the first ones are busy with the weight table)
+      if (tid >= CONV - BM) {
         const int r = tid - (CONV - BM);
-        const bool ok = m0 + r < M;
-        const float* __restrict__ src = t.gx + (size_t)(m0 + (ok ? r : 0)) * t.ldgx;
-        float x[GK_MAX];
-#pragma unroll
-        for (int i = 0; i < GK_MAX; ++i) x[i] = (i < gk && ok) ? src[i] : 0.f;
 #pragma unroll
         for (int i = 0; i < GK_MAX; ++i)
-          if (i < gk) xs[r * XS_LD + i] = x[i];
+          if (i < gk) xs[r * XS_LD + i] = xpre[i];
       }
     }
     if constexpr (RED) {
-      const float* __restrict__ rw = t.rw;
-      for (int e = tid; e < t.red_n * BN; e += CONV) {
-        const int j = e / BN, n = e - j * BN;
-        rws[e] = (n0 + n < N) ? rw[(size_t)j * t.rs_j + (size_t)(n0 + n) * t.rs_n] : 0.f;
+#pragma unroll
+      for (int u = 0; u < (RED_MAX * BN + CONV - 1) / CONV; ++u) {
+        const int e = tid + u * CONV;
+        if (e < t.red_n * BN) rws[e] = rpre[u];
       }
     }
     // A operand: thread = (row = this warp's TMEM lane quarter * 32 + lane, k-quarter of the 32-float slab)
@@ -391,18 +408,42 @@ __global__ void __launch_bounds__(THREADS, 1) k_fz(const __grid_constant__ FzPac
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             const float4 b = *reinterpret_cast<const float4*>(bp + 4 * q);
-            g[q].x = apply_act(g[q].x + b.x, ga); g[q].y = apply_act(g[q].y + b.y, ga);
-            g[q].z = apply_act(g[q].z + b.z, ga); g[q].w = apply_act(g[q].w + b.w, ga);
-            if (k0 + kq * 8 + 4 * q >= K) g[q] = make_float4(0.f, 0.f, 0.f, 0.f);   // k padding (K % 4 == 0)
+            g[q].x += b.x; g[q].y += b.y; g[q].z += b.z; g[q].w += b.w;
           }
+          // one warp-uniform branch per slab instead of a per-element select: inlined per element the compiler
+          // if-converts apply_act and every ReLU network pays for 8 tanh evaluations (~200 instructions) per slab
+          if (ga == ACT_RELU) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              g[q].x = fmaxf(g[q].x, 0.f); g[q].y = fmaxf(g[q].y, 0.f); g[q].z = fmaxf(g[q].z, 0.f); g[q].w = fmaxf(g[q].w, 0.f);
+            }
+          } else if (ga == ACT_TANH) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) { g[q].x = tanhf(g[q].x); g[q].y = tanhf(g[q].y); g[q].z = tanhf(g[q].z); g[q].w = tanhf(g[q].w); }
+          }
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+            if (k0 + kq * 8 + 4 * q >= K) g[q] = make_float4(0.f, 0.f, 0.f, 0.f);   // k padding (K % 4 == 0)
         } else {
+          float4 hq[2];
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             const int k = k0 + kq * 8 + 4 * q;
-            float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rowok && k < K) h = lds128(ra + (row * RAW_KC_LD + kq * 8 + 4 * q) * 4);
-            g[q].x = dact_mul(g[q].x, h.x, ga); g[q].y = dact_mul(g[q].y, h.y, ga);
-            g[q].z = dact_mul(g[q].z, h.z, ga); g[q].w = dact_mul(g[q].w, h.w, ga);
+            hq[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rowok && k < K) hq[q] = lds128(ra + (row * RAW_KC_LD + kq * 8 + 4 * q) * 4);
+          }
+          if (ga == ACT_RELU) {          // (uniform branch, see above)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              g[q].x = hq[q].x > 0.f ? g[q].x : 0.f; g[q].y = hq[q].y > 0.f ? g[q].y : 0.f;
+              g[q].z = hq[q].z > 0.f ? g[q].z : 0.f; g[q].w = hq[q].w > 0.f ? g[q].w : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              g[q].x = dact_mul(g[q].x, hq[q].x, ga); g[q].y = dact_mul(g[q].y, hq[q].y, ga);
+              g[q].z = dact_mul(g[q].z, hq[q].z, ga); g[q].w = dact_mul(g[q].w, hq[q].w, ga);
+            }
           }
         }
         if (gstore && rowok) {
@@ -649,9 +690,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_fz(const __grid_constant__ FzPac
         for (int e = tid; e < BM * rn; e += CONV) {
           const int rr = e / rn, j = e - rr * rn, g = m0 + rr;
           if (g >= M) break;
+          // all partials of this output in flight at once, then summed in slot order (a load -> add loop over a
+          // run-time trip count serialises `slots` L2 round trips: 5k of this phase's 7-13k cycles)
+          const float rb = t.rbias ? t.rbias[j] : 0.f;
           float v = 0.f;
-          for (int s = 0; s < slots; ++s) v += __ldcg(rp + ((size_t)s * M + g) * rn + j);
-          if (t.rbias) v += t.rbias[j];
+          for (int s0 = 0; s0 < slots; s0 += 16) {
+            float pv[16];
+#pragma unroll
+            for (int s = 0; s < 16; ++s) pv[s] = s0 + s < slots ? __ldcg(rp + ((size_t)(s0 + s) * M + g) * rn + j) : 0.f;
+#pragma unroll
+            for (int s = 0; s < 16; ++s)
+              if (s0 + s < slots) v += pv[s];
+          }
+          v += rb;
           v = apply_act(v, ract);
           if (t.raux) t.raux[(size_t)g * t.ldraux + j] = v;
           v *= rscale;
