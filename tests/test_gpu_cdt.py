@@ -88,7 +88,9 @@ def test_cdt_against_live_oracle(lib_built, case, gemm):
     eng.load_params(orc.params)
     rng = np.random.default_rng(77)
     strict = total = 0
-    max_frac, cap = (0.05, 1e-2) if gemm == "ffma" else (0.2, 2e-1)
+    # measured on B200 (profiles/r02_parity_margins.json): 239 gradient tensors per GEMM mode, worst max-rel 4.8e-6
+    # (fused tcgen05 path), no tensor above the 2e-5 bound -> at most one outlier per step, and then below 1e-4
+    max_frac, cap = 0.02, 1e-4
     for s in range(steps):
         b = make_seq_batch(rng, B, cfg.seq_len, cfg.state_dim, cfg.action_dim)
         o64 = _to_double(orc)
@@ -335,11 +337,11 @@ def test_cdt_b2048_fixture_and_split_k(lib_built):
             if float(g.abs().max()) == 0.0 or "in_proj_bias" in k:
                 continue
             err = maxrel(G[k], g)
-            record_margin("cdt_b2048", "grad (max-rel)", err, 1e-4)
-            if err > 1e-4:      # 81,920-term fp32 reductions in a different order than torch's
+            record_margin("cdt_b2048", "grad (max-rel)", err, 2e-5)
+            if err > 2e-5:      # 81,920-term fp32 reductions in a different order than torch's: measured worst 4.2e-6
                 bad.append((k, err))
-                assert err <= 2e-2, f"step {s} grad {k}: {err:.2e}"
-        assert len(bad) <= max(1, int(0.1 * len(orc.last_grads))), bad[:6]
+                assert err <= 1e-4, f"step {s} grad {k}: {err:.2e}"
+        assert len(bad) <= 1, bad[:6]
         eng2.step_seq(b, masks)
         G2 = eng2.read_section("grad")
         worst = max(maxrel(G2[k], G[k]) for k in G if float(G[k].abs().max()) > 0)
