@@ -60,8 +60,10 @@ void build_cdt(Engine& e) {
   OSRL_REQUIRE(E == 32 || E == 64 || E == 128 || E == 256 || E == 512, "embedding_dim must be 32/64/128/256/512");
   const int attn_threads = (H * Lq + 31) / 32 * 32;
   OSRL_REQUIRE(attn_threads <= 1024, "num_heads * 4 * seq_len must be <= 1024");
-  const int smem_fwd = 2 * Lq * E * (int)sizeof(float);
-  const int smem_bwd = (4 * Lq * E + 2 * H * Lq) * (int)sizeof(float);
+  // + key validity [Lq] and, with attention dropout, this batch element's multipliers [H][Lq][Lq + 1]
+  const int attn_extra = ((Lq + 3) & ~3) + (c.attention_dropout > 0.f ? H * Lq * (Lq + 1) : 0);
+  const int smem_fwd = (2 * Lq * E + attn_extra) * (int)sizeof(float);
+  const int smem_bwd = (4 * Lq * E + 2 * H * Lq + attn_extra) * (int)sizeof(float);
   OSRL_REQUIRE(smem_bwd <= 227 * 1024, "sequence too long for the single-CTA attention kernel");
   if (D == 8) set_attn_attr<8>(smem_bwd);
   else if (D == 16) set_attn_attr<16>(smem_bwd);

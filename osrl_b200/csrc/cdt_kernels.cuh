@@ -166,6 +166,24 @@ static __global__ void k_mul_mask(const float* in, const float* __restrict__ mul
 // qkv [B, L, 3E] (q | k | v, head h at columns h*D..), key j is attendable by query i iff j <= i and
 // the step of token j is valid (key_padding_mask = ~mask repeated over the 4 tokens of a step, cdt.py:203-205).
 // One CTA per batch element, one thread per (head, query/key row).
+// [H][L][L] dropout multipliers of one batch element -> shared [H][L][L + 1] (the pad makes both access patterns of
+// the kernels -- lanes over query rows, lanes over key columns -- conflict free); 16-byte coalesced global loads
+__device__ __forceinline__ void attn_stage_drop(const float* __restrict__ src, int H, int L, float* __restrict__ Pd) {
+  const int n = H * L * L;
+  if ((L & 3) == 0) {
+    for (int e4 = threadIdx.x; e4 < n / 4; e4 += blockDim.x) {
+      const float4 v = reinterpret_cast<const float4*>(src)[e4];
+      const int e = e4 * 4, row = e / L, j = e - row * L;
+      float* d = Pd + (size_t)row * (L + 1) + j;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+  } else {
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      const int row = e / L, j = e - row * L;
+      Pd[(size_t)row * (L + 1) + j] = src[e];
+    }
+  }
+}
 template <int D>
 // pdrop (optional) [B, H, L, L]: dropout multipliers of the attention weights (nn.MultiheadAttention dropout):
 // O = (softmax(S) * pdrop) V -- the normaliser is the un-dropped sum, so lse is unchanged.
@@ -176,12 +194,18 @@ static __global__ void k_attn_fwd(const float* __restrict__ qkv, const float* __
   const int E = H * D, b = blockIdx.x, T = L / tok_per_step;
   float* Ks = sm;              // [L][E]
   float* Vs = sm + L * E;      // [L][E]
+  float* valid = sm + 2 * L * E;            // [L] key j attendable
+  float* Pd = valid + ((L + 3) & ~3);       // [H][L][L + 1] dropout multipliers of this batch element (pdrop only)
   const float* base = qkv + (size_t)b * L * 3 * E;
   for (int e4 = threadIdx.x; e4 < L * E / 4; e4 += blockDim.x) {
     const int e = e4 * 4, j = e / E, c = e % E;
     *reinterpret_cast<float4*>(Ks + e) = *reinterpret_cast<const float4*>(base + (size_t)j * 3 * E + E + c);
     *reinterpret_cast<float4*>(Vs + e) = *reinterpret_cast<const float4*>(base + (size_t)j * 3 * E + 2 * E + c);
   }
+  // the key-padding mask and the dropout multipliers are read in every iteration of the inner loop: from global
+  // memory (one 4-byte load per lane, strided by L) they bound the kernel at one CTA per SM
+  for (int j = threadIdx.x; j < L; j += blockDim.x) valid[j] = mask[(size_t)b * T + j / tok_per_step];
+  if (pdrop) attn_stage_drop(pdrop + (size_t)b * H * L * L, H, L, Pd);
   __syncthreads();
   const int h = threadIdx.x / L, i = threadIdx.x % L;
   if (h >= H) return;
@@ -189,10 +213,10 @@ static __global__ void k_attn_fwd(const float* __restrict__ qkv, const float* __
 #pragma unroll
   for (int c = 0; c < D; ++c) { q[c] = base[(size_t)i * 3 * E + h * D + c]; acc[c] = 0.f; }
   const float scale = rsqrtf((float)D);
-  const float* __restrict__ drow = pdrop ? pdrop + (((size_t)b * H + h) * L + i) * L : nullptr;
+  const float* __restrict__ drow = pdrop ? Pd + (size_t)(h * L + i) * (L + 1) : nullptr;
   float m = -INFINITY, l = 0.f;
   for (int j = 0; j <= i; ++j) {
-    if (mask[(size_t)b * T + j / tok_per_step] <= 0.f) continue;
+    if (valid[j] <= 0.f) continue;
     float kj[D], vj[D];
     {
       const float4* __restrict__ kp = reinterpret_cast<const float4*>(Ks + j * E + h * D);
@@ -246,7 +270,11 @@ static __global__ void k_attn_bwd(const float* __restrict__ qkv, const float* __
   float* dOs = sm + 3 * L * E;
   float* Ls = sm + 4 * L * E;      // [H*L] log-sum-exp
   float* Ds = Ls + H * L;          // [H*L] rowsum(dO * O)
+  float* valid = Ds + H * L;                // [L] key j attendable
+  float* Pd = valid + ((L + 3) & ~3);       // [H][L][L + 1] dropout multipliers (pdrop only), see k_attn_fwd
   const float* base = qkv + (size_t)b * L * 3 * E;
+  for (int j = threadIdx.x; j < L; j += blockDim.x) valid[j] = mask[(size_t)b * T + j / tok_per_step];
+  if (pdrop) attn_stage_drop(pdrop + (size_t)b * H * L * L, H, L, Pd);
   for (int e4 = threadIdx.x; e4 < L * E / 4; e4 += blockDim.x) {   // 16-byte global loads / shared stores
     const int e = e4 * 4, j = e / E, c = e % E;
     *reinterpret_cast<float4*>(Qs + e) = *reinterpret_cast<const float4*>(base + (size_t)j * 3 * E + c);
@@ -278,9 +306,10 @@ static __global__ void k_attn_bwd(const float* __restrict__ qkv, const float* __
 #pragma unroll
     for (int c = 0; c < D; ++c) dq[c] = 0.f;
     const float li = Ls[h * L + i], di = Ds[h * L + i];
-    const float* __restrict__ dmat = pdrop ? pdrop + ((size_t)b * H + h) * L * L : nullptr;   // [L][L] of this head
+    const int LP = L + 1;
+    const float* __restrict__ dmat = pdrop ? Pd + (size_t)h * L * LP : nullptr;   // [L][L + 1] of this head (shared)
     for (int j = 0; j <= i; ++j) {
-      if (mask[(size_t)b * T + j / tok_per_step] <= 0.f) continue;
+      if (valid[j] <= 0.f) continue;
       float kj[D], vj[D];
       ld_row<D>(Ks, j, E, h, kj);
       ld_row<D>(Vs, j, E, h, vj);
@@ -291,7 +320,7 @@ static __global__ void k_attn_bwd(const float* __restrict__ qkv, const float* __
         dp = fmaf(doi[c], vj[c], dp);
       }
       const float p = expf(s * scale - li);
-      if (dmat) dp *= dmat[i * L + j];   // d softmax = (dO V^T) * dropout multiplier; rowsum(dP * P) is still dO.O
+      if (dmat) dp *= dmat[i * LP + j];  // d softmax = (dO V^T) * dropout multiplier; rowsum(dP * P) is still dO.O
       const float ds = p * (dp - di) * scale;
 #pragma unroll
       for (int c = 0; c < D; ++c) dq[c] = fmaf(ds, kj[c], dq[c]);
@@ -304,8 +333,13 @@ static __global__ void k_attn_bwd(const float* __restrict__ qkv, const float* __
     float dk[D], dv[D];
 #pragma unroll
     for (int c = 0; c < D; ++c) { dk[c] = 0.f; dv[c] = 0.f; }
-    if (mask[(size_t)b * T + j / tok_per_step] > 0.f) {
-      for (int r = j; r < L; ++r) {
+    if (valid[j] > 0.f) {
+      // every lane walks the SAME query row r in the same iteration (rows above the lane's key are skipped by a
+      // predicate, not by a later loop start): the row loads are then warp broadcasts.  Starting each lane at its own
+      // r = j made the lanes of a warp read 32 different rows, 128 floats apart -- all in the same banks (ncu: 101 M
+      // bank conflicts on 16.9 M shared loads, the kernel's whole run time).
+      for (int r = 0; r < L; ++r) {
+        if (r < j) continue;
         float qr[D], dor[D];
         ld_row<D>(Qs, r, E, h, qr);
         ld_row<D>(dOs, r, E, h, dor);
@@ -316,7 +350,7 @@ static __global__ void k_attn_bwd(const float* __restrict__ qkv, const float* __
           dp = fmaf(dor[c], vi[c], dp);
         }
         const float p = expf(s * scale - Ls[h * L + r]);
-        const float mrj = dmat ? dmat[r * L + j] : 1.f;
+        const float mrj = dmat ? dmat[r * LP + j] : 1.f;
         const float ds = p * (dp * mrj - Ds[h * L + r]) * scale;
         const float pv = p * mrj;
 #pragma unroll
