@@ -48,7 +48,7 @@ static void emit_ln_bwd(Engine& e, Program& p, const float* dy, const float* x, 
     }
     ep->launches++;
   });
-  KOP(p, e, 0.0, (k_ln_param_reduce<<<(E + 127) / 128, 128, 0, s>>>(pg, pb, nblk, E, dg, db)));
+  KOP(p, e, 0.0, (k_ln_param_reduce<<<(E + 31) / 32, dim3(32, 16), 0, s>>>(pg, pb, nblk, E, dg, db)));
 }
 
 void build_cdt(Engine& e) {
@@ -182,17 +182,16 @@ void build_cdt(Engine& e) {
     DevState* ds = e.ds;
     float* stat = e.stats;
     const int world = e.world;
-    if (world == 1) {
-      KOP(p, e, 0.0, (k_cdt_loss<<<1, 512, 0, s>>>(mh, ah, actions, costs, states, mask, B, T, a, o, wc, wsw, tent, lr,
-                                                   warm, grp, ds, dmh, dah, stat, 0, nullptr, 1)));
-    } else {   // masked means over the global batch: all-reduce the six partial sums between the two phases
-      double* sums = (double*)e.ws(16);
-      KOP(p, e, 0.0, (k_cdt_loss<<<1, 512, 0, s>>>(mh, ah, actions, costs, states, mask, B, T, a, o, wc, wsw, tent, lr,
-                                                   warm, grp, ds, dmh, dah, stat, 1, sums, world)));
-      emit_allreduce(e, p, (float*)sums, 6, /*f64=*/true);
-      KOP(p, e, 0.0, (k_cdt_loss<<<1, 512, 0, s>>>(mh, ah, actions, costs, states, mask, B, T, a, o, wc, wsw, tent, lr,
-                                                   warm, grp, ds, dmh, dah, stat, 2, sums, world)));
-    }
+    // three launches: partial sums on `nb` CTAs, a fold (+ all-reduce of the six totals under data parallelism: the masked
+    // means are over the global batch), gradients on `nb` CTAs.  (One CTA for everything took 0.5 ms at B = 2048.)
+    const int nb = std::max(1, std::min(148, (BT + 255) / 256));
+    double* sums = (double*)e.ws((size_t)2 * 6 * nb + 16);
+    KOP(p, e, 0.0, (k_cdt_loss<<<nb, 256, 0, s>>>(mh, ah, actions, costs, states, mask, B, T, a, o, wc, wsw, tent, lr,
+                                                  warm, grp, ds, dmh, dah, stat, 1, sums, world)));
+    KOP(p, e, 0.0, (k_cdt_fold<<<1, 32, 0, s>>>(sums, nb, ds)));
+    if (world > 1) emit_allreduce(e, p, (float*)sums, 6, /*f64=*/true);
+    KOP(p, e, 0.0, (k_cdt_loss<<<nb, 256, 0, s>>>(mh, ah, actions, costs, states, mask, B, T, a, o, wc, wsw, tent, lr,
+                                                  warm, grp, ds, dmh, dah, stat, 2, sums, world)));
   }
 
   // ---------------- backward
