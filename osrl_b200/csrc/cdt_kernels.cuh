@@ -212,27 +212,30 @@ static __global__ void k_attn_fwd(const float* __restrict__ qkv, const float* __
                                   int tok_per_step, float* __restrict__ out, float* __restrict__ lse,
                                   const float* __restrict__ pdrop) {
   extern __shared__ __align__(16) float sm[];
+  // gridDim.y head groups per batch element: HL heads (EL columns) per CTA -- smaller tiles and fewer threads per CTA
+  // let several CTAs share an SM (the kernels run at one 125-register, 137 KB CTA per SM otherwise)
   const int E = H * D, b = blockIdx.x, T = L / tok_per_step;
-  float* Ks = sm;              // [L][E]
-  float* Vs = sm + L * E;      // [L][E]
-  float* valid = sm + 2 * L * E;            // [L] key j attendable
-  float* Pd = valid + ((L + 3) & ~3);       // [H][L][L + 1] dropout multipliers of this batch element (pdrop only)
+  const int HL = H / gridDim.y, hg = blockIdx.y, EL = HL * D, c0 = hg * EL;
+  float* Ks = sm;              // [L][EL]
+  float* Vs = sm + L * EL;     // [L][EL]
+  float* valid = sm + 2 * L * EL;           // [L] key j attendable
+  float* Pd = valid + ((L + 3) & ~3);       // [HL][L][L + 1] dropout multipliers of this batch element (pdrop only)
   const float* base = qkv + (size_t)b * L * 3 * E;
-  for (int e4 = threadIdx.x; e4 < L * E / 4; e4 += blockDim.x) {
-    const int e = e4 * 4, j = e / E, c = e % E;
-    *reinterpret_cast<float4*>(Ks + e) = *reinterpret_cast<const float4*>(base + (size_t)j * 3 * E + E + c);
-    *reinterpret_cast<float4*>(Vs + e) = *reinterpret_cast<const float4*>(base + (size_t)j * 3 * E + 2 * E + c);
+  for (int e4 = threadIdx.x; e4 < L * EL / 4; e4 += blockDim.x) {
+    const int e = e4 * 4, j = e / EL, c = e % EL;
+    *reinterpret_cast<float4*>(Ks + e) = *reinterpret_cast<const float4*>(base + (size_t)j * 3 * E + E + c0 + c);
+    *reinterpret_cast<float4*>(Vs + e) = *reinterpret_cast<const float4*>(base + (size_t)j * 3 * E + 2 * E + c0 + c);
   }
-  // the key-padding mask and the dropout multipliers are read in every iteration of the inner loop: from global
-  // memory (one 4-byte load per lane, strided by L) they bound the kernel at one CTA per SM
+  // the key-padding mask and the dropout multipliers are read in every iteration of the inner loop: staged once
   for (int j = threadIdx.x; j < L; j += blockDim.x) valid[j] = mask[(size_t)b * T + j / tok_per_step];
-  if (pdrop) attn_stage_drop(pdrop + (size_t)b * H * L * L, H, L, Pd);
+  if (pdrop) attn_stage_drop(pdrop + ((size_t)b * H + (size_t)hg * HL) * L * L, HL, L, Pd);
   __syncthreads();
-  const int h = threadIdx.x / L, i = threadIdx.x % L;
-  if (h >= H) return;
+  const int h = threadIdx.x / L, i = threadIdx.x % L;   // h: head inside the group
+  if (h >= HL) return;
+  const int hh = hg * HL + h;
   float q[D], acc[D];
 #pragma unroll
-  for (int c = 0; c < D; ++c) { q[c] = base[(size_t)i * 3 * E + h * D + c]; acc[c] = 0.f; }
+  for (int c = 0; c < D; ++c) { q[c] = base[(size_t)i * 3 * E + hh * D + c]; acc[c] = 0.f; }
   const float scale = rsqrtf((float)D);
   const float* __restrict__ drow = pdrop ? Pd + (size_t)(h * L + i) * (L + 1) : nullptr;
   float m = -INFINITY, l = 0.f;
@@ -240,8 +243,8 @@ static __global__ void k_attn_fwd(const float* __restrict__ qkv, const float* __
     if (valid[j] <= 0.f) continue;
     float kj[D], vj[D];
     {
-      const float4* __restrict__ kp = reinterpret_cast<const float4*>(Ks + j * E + h * D);
-      const float4* __restrict__ vp = reinterpret_cast<const float4*>(Vs + j * E + h * D);
+      const float4* __restrict__ kp = reinterpret_cast<const float4*>(Ks + j * EL + h * D);
+      const float4* __restrict__ vp = reinterpret_cast<const float4*>(Vs + j * EL + h * D);
 #pragma unroll
       for (int q4 = 0; q4 < D / 4; ++q4) {
         const float4 a = kp[q4], v = vp[q4];
@@ -263,8 +266,8 @@ static __global__ void k_attn_fwd(const float* __restrict__ qkv, const float* __
   }
   const float inv = 1.f / l;
 #pragma unroll
-  for (int c = 0; c < D; ++c) out[((size_t)b * L + i) * E + h * D + c] = acc[c] * inv;
-  lse[((size_t)b * H + h) * L + i] = m + logf(l);
+  for (int c = 0; c < D; ++c) out[((size_t)b * L + i) * E + hh * D + c] = acc[c] * inv;
+  lse[((size_t)b * H + hh) * L + i] = m + logf(l);
 }
 
 // row r, head h of a [L][E] shared tile as D/4 float4 (16-byte shared loads: a quarter of the LDS instructions of
@@ -285,43 +288,45 @@ static __global__ void k_attn_bwd(const float* __restrict__ qkv, const float* __
                                   const float* __restrict__ pdrop) {
   extern __shared__ __align__(16) float sm[];
   const int E = H * D, b = blockIdx.x, T = L / tok_per_step;
+  const int HL = H / gridDim.y, hg = blockIdx.y, EL = HL * D, c0 = hg * EL;   // head group, see k_attn_fwd
   float* Qs = sm;
-  float* Ks = sm + L * E;
-  float* Vs = sm + 2 * L * E;
-  float* dOs = sm + 3 * L * E;
-  float* Ls = sm + 4 * L * E;      // [H*L] log-sum-exp
-  float* Ds = Ls + H * L;          // [H*L] rowsum(dO * O)
-  float* valid = Ds + H * L;                // [L] key j attendable
-  float* Pd = valid + ((L + 3) & ~3);       // [H][L][L + 1] dropout multipliers (pdrop only), see k_attn_fwd
+  float* Ks = sm + L * EL;
+  float* Vs = sm + 2 * L * EL;
+  float* dOs = sm + 3 * L * EL;
+  float* Ls = sm + 4 * L * EL;     // [HL*L] log-sum-exp
+  float* Ds = Ls + HL * L;         // [HL*L] rowsum(dO * O)
+  float* valid = Ds + HL * L;               // [L] key j attendable
+  float* Pd = valid + ((L + 3) & ~3);       // [HL][L][L + 1] dropout multipliers (pdrop only), see k_attn_fwd
   const float* base = qkv + (size_t)b * L * 3 * E;
   for (int j = threadIdx.x; j < L; j += blockDim.x) valid[j] = mask[(size_t)b * T + j / tok_per_step];
-  if (pdrop) attn_stage_drop(pdrop + (size_t)b * H * L * L, H, L, Pd);
-  for (int e4 = threadIdx.x; e4 < L * E / 4; e4 += blockDim.x) {   // 16-byte global loads / shared stores
-    const int e = e4 * 4, j = e / E, c = e % E;
-    *reinterpret_cast<float4*>(Qs + e) = *reinterpret_cast<const float4*>(base + (size_t)j * 3 * E + c);
-    *reinterpret_cast<float4*>(Ks + e) = *reinterpret_cast<const float4*>(base + (size_t)j * 3 * E + E + c);
-    *reinterpret_cast<float4*>(Vs + e) = *reinterpret_cast<const float4*>(base + (size_t)j * 3 * E + 2 * E + c);
-    *reinterpret_cast<float4*>(dOs + e) = *reinterpret_cast<const float4*>(dout + ((size_t)b * L + j) * E + c);
+  if (pdrop) attn_stage_drop(pdrop + ((size_t)b * H + (size_t)hg * HL) * L * L, HL, L, Pd);
+  for (int e4 = threadIdx.x; e4 < L * EL / 4; e4 += blockDim.x) {   // 16-byte global loads / shared stores
+    const int e = e4 * 4, j = e / EL, c = e % EL;
+    *reinterpret_cast<float4*>(Qs + e) = *reinterpret_cast<const float4*>(base + (size_t)j * 3 * E + c0 + c);
+    *reinterpret_cast<float4*>(Ks + e) = *reinterpret_cast<const float4*>(base + (size_t)j * 3 * E + E + c0 + c);
+    *reinterpret_cast<float4*>(Vs + e) = *reinterpret_cast<const float4*>(base + (size_t)j * 3 * E + 2 * E + c0 + c);
+    *reinterpret_cast<float4*>(dOs + e) = *reinterpret_cast<const float4*>(dout + ((size_t)b * L + j) * E + c0 + c);
   }
-  const int h = threadIdx.x / L, i = threadIdx.x % L;
-  const bool active = h < H;
+  const int h = threadIdx.x / L, i = threadIdx.x % L;   // h: head inside the group
+  const bool active = h < HL;
+  const int hh = hg * HL + h;
   const float scale = rsqrtf((float)D);
   if (active) {
     float d = 0.f;
 #pragma unroll
     for (int c = 0; c < D; ++c)
-      d += dout[((size_t)b * L + i) * E + h * D + c] * out[((size_t)b * L + i) * E + h * D + c];
+      d += dout[((size_t)b * L + i) * E + hh * D + c] * out[((size_t)b * L + i) * E + hh * D + c];
     Ds[h * L + i] = d;
-    Ls[h * L + i] = lse[((size_t)b * H + h) * L + i];
+    Ls[h * L + i] = lse[((size_t)b * H + hh) * L + i];
   }
   __syncthreads();
   float* dbase = dqkv + (size_t)b * L * 3 * E;
   if (active) {
     float qi[D], doi[D], ki[D], vi[D];
-    ld_row<D>(Qs, i, E, h, qi);
-    ld_row<D>(dOs, i, E, h, doi);
-    ld_row<D>(Ks, i, E, h, ki);
-    ld_row<D>(Vs, i, E, h, vi);
+    ld_row<D>(Qs, i, EL, h, qi);
+    ld_row<D>(dOs, i, EL, h, doi);
+    ld_row<D>(Ks, i, EL, h, ki);
+    ld_row<D>(Vs, i, EL, h, vi);
     // ---- dq for query row i
     float dq[D];
 #pragma unroll
@@ -332,8 +337,8 @@ static __global__ void k_attn_bwd(const float* __restrict__ qkv, const float* __
     for (int j = 0; j <= i; ++j) {
       if (valid[j] <= 0.f) continue;
       float kj[D], vj[D];
-      ld_row<D>(Ks, j, E, h, kj);
-      ld_row<D>(Vs, j, E, h, vj);
+      ld_row<D>(Ks, j, EL, h, kj);
+      ld_row<D>(Vs, j, EL, h, vj);
       float s = 0.f, dp = 0.f;
 #pragma unroll
       for (int c = 0; c < D; ++c) {
@@ -348,7 +353,7 @@ static __global__ void k_attn_bwd(const float* __restrict__ qkv, const float* __
     }
 #pragma unroll
     for (int c = 0; c < D; c += 4)
-      *reinterpret_cast<float4*>(dbase + (size_t)i * 3 * E + h * D + c) = make_float4(dq[c], dq[c + 1], dq[c + 2], dq[c + 3]);
+      *reinterpret_cast<float4*>(dbase + (size_t)i * 3 * E + hh * D + c) = make_float4(dq[c], dq[c + 1], dq[c + 2], dq[c + 3]);
     // ---- dk, dv for key row j = i
     const int j = i;
     float dk[D], dv[D];
@@ -362,8 +367,8 @@ static __global__ void k_attn_bwd(const float* __restrict__ qkv, const float* __
       for (int r = 0; r < L; ++r) {
         if (r < j) continue;
         float qr[D], dor[D];
-        ld_row<D>(Qs, r, E, h, qr);
-        ld_row<D>(dOs, r, E, h, dor);
+        ld_row<D>(Qs, r, EL, h, qr);
+        ld_row<D>(dOs, r, EL, h, dor);
         float s = 0.f, dp = 0.f;
 #pragma unroll
         for (int c = 0; c < D; ++c) {
@@ -383,8 +388,8 @@ static __global__ void k_attn_bwd(const float* __restrict__ qkv, const float* __
     }
 #pragma unroll
     for (int c = 0; c < D; c += 4) {
-      *reinterpret_cast<float4*>(dbase + (size_t)j * 3 * E + E + h * D + c) = make_float4(dk[c], dk[c + 1], dk[c + 2], dk[c + 3]);
-      *reinterpret_cast<float4*>(dbase + (size_t)j * 3 * E + 2 * E + h * D + c) = make_float4(dv[c], dv[c + 1], dv[c + 2], dv[c + 3]);
+      *reinterpret_cast<float4*>(dbase + (size_t)j * 3 * E + E + hh * D + c) = make_float4(dk[c], dk[c + 1], dk[c + 2], dk[c + 3]);
+      *reinterpret_cast<float4*>(dbase + (size_t)j * 3 * E + 2 * E + hh * D + c) = make_float4(dv[c], dv[c + 1], dv[c + 2], dv[c + 3]);
     }
   }
 }
