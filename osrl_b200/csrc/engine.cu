@@ -902,7 +902,14 @@ static void free_all(Engine* e) {
   for (auto& ps : e->par_streams)
     for (cudaStream_t x : ps.second) cudaStreamDestroy(x);
   for (cudaEvent_t ev : e->par_events) cudaEventDestroy(ev);
-  for (void* p : e->allocs) cudaFree(p);
+  for (void* p : e->allocs) {
+    // Exported over cudaIpc: a peer process may not have closed its mapping yet (engines are destroyed without a
+    // cross-rank barrier -- a collective in a destructor can deadlock on destruction order), and freeing memory that is
+    // still imported elsewhere is undefined.  The two exported blocks (gradient section, 21 KB of flags) stay allocated
+    // until the process exits.
+    if (e->peer_on && (p == (void*)e->G || p == (void*)e->dp_flags)) continue;
+    cudaFree(p);
+  }
   if (e->comm2 && nccl::CommDestroy) nccl::CommDestroy(e->comm2);
   if (e->comm && nccl::CommDestroy) nccl::CommDestroy(e->comm);
 }
