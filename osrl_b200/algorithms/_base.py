@@ -150,13 +150,17 @@ class EngineTrainer:
         self.model.train()
         return np.mean(rets) / self.reward_scale, np.mean(costs) / self.cost_scale, np.mean(lens)
 
+    # how rollout() calls model.act: BCQ-Lag `act(obs)` (bcql.py:331); CPQ / BEAR-Lag / COptiDICE roll out the
+    # DETERMINISTIC policy, `act(obs, True, True)` (cpq.py:338, bearl.py:437, coptidice.py:312)
+    act_args = ()
+
     @torch.no_grad()
     def rollout(self):
         """One episode with the current policy: (return, length, cost) in the trainer's scaled units."""
         obs, info = self.env.reset()
         ret, cost, n = 0.0, 0.0, 0
         for _ in range(self.model.episode_len):
-            act, _ = self.model.act(obs)
+            act, _ = self.model.act(obs, *self.act_args)
             obs, reward, terminated, truncated, info = self.env.step(act)
             ret += reward
             cost += info["cost"] * self.cost_scale

@@ -54,11 +54,14 @@ class CPQ(EngineModel):
     def act(self, obs, deterministic=False, with_logprob=False):
         dev = self.vae.d1.weight.device
         obs = torch.tensor(obs[None, ...], dtype=torch.float32, device=dev)
-        a, _ = self.actor(obs, deterministic, with_logprob)
-        return np.squeeze((a * self.max_action).data.cpu().numpy(), axis=0), None
+        a, logp = self.actor(obs, deterministic, with_logprob)
+        logp = np.squeeze(logp.data.cpu().numpy()) if logp is not None else None
+        return np.squeeze((a * self.max_action).data.cpu().numpy(), axis=0), logp
 
 
 class CPQTrainer(EngineTrainer):
+    act_args = (True, True)   # deterministic roll-outs (cpq.py rollout)
+
     def __init__(self, model: CPQ, env=None, logger=None, actor_lr: float = 1e-4, critic_lr: float = 1e-4,
                  alpha_lr: float = 1e-4, vae_lr: float = 1e-4, reward_scale: float = 1.0, cost_scale: float = 1.0,
                  device="cuda:0", **kw):
