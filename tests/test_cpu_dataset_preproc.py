@@ -124,3 +124,29 @@ def test_oracle_split_trajectories_is_the_reference(ref_dataset, cost_reverse):
     for w, g in zip(want, got):
         for k in ("observations", "actions", "rewards", "costs", "returns", "cost_returns"):
             assert w[k].dtype == g[k].dtype and np.array_equal(w[k], g[k]), k
+
+
+@pytest.mark.parametrize("state_init", [False, True])
+def test_transition_dataset_stream_is_the_reference(ref_dataset, state_init):
+    """TransitionDataset (dataset.py:790-847): done / is_init columns, the float32 scaling of rewards and costs, the
+    tuple layout and the index stream of __iter__ under the same numpy seed; get_dataset_states for COptiDICE."""
+    from osrl_b200.common.dataset import TransitionDataset
+    d = _data(seed=4, eps=12, T=9)
+    d["terminals"][20] = True
+    a = ref_dataset.TransitionDataset({k: v.copy() for k, v in d.items()}, 0.1, 3.0, state_init)
+    b = TransitionDataset({k: v.copy() for k, v in d.items()}, 0.1, 3.0, state_init)
+    for k in ("done",) + (("is_init",) if state_init else ()):
+        assert a.dataset[k].dtype == b.dataset[k].dtype and np.array_equal(a.dataset[k], b.dataset[k]), k
+    np.random.seed(2)
+    ia = iter(a)
+    want = [next(ia) for _ in range(25)]
+    np.random.seed(2)
+    ib = iter(b)
+    got = [next(ib) for _ in range(25)]
+    for w, g in zip(want, got):
+        assert len(w) == len(g) == (7 if state_init else 6)
+        for x, y in zip(w, g):
+            assert np.asarray(x).dtype == np.asarray(y).dtype and np.array_equal(x, y)
+    if state_init:
+        for x, y in zip(a.get_dataset_states(), b.get_dataset_states()):
+            assert np.array_equal(np.asarray(x), np.asarray(y))
