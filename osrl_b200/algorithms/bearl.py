@@ -74,8 +74,8 @@ class BEARL(EngineModel):
 class BEARLTrainer(EngineTrainer):
     act_args = (True, True)   # deterministic roll-outs (bearl.py rollout)
 
-    def __init__(self, model: BEARL, env=None, logger=None, actor_lr: float = 1e-4, critic_lr: float = 1e-4,
-                 alpha_lr: float = 1e-3, vae_lr: float = 1e-4, reward_scale: float = 1.0, cost_scale: float = 1.0,
+    def __init__(self, model: BEARL, env=None, logger=None, actor_lr: float = 1e-3, critic_lr: float = 1e-3,
+                 alpha_lr: float = 1e-3, vae_lr: float = 1e-3, reward_scale: float = 1.0, cost_scale: float = 1.0,
                  device="cuda:0", **kw):
         super().__init__(model, env, logger, reward_scale, cost_scale, device, **kw)
         self.model.setup_optimizers(actor_lr, critic_lr, vae_lr, alpha_lr)
