@@ -392,7 +392,13 @@ def main_coptidice():
     osrl = ref_shim.import_reference()
     cfg = oc.COptiDICEConfig(8, 2, 1.0, f_type="softchi", init_state_propotion=0.25, a_hidden_sizes=[32, 32],
                              c_hidden_sizes=[32, 32], num_nu=2, num_chi=2, actor_lr=1e-3, critic_lr=1e-3, scalar_lr=1e-3)
-    B, steps = 32, 4
+    run_coptidice_case(osrl, "coptidice_small", cfg, 32, 4)
+
+
+def run_coptidice_case(osrl, name, cfg, B, steps):
+    """oracle.coptidice == the unmodified reference over `steps` steps at configuration `cfg` (asserted), fixture
+    written to OUT/<name>.npz."""
+    from oracle import coptidice as oc
     rng = np.random.default_rng(21)
     obs_std = rng.uniform(0.5, 1.5, (1, cfg.state_dim)).astype(np.float32)
     act_std = rng.uniform(0.3, 0.8, (1, cfg.action_dim)).astype(np.float32)
@@ -438,7 +444,7 @@ def main_coptidice():
     perr = max(rel_err(orc.params[k], v) for k, v in ref.state_dict().items())
     serr = max(abs(float(ref.tau) - float(orc.params["tau"])), abs(float(ref.lmbda) - float(orc.params["lmbda"])))
     assert perr < 2e-5 and serr < 1e-6, (perr, serr)
-    print(f"[golden] coptidice_small: oracle == reference over {steps} steps (stat rel err {worst:.2e}, "
+    print(f"[golden] {name}: oracle == reference over {steps} steps (stat rel err {worst:.2e}, "
           f"param rel err {perr:.2e}, tau/lambda abs err {serr:.1e})")
     cfgd = dataclasses.asdict(cfg)
     out["meta"] = json.dumps({"algo": "coptidice", "cfg": cfgd, "B": B, "steps": steps, "keys": list(init.keys()),
@@ -450,7 +456,7 @@ def main_coptidice():
     for k, v in ref.state_dict().items():
         out["final/" + k] = v.numpy()
     out["final/tau"], out["final/lmbda"] = ref.tau.detach().numpy(), ref.lmbda.detach().numpy()
-    np.savez_compressed(os.path.join(OUT, "coptidice_small.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
 
 
 if __name__ == "__main__" and "coptidice" in sys.argv[1:]:

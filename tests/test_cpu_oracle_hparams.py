@@ -55,3 +55,55 @@ def test_oracle_equals_reference_off_the_defaults(osrl_ref, name, tmp_path, monk
     algo, cfg, B, steps = TWISTED[name]
     monkeypatch.setattr(make_golden, "OUT", str(tmp_path))     # the comparison is the point; the fixture is thrown away
     make_golden.run_case(osrl_ref, name, algo, cfg, B, steps, True)
+
+
+CDT_TWISTED = {
+    "cdt_t1": (dict(state_dim=6, action_dim=2, max_action=2.0, seq_len=6, episode_len=950, embedding_dim=48, num_layers=1,
+                    num_heads=3, init_temperature=0.3, learning_rate=2e-3, weight_decay=1e-2, betas=(0.8, 0.95),
+                    clip_grad=0.1, lr_warmup_steps=3, loss_cost_weight=0.5, loss_state_weight=0.3), 6, 4),
+    "cdt_t2": (dict(state_dim=4, action_dim=3, max_action=1.0, seq_len=4, episode_len=1200, embedding_dim=32, num_layers=2,
+                    num_heads=2, init_temperature=0.05, learning_rate=5e-4, weight_decay=0.0, betas=(0.9, 0.999),
+                    clip_grad=5.0, lr_warmup_steps=1, loss_cost_weight=0.0, loss_state_weight=1.0,
+                    attention_dropout=0.2, residual_dropout=0.1, embedding_dropout=0.05), 5, 3),
+}
+
+
+@pytest.mark.parametrize("name", list(CDT_TWISTED))
+def test_cdt_oracle_equals_reference_off_the_defaults(osrl_ref, name, tmp_path, monkeypatch):
+    """oracle/cdt.py against the unmodified CDT / CDTTrainer (run_cdt_case asserts stats and parameters): other window
+    length, width, head count, temperature, AdamW betas / decay, clip threshold on both sides of the gradient norm,
+    warm-up, both auxiliary loss weights, and replayed dropout at three different rates."""
+    from oracle import cdt as ocdt
+    from oracle import make_golden
+    kw, B, steps = CDT_TWISTED[name]
+    monkeypatch.setattr(make_golden, "OUT", str(tmp_path))
+    make_golden.run_cdt_case(osrl_ref, name, ocdt.CDTConfig(**kw), B, steps, True)
+
+
+def _cop(**kw):
+    from oracle import coptidice as oc
+    return oc.COptiDICEConfig(**kw)
+
+
+COP_TWISTED = {
+    "cop_chi2": (dict(state_dim=7, action_dim=3, max_action=1.5, f_type="chi2", init_state_propotion=0.4,
+                      a_hidden_sizes=[24, 40], c_hidden_sizes=[40, 24], gamma=0.95, alpha=0.8, cost_ub_epsilon=0.05,
+                      num_nu=3, num_chi=1, cost_limit=4, episode_len=120, actor_lr=3e-4, critic_lr=2e-3, scalar_lr=5e-3), 20, 3),
+    "cop_kl": (dict(state_dim=6, action_dim=2, max_action=1.0, f_type="kl", init_state_propotion=1.0,
+                    a_hidden_sizes=[32, 32], c_hidden_sizes=[32, 32], gamma=0.99, alpha=0.2, cost_ub_epsilon=0.0,
+                    num_nu=1, num_chi=3, cost_limit=25, episode_len=500, actor_lr=1e-3, critic_lr=5e-4, scalar_lr=1e-2), 16, 3),
+    "cop_softchi": (dict(state_dim=5, action_dim=2, max_action=2.0, f_type="softchi", init_state_propotion=0.1,
+                         a_hidden_sizes=[16, 48], c_hidden_sizes=[48, 16], gamma=0.9, alpha=1.5, cost_ub_epsilon=0.2,
+                         num_nu=2, num_chi=2, cost_limit=1, episode_len=40, actor_lr=2e-3, critic_lr=2e-3, scalar_lr=2e-3), 24, 4),
+}
+
+
+@pytest.mark.parametrize("name", list(COP_TWISTED))
+def test_coptidice_oracle_equals_reference_off_the_defaults(osrl_ref, name, tmp_path, monkeypatch):
+    """oracle/coptidice.py against the unmodified COptiDICE.update (run_coptidice_case asserts stats, parameters, tau
+    and lambda): all three f-divergences (the committed fixture is softchi only), ensemble sizes 1..3, discount, alpha,
+    the cost upper-bound epsilon incl. 0, initial-state proportion, cost limits and the three learning rates."""
+    from oracle import make_golden
+    kw, B, steps = COP_TWISTED[name]
+    monkeypatch.setattr(make_golden, "OUT", str(tmp_path))
+    make_golden.run_coptidice_case(osrl_ref, name, _cop(**kw), B, steps)
