@@ -20,3 +20,17 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "BCQ-Lag" in d["config"]["workload"]
+
+
+def test_own_arm_fails_loudly_without_a_gpu():
+    """The product arm must not fall back to anything on a machine without CUDA: no JSON line, non-zero exit."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("GPU present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "3", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode != 0 and r.stdout.strip() == "", (r.returncode, r.stdout[:200])
